@@ -1,0 +1,194 @@
+/* mpm_b200.h -- C ABI of libmpm_b200.so, the sm_100a MLS-MPM substep engine
+ * that sits behind taichi_elements' Python `MPMSolver` class.
+ *
+ * The reference (taichi-dev/taichi_elements) has no FFI of its own: its hot
+ * path is a set of @ti.kernel methods JIT-compiled by Taichi.  Each entry point
+ * below names the reference kernel/method (file:line under /root/reference) it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer would add to
+ * engine/mpm_solver.py.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints, doubles; no torch/C++ types cross the ABI.
+ *   - every function returns int: 0 = MPM_OK, >0 = a recoverable condition the
+ *     host must act on (grow a buffer and call again), <0 = failure;
+ *     mpm_last_error(ctx) gives the text.  No exception crosses the ABI.
+ *   - the library never allocates or frees device memory: the host (PyTorch)
+ *     owns the particle state buffers and one workspace buffer and binds them
+ *     with mpm_bind().  Pointers named *_dev are device pointers, *_host host.
+ *   - one CUDA stream per call (cudaStream_t passed as void*, NULL = default);
+ *     a ctx is not re-entrant; any host thread may call (the device is set per
+ *     call), matching Blender's use of MPMSolver from a worker thread
+ *     (blender/operators.py:403-405).
+ *
+ * Particle state layout (device, 32-bit words, structure of arrays):
+ *   state[set][field][capacity], set in {0,1} (ping-pong), fields in order
+ *     x[dim] v[dim] F[dim*dim] C[dim*dim] Jp material color id emitter
+ *   (engine/mpm_solver.py:101-136, 263-273).  `id` is the insertion index:
+ *   particles are physically kept in grid-block order, `id` restores the
+ *   reference's append order on read-back.
+ */
+#ifndef MPM_B200_H
+#define MPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPM_OK 0
+#define MPM_E_BLOCK_CAPACITY 1 /* workspace too small for the active blocks: query mpm_get_stats, re-bind, retry */
+#define MPM_E_KEY_BITS 2       /* particle bounding box needs > 32 key bits */
+#define MPM_E_INVALID (-1)
+#define MPM_E_CUDA (-2)
+#define MPM_E_UNBOUND (-3)
+
+#define MPM_ABI_VERSION 1
+
+typedef struct mpm_ctx mpm_ctx;
+
+/* Constants of MPMSolver.__init__ (engine/mpm_solver.py:67-99, 143-159, 198-210).
+ * Doubles are the Python floats; the library rounds them to f32 exactly where
+ * Taichi would (kernel-captured constants). */
+typedef struct mpm_params {
+  int32_t dim;             /* 2 or 3 (:76-77) */
+  int32_t res[3];
+  int32_t grid_size;       /* 4096, doubled while <= 2*max(res) when unbounded (:74,143-148) */
+  int32_t leaf;            /* leaf_block_size: 16 (2D) / 4 (3D) (:155-159) */
+  int32_t padding;         /* :52 */
+  int32_t support_plasticity;
+  int32_t device;          /* CUDA device ordinal */
+  int32_t reserved;
+  double dx, inv_dx;       /* :82-83 */
+  double p_vol, p_mass;    /* :85-87 */
+  double mu_0, lambda_0;   /* :203-205 */
+  double alpha;            /* :208-210 */
+  double water_density;    /* :61 */
+} mpm_params;
+
+/* One entry of MPMSolver.grid_postprocess, applied in order after
+ * normalisation+gravity (:794-795). */
+#define MPM_COLLIDER_BBOX 0   /* grid_bounding_box (:600-616); a[0] = unbounded flag */
+#define MPM_COLLIDER_SPHERE 1 /* add_sphere_collider (:618-642): a = center, b[0] = radius */
+#define MPM_COLLIDER_PLANE 2  /* add_surface_collider (:647-687): a = point, b = unit normal */
+typedef struct mpm_collider {
+  int32_t kind;
+  int32_t surface; /* 0 sticky, 1 slip, 2 separate (:29-42) */
+  double a[3];
+  double b[3];
+  double friction;
+} mpm_collider;
+
+/* Read-back of the per-substep device status block. */
+typedef struct mpm_stats {
+  int64_t n_particles;
+  int32_t n_particle_blocks; /* leaf blocks holding >= 1 particle base (build_pid lists, :344-361) */
+  int32_t n_grid_blocks;     /* leaf blocks activated by P2G writes (:582-584) */
+  int32_t max_blocks;        /* bound capacity */
+  int32_t key_bits;
+  int32_t bbox_min[3], bbox_max[3]; /* particle base-cell bounding box (global signed cell index) */
+  float max_velocity;        /* compute_max_velocity (:726-735): max over the substeps of the last call */
+  int32_t launches;          /* kernels launched by the last mpm_substep(s) call */
+  int32_t substeps_done;     /* substeps completed by the last mpm_substep(s) call */
+  int32_t reserved;
+  float ms_sort, ms_p2g, ms_grid, ms_g2p; /* filled when profiling is enabled */
+} mpm_stats;
+
+int mpm_abi_version(void);
+
+/* words per particle for `dim` (2*dim + 2*dim*dim + 5) */
+int mpm_state_fields(int dim);
+/* bytes the workspace must have for `capacity` particles and `max_blocks` leaf blocks */
+size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks);
+
+/* MPMSolver.__init__ (engine/mpm_solver.py:44-310) */
+int mpm_create(const mpm_params* params, mpm_ctx** out);
+int mpm_destroy(mpm_ctx* ctx);
+const char* mpm_last_error(mpm_ctx* ctx);
+
+/* Bind host-owned device memory.  state0/state1: [fields][capacity] words each. */
+int mpm_bind(mpm_ctx* ctx, void* state0_dev, void* state1_dev, int64_t capacity, void* workspace_dev,
+             size_t workspace_bytes, int32_t max_blocks);
+/* Which set holds the live state, and how many particles (n_particles[None], :81). */
+int mpm_get_state(mpm_ctx* ctx, int32_t* current_set, int64_t* n_particles);
+int mpm_set_state(mpm_ctx* ctx, int32_t current_set, int64_t n_particles);
+
+/* set_gravity (:316-319) */
+int mpm_set_gravity(mpm_ctx* ctx, const double* g);
+/* add_sphere_collider / add_surface_collider / add_bounding_box / clear_grid_postprocess
+ * (:618-692): the whole ordered table is replaced. */
+int mpm_set_colliders(mpm_ctx* ctx, const mpm_collider* table, int32_t n);
+
+/* seed_from_external_array + seed_particle (:823-838, 1081-1095): append n
+ * particles whose positions are x_dev[n][dim] (f32, device).  velocity may be
+ * NULL (zero). */
+int mpm_seed_positions(mpm_ctx* ctx, const float* x_dev, int64_t n, int32_t material, int32_t color,
+                       const double* velocity, int32_t emitter, void* stream);
+/* seed (:840-850): n particles uniform in lower + u*size, u from the
+ * counter-based generator documented in DESIGN.md (seed, particle id, axis). */
+int mpm_seed_cube(mpm_ctx* ctx, int64_t n, const double* lower, const double* size, int32_t material,
+                  int32_t color, const double* velocity, int32_t emitter, uint64_t seed, void* stream);
+/* seed_ellipsoid + random_point_in_unit_sphere (:959-978): rejection sampling. */
+int mpm_seed_ellipsoid(mpm_ctx* ctx, int64_t n, const double* center, const double* radius,
+                       int32_t material, int32_t color, const double* velocity, int32_t emitter,
+                       uint64_t seed, void* stream);
+/* recover_from_external_array (:1106-1126): positions, velocities, per-particle material/color */
+int mpm_seed_restart(mpm_ctx* ctx, const float* x_dev, const float* v_dev, const int32_t* material_dev,
+                     const int32_t* color_dev, int64_t n, void* stream);
+
+/* One substep of step() (:789-799): deactivate_all, build_pid, p2g,
+ * grid_normalization_and_gravity, grid_postprocess[*], g2p, compute_max_velocity.
+ * On MPM_OK the live set has flipped; on a recoverable code nothing changed. */
+int mpm_substep(mpm_ctx* ctx, double dt, double t, void* stream);
+/* n substeps back to back with one host synchronisation at the end */
+int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t n, void* stream);
+int mpm_get_stats(mpm_ctx* ctx, mpm_stats* out);
+int mpm_set_profiling(mpm_ctx* ctx, int32_t enabled);
+
+/* copy_dynamic(_nd) / copy_ranged(_nd) (:1146-1170): particles [begin,end) of
+ * one state word (field index per the layout above) in insertion order, to
+ * host memory (4 bytes per particle). */
+int mpm_download(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_host, void* stream);
+/* same, device destination */
+int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream);
+
+
+/* ---- mesh seeding (setup path of add_mesh, engine/mpm_solver.py:1049-1079) ---- */
+/* Voxelizer.voxelize_triangles (engine/voxelizer.py:46-109): signed winding
+ * count per voxel of the super-sampled grid, rasterised in f64.  `res` is the
+ * super-sampled resolution, `dx` the voxel size; `voxels_dev` is a dense,
+ * zero-initialised int32 box [box_lo, box_hi) (row-major x,y,z) that must
+ * cover every pixel column the triangles touch. */
+int mpm_voxelize(int32_t device, const double* tris_dev, int64_t ntri, const int32_t* res, double dx,
+                 int32_t padding, const int32_t* box_lo, const int32_t* box_hi, int32_t* voxels_dev, void* stream);
+/* seed_from_voxels (engine/mpm_solver.py:1017-1047) in two passes over the same
+ * box: pass 0 writes the particle count of every voxel to counts_dev; pass 1
+ * writes positions [n][3] (f32) at offsets_dev (exclusive prefix sum of the
+ * counts, int64).  cell = dx / super_sample. */
+int mpm_voxel_sample(int32_t device, const int32_t* voxels_dev, const int32_t* res, const int32_t* box_lo,
+                     const int32_t* box_hi, int32_t sample_density, int32_t super_sample, double cell,
+                     const double* translation, int32_t grid_size, int32_t padding, uint64_t seed, int32_t pass,
+                     int32_t* counts_dev, const int64_t* offsets_dev, float* x_out_dev, void* stream);
+
+/* ---- parity/debug getters (tests only; not on the hot path) ---- */
+/* build_pid result: per particle (insertion order) the leaf-block coordinate
+ * (base - offset) // leaf, int32 [n][dim] to host. */
+int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream);
+/* Structure of the LAST substep: particle blocks (coords [npb][dim], counts[npb])
+ * and grid (active) blocks (coords [ngb][dim]); arrays may be NULL to query sizes. */
+int mpm_debug_blocks(mpm_ctx* ctx, int32_t* pb_coords_host, int32_t* pb_counts_host, int32_t* npb,
+                     int32_t* gb_coords_host, int32_t* ngb);
+/* Grid of the LAST substep after the grid op: for every cell of every grid
+ * block, global signed cell index [ncell][dim] and (v[dim], m) as [ncell][4]
+ * floats (2D: vx, vy, m, 0). */
+int mpm_debug_grid(mpm_ctx* ctx, int32_t* cell_host, float* vm_host, int64_t max_cells, int64_t* ncell);
+/* Device SVD / constitutive update on host arrays (round trip through the GPU). */
+int mpm_debug_particle_update(mpm_ctx* ctx, double dt, int64_t n, const int32_t* material_host,
+                              float* F_host, const float* C_host, float* Jp_host, float* affine_host,
+                              float* mass_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPM_B200_H */

@@ -1,0 +1,699 @@
+// libmpm_b200.so -- host side of the C ABI declared in include/mpm_b200.h.
+// Orchestrates the per-substep kernel sequence on one CUDA stream; owns no
+// device memory (state and workspace are bound by the caller).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpm_b200.h"
+#include "mpm_kernels.cuh"
+
+using namespace mpm;
+
+struct mpm_ctx {
+  mpm_params P;
+  Consts K;
+  int dim = 0, nf = 0, cells = 0, no = 0, cb = 0, log_leaf = 0;
+  uint32_t* state[2] = {nullptr, nullptr};
+  size_t cap = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int max_blocks = 0;
+  // carved workspace
+  Status* d_status = nullptr;
+  ColliderTable* d_ct = nullptr;
+  uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *stage = nullptr;
+  void* cub_temp = nullptr;
+  size_t cub_bytes = 0;
+  int* pb_start = nullptr;
+  uint32_t* pb_mask = nullptr;
+  int* pb_nbr = nullptr;
+  uint32_t *cand_a = nullptr, *cand_b = nullptr, *gb_key = nullptr;
+  float4* grid = nullptr;
+  Status* h_status = nullptr;   // pinned
+  int cur = 0;
+  int64_t n = 0;
+  bool bbox_valid = false;
+  int bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  KeyLayout L{};
+  bool layout_valid = false;
+  // structure of the last completed substep (debug getters)
+  bool last_valid = false;
+  const uint32_t* last_keys = nullptr;
+  KeyLayout lastL{};
+  Status last{};
+  ColliderTable h_ct{};
+  bool ct_dirty = true;
+  Grav grav{};
+  GridCfg gcfg{};
+  int sm_count = 148;
+  int grid_p2g = 148, grid_g2p = 148;
+  int launches = 0;
+  int done_last = 0;
+  bool profiling = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float ms[4] = {0, 0, 0, 0};
+  std::string err;
+};
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return MPM_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+static int fail(mpm_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static inline int gs_blocks(int64_t n, int threads, int sm) {
+  int64_t b = (n + threads - 1) / threads;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm * 16));
+}
+
+// ------------------------------------------------------------------ sizes
+struct Carve {
+  size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
+      off_cand_b, off_gb_key, off_grid, total, cub_bytes;
+};
+
+static size_t cub_temp_bytes(int64_t cap, int64_t ncand) {
+  size_t best = 0, b = 0;
+  cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, b, k, v, (int)std::max<int64_t>(cap, 1));
+  best = std::max(best, b);
+  cub::DeviceRadixSort::SortKeys(nullptr, b, k, (int)std::max<int64_t>(ncand, 1));
+  best = std::max(best, b);
+  thrust::counting_iterator<int> it(0);
+  cub::DeviceSelect::If(nullptr, b, it, BoundedOut{nullptr, 0}, (int*)nullptr, (int)std::max<int64_t>(cap, 1),
+                        HeadOp{nullptr, 0});
+  best = std::max(best, b);
+  cub::DeviceSelect::Unique(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr,
+                            (int)std::max<int64_t>(ncand, 1));
+  best = std::max(best, b);
+  return best + 256;
+}
+
+static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
+  const int no = dim == 3 ? 8 : 4, cells = dim == 3 ? 64 : 256;
+  Carve c{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  c.off_status = take(sizeof(Status));
+  c.off_ct = take(sizeof(ColliderTable));
+  c.off_scratch = take((size_t)5 * cap * 4);
+  c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks);
+  c.off_cub = take(c.cub_bytes);
+  c.off_pb_start = take((size_t)(max_blocks + 2) * 4);
+  c.off_pb_mask = take((size_t)max_blocks * 4);
+  c.off_pb_nbr = take((size_t)max_blocks * no * 4);
+  c.off_cand_a = take((size_t)max_blocks * no * 4);
+  c.off_cand_b = take((size_t)max_blocks * no * 4);
+  c.off_gb_key = take(((size_t)max_blocks * no + 1) * 4);
+  c.off_grid = take((size_t)max_blocks * cells * sizeof(float4));
+  c.total = o;
+  return c;
+}
+
+extern "C" int mpm_abi_version(void) { return MPM_ABI_VERSION; }
+extern "C" int mpm_state_fields(int dim) { return dim == 3 ? Geo<3>::NF : (dim == 2 ? Geo<2>::NF : -1); }
+extern "C" size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks) {
+  if ((dim != 2 && dim != 3) || capacity < 0 || max_blocks < 1) return 0;
+  return carve(dim, capacity, max_blocks).total;
+}
+
+// ------------------------------------------------------------------ lifecycle
+extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
+  if (!p || !out) return MPM_E_INVALID;
+  if (p->dim != 2 && p->dim != 3) return MPM_E_INVALID;          // engine/mpm_solver.py:76-77
+  if (p->leaf != (p->dim == 3 ? 4 : 16)) return MPM_E_INVALID;
+  mpm_ctx* ctx = new mpm_ctx();
+  ctx->P = *p;
+  ctx->dim = p->dim;
+  ctx->nf = mpm_state_fields(p->dim);
+  ctx->cells = p->dim == 3 ? 64 : 256;
+  ctx->no = p->dim == 3 ? 8 : 4;
+  ctx->cb = p->dim == 3 ? 6 : 8;
+  ctx->log_leaf = p->dim == 3 ? 2 : 4;
+  Consts& K = ctx->K;
+  K.dx = (float)p->dx; K.inv_dx = (float)p->inv_dx;
+  K.p_vol = (float)p->p_vol; K.p_mass = (float)p->p_mass;
+  K.mu_0 = (float)p->mu_0; K.lambda_0 = (float)p->lambda_0;
+  K.alpha = (float)p->alpha;
+  K.sand_coef = (float)((p->dim * p->lambda_0 + 2 * p->mu_0) / (2 * p->mu_0));
+  K.water_density = (float)p->water_density;
+  K.inv_dx2 = (float)(p->inv_dx * p->inv_dx);
+  K.four_inv_dx = (float)(4 * p->inv_dx);
+  K.support_plasticity = p->support_plasticity;
+  for (int d = 0; d < 3; ++d) ctx->gcfg.res[d] = p->res[d];
+  ctx->gcfg.padding = p->padding;
+  ctx->gcfg.grid_size = p->grid_size;
+  ctx->grav.g[0] = 0.f; ctx->grav.g[1] = -9.8f; ctx->grav.g[2] = 0.f;   // :283, 296
+  ctx->h_ct.n = 0;
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_status, sizeof(Status));
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, p->device);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mpm_create: %s\n", cudaGetErrorString(e));
+    delete ctx;
+    return MPM_E_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  int occ = 1;
+  if (p->dim == 3) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g<3>, P2G_THREADS, 0);
+    ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<3>, G2P_THREADS, 0);
+    ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g<2>, P2G_THREADS, 0);
+    ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<2>, G2P_THREADS, 0);
+    ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
+  }
+  for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
+  *out = ctx;
+  return MPM_OK;
+}
+
+extern "C" int mpm_destroy(mpm_ctx* ctx) {
+  if (!ctx) return MPM_E_INVALID;
+  cudaSetDevice(ctx->P.device);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  for (int i = 0; i < 5; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  delete ctx;
+  return MPM_OK;
+}
+
+extern "C" const char* mpm_last_error(mpm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void* ws, size_t ws_bytes,
+                        int32_t max_blocks) {
+  if (!ctx || !s0 || !s1 || !ws || capacity < 1 || max_blocks < 1) return fail(ctx, MPM_E_INVALID, "mpm_bind: bad argument");
+  if (capacity % 64 != 0) return fail(ctx, MPM_E_INVALID, "mpm_bind: capacity must be a multiple of 64");
+  if (capacity >= (int64_t)1 << 31) return fail(ctx, MPM_E_INVALID, "mpm_bind: capacity must be < 2^31");
+  Carve c = carve(ctx->dim, capacity, max_blocks);
+  if (ws_bytes < c.total) return fail(ctx, MPM_E_INVALID, "mpm_bind: workspace too small");
+  CK(cudaSetDevice(ctx->P.device));
+  ctx->state[0] = (uint32_t*)s0;
+  ctx->state[1] = (uint32_t*)s1;
+  ctx->cap = (size_t)capacity;
+  ctx->ws = ws;
+  ctx->ws_bytes = ws_bytes;
+  ctx->max_blocks = max_blocks;
+  char* b = (char*)ws;
+  ctx->d_status = (Status*)(b + c.off_status);
+  ctx->d_ct = (ColliderTable*)(b + c.off_ct);
+  uint32_t* sc = (uint32_t*)(b + c.off_scratch);
+  ctx->keys_a = sc; ctx->keys_b = sc + capacity; ctx->vals_a = sc + 2 * capacity;
+  ctx->vals_b = sc + 3 * capacity; ctx->stage = sc + 4 * capacity;
+  ctx->cub_temp = b + c.off_cub;
+  ctx->cub_bytes = c.cub_bytes;
+  ctx->pb_start = (int*)(b + c.off_pb_start);
+  ctx->pb_mask = (uint32_t*)(b + c.off_pb_mask);
+  ctx->pb_nbr = (int*)(b + c.off_pb_nbr);
+  ctx->cand_a = (uint32_t*)(b + c.off_cand_a);
+  ctx->cand_b = (uint32_t*)(b + c.off_cand_b);
+  ctx->gb_key = (uint32_t*)(b + c.off_gb_key);
+  ctx->grid = (float4*)(b + c.off_grid);
+  ctx->ct_dirty = true;
+  ctx->last_valid = false;
+  return MPM_OK;
+}
+
+extern "C" int mpm_get_state(mpm_ctx* ctx, int32_t* cur, int64_t* n) {
+  if (!ctx) return MPM_E_INVALID;
+  if (cur) *cur = ctx->cur;
+  if (n) *n = ctx->n;
+  return MPM_OK;
+}
+extern "C" int mpm_set_state(mpm_ctx* ctx, int32_t cur, int64_t n) {
+  if (!ctx || (cur != 0 && cur != 1) || n < 0 || (size_t)n > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_set_state: bad argument");
+  ctx->cur = cur;
+  ctx->n = n;
+  ctx->bbox_valid = false;
+  ctx->last_valid = false;
+  return MPM_OK;
+}
+
+extern "C" int mpm_set_gravity(mpm_ctx* ctx, const double* g) {
+  if (!ctx || !g) return MPM_E_INVALID;
+  for (int d = 0; d < 3; ++d) ctx->grav.g[d] = d < ctx->dim ? (float)g[d] : 0.f;
+  return MPM_OK;
+}
+
+extern "C" int mpm_set_colliders(mpm_ctx* ctx, const mpm_collider* t, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && !t)) return MPM_E_INVALID;
+  if (n > MAX_COLLIDERS) return fail(ctx, MPM_E_INVALID, "too many colliders (max 64)");
+  ctx->h_ct.n = n;
+  for (int i = 0; i < n; ++i) {
+    ColliderDev& c = ctx->h_ct.c[i];
+    c.kind = t[i].kind;
+    c.surface = t[i].surface;
+    for (int d = 0; d < 3; ++d) { c.a[d] = (float)t[i].a[d]; c.b[d] = (float)t[i].b[d]; }
+    c.r2 = (float)(t[i].b[0] * t[i].b[0]);   // radius * radius evaluated in double, rounded once (:625)
+    c.friction = (float)t[i].friction;
+    c.unbounded = t[i].kind == MPM_COLLIDER_BBOX ? (t[i].a[0] != 0.0) : 0;
+  }
+  ctx->ct_dirty = true;
+  return MPM_OK;
+}
+
+// ------------------------------------------------------------------ seeding
+static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  if (a.n < 0 || (size_t)(ctx->n + a.n) > ctx->cap) return fail(ctx, MPM_E_INVALID, "seed: capacity exceeded");
+  if (a.n == 0) return MPM_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  a.state = ctx->state[ctx->cur];
+  a.cap = ctx->cap;
+  a.n0 = ctx->n;
+  int blocks = gs_blocks(a.n, 256, ctx->sm_count);
+  if (ctx->dim == 3) k_seed<3><<<blocks, 256, 0, s>>>(a); else k_seed<2><<<blocks, 256, 0, s>>>(a);
+  CK(cudaGetLastError());
+  ctx->n += a.n;
+  ctx->bbox_valid = false;
+  ctx->last_valid = false;
+  return MPM_OK;
+}
+static void fill3(float* dst, const double* src, int dim, float dflt) {
+  for (int d = 0; d < 3; ++d) dst[d] = (src && d < dim) ? (float)src[d] : dflt;
+}
+
+extern "C" int mpm_seed_positions(mpm_ctx* ctx, const float* x_dev, int64_t n, int32_t material, int32_t color,
+                                  const double* velocity, int32_t emitter, void* stream) {
+  if (!ctx || (n > 0 && !x_dev)) return MPM_E_INVALID;
+  SeedArgs a{};
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.x = x_dev; a.mode = 0;
+  fill3(a.vel, velocity, ctx->dim, 0.f);
+  return seed_common(ctx, a, stream);
+}
+extern "C" int mpm_seed_cube(mpm_ctx* ctx, int64_t n, const double* lower, const double* size, int32_t material,
+                             int32_t color, const double* velocity, int32_t emitter, uint64_t seed, void* stream) {
+  if (!ctx || !lower || !size) return MPM_E_INVALID;
+  SeedArgs a{};
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 1; a.seed = seed;
+  fill3(a.vel, velocity, ctx->dim, 0.f);
+  fill3(a.a, lower, ctx->dim, 0.f);
+  fill3(a.b, size, ctx->dim, 0.f);
+  return seed_common(ctx, a, stream);
+}
+extern "C" int mpm_seed_ellipsoid(mpm_ctx* ctx, int64_t n, const double* center, const double* radius,
+                                  int32_t material, int32_t color, const double* velocity, int32_t emitter,
+                                  uint64_t seed, void* stream) {
+  if (!ctx || !center || !radius) return MPM_E_INVALID;
+  SeedArgs a{};
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 2; a.seed = seed;
+  fill3(a.vel, velocity, ctx->dim, 0.f);
+  fill3(a.a, center, ctx->dim, 0.f);
+  fill3(a.b, radius, ctx->dim, 0.f);
+  return seed_common(ctx, a, stream);
+}
+extern "C" int mpm_seed_restart(mpm_ctx* ctx, const float* x_dev, const float* v_dev, const int32_t* m_dev,
+                                const int32_t* c_dev, int64_t n, void* stream) {
+  if (!ctx || (n > 0 && (!x_dev || !v_dev || !m_dev || !c_dev))) return MPM_E_INVALID;
+  SeedArgs a{};
+  a.n = n; a.x = x_dev; a.v = v_dev; a.mats = m_dev; a.colors = c_dev; a.mode = 3;
+  return seed_common(ctx, a, stream);
+}
+
+// ------------------------------------------------------------------ substep
+static int upload_colliders(mpm_ctx* ctx, cudaStream_t s) {
+  if (!ctx->ct_dirty) return MPM_OK;
+  CK(cudaMemcpyAsync(ctx->d_ct, &ctx->h_ct, sizeof(ColliderTable), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));   // h_ct is pageable host memory owned by ctx
+  ctx->ct_dirty = false;
+  return MPM_OK;
+}
+
+static int refresh_bbox(mpm_ctx* ctx, cudaStream_t s) {
+  if (ctx->bbox_valid) return MPM_OK;
+  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+  k_reset<<<1, 1, 0, s>>>(ctx->d_status);
+  int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
+  if (ctx->dim == 3) k_bbox<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status);
+  else k_bbox<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = ctx->h_status->bb_min[d]; ctx->bb_max[d] = ctx->h_status->bb_max[d]; }
+  ctx->bbox_valid = true;
+  return MPM_OK;
+}
+
+// Keep a sticky block-aligned box around the particles so the key layout (and
+// the number of radix passes) only changes when particles approach its faces.
+static int update_layout(mpm_ctx* ctx) {
+  const int half = ctx->P.grid_size / 2, ll = ctx->log_leaf;
+  const int MARGIN = 2;
+  bool keep = ctx->layout_valid;
+  int bmin[3], bmax[3];
+  for (int d = 0; d < ctx->dim; ++d) {
+    bmin[d] = (ctx->bb_min[d] + half) >> ll;
+    bmax[d] = (ctx->bb_max[d] + half) >> ll;
+    if (keep && !(bmin[d] >= ctx->L.ob[d] + 1 && bmax[d] <= ctx->L.ob[d] + ctx->L.eb[d] - 3)) keep = false;
+  }
+  if (!keep) {
+    KeyLayout L{};
+    L.half = half;
+    double prod = 1.0;
+    for (int d = 0; d < 3; ++d) { L.ob[d] = 0; L.eb[d] = 1; }
+    for (int d = 0; d < ctx->dim; ++d) {
+      L.ob[d] = bmin[d] - MARGIN;
+      L.eb[d] = (bmax[d] + MARGIN + 1) - L.ob[d] + 1;
+      prod *= (double)L.eb[d];
+    }
+    int bits = 0;
+    while (bits < 40 && (double)(1ull << bits) < prod) ++bits;
+    L.key_bits = bits + ctx->cb;
+    if (L.key_bits > 32) {
+      ctx->layout_valid = false;
+      return fail(ctx, MPM_E_KEY_BITS, "particle bounding box needs more than 32 key bits (diverged simulation?)");
+    }
+    ctx->L = L;
+    ctx->layout_valid = true;
+  }
+  return MPM_OK;
+}
+
+template <int D>
+static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, bool prof) {
+  using G = Geo<D>;
+  const int n = (int)ctx->n;
+  const int sm = ctx->sm_count;
+  Status* st = ctx->d_status;
+  const uint32_t* src = ctx->state[cur];
+  uint32_t* dst = ctx->state[cur ^ 1];
+  if (prof) cudaEventRecord(ctx->ev[0], s);
+  k_reset<<<1, 1, 0, s>>>(st);
+  k_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->vals_a, st);
+  cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
+  size_t tb = ctx->cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, n, 0, ctx->L.key_bits, s));
+  const uint32_t* keys = dk.Current();
+  const uint32_t* perm = dv.Current();
+  tb = ctx->cub_bytes;
+  thrust::counting_iterator<int> it(0);
+  CK(cub::DeviceSelect::If(ctx->cub_temp, tb, it, BoundedOut{ctx->pb_start, ctx->max_blocks + 1}, &st->npb, n,
+                           HeadOp{keys, G::CB}, s));
+  k_pb_finalize<<<1, 1, 0, s>>>(st, ctx->pb_start, n, ctx->max_blocks);
+  k_pb_masks<D><<<gs_blocks((int64_t)ctx->max_blocks * 32, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->L, ctx->max_blocks,
+                                                                              ctx->pb_mask, ctx->cand_a, st);
+  const int ncand = ctx->max_blocks * G::NO;
+  cub::DoubleBuffer<uint32_t> dc(ctx->cand_a, ctx->cand_b);
+  tb = ctx->cub_bytes;
+  CK(cub::DeviceRadixSort::SortKeys(ctx->cub_temp, tb, dc, ncand, 0, 32, s));
+  tb = ctx->cub_bytes;
+  CK(cub::DeviceSelect::Unique(ctx->cub_temp, tb, dc.Current(), ctx->gb_key, &st->ngb_raw, ncand, s));
+  k_gb_finalize<<<1, 1, 0, s>>>(st, ctx->gb_key, ctx->max_blocks);
+  k_nbr<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->pb_mask, ctx->gb_key,
+                                                                            ctx->L, ctx->pb_nbr, st);
+  k_clear_grid<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(ctx->grid, st);
+  if (prof) cudaEventRecord(ctx->ev[1], s);
+  SubstepArgs<D> a{};
+  a.src = src; a.dst = dst; a.cap = ctx->cap; a.keys = keys; a.perm = perm;
+  a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = st;
+  a.L = ctx->L; a.K = ctx->K; a.dt = dt;
+  k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
+  if (prof) cudaEventRecord(ctx->ev[2], s);
+  k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
+      ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
+  if (prof) cudaEventRecord(ctx->ev[3], s);
+  k_g2p<D><<<ctx->grid_g2p, G2P_THREADS, 0, s>>>(a);
+  k_end<<<1, 1, 0, s>>>(st);
+  if (prof) cudaEventRecord(ctx->ev[4], s);
+  CK(cudaGetLastError());
+  ctx->launches += 11;   // our own kernels; CUB's internal launches are not counted
+  ctx->last_keys = keys;
+  return MPM_OK;
+}
+
+extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, void* stream) {
+  (void)t;   // built-in colliders ignore t (engine/mpm_solver.py:621-640, 660-685)
+  if (!ctx || count < 0) return MPM_E_INVALID;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  ctx->launches = 0;
+  ctx->done_last = 0;
+  if (count == 0 || ctx->n == 0) return MPM_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = upload_colliders(ctx, s);
+  if (rc) return rc;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    rc = refresh_bbox(ctx, s);
+    if (rc) return rc;
+    rc = update_layout(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+    const int cur0 = ctx->cur;
+    const bool prof = ctx->profiling && count == 1;
+    for (int i = 0; i < count; ++i) {
+      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), s, prof)
+                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), s, prof);
+      if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const Status& h = *ctx->h_status;
+    ctx->cur = cur0 ^ (h.done & 1);
+    count -= h.done;
+    ctx->done_last += h.done;
+    if (h.done > 0) {
+      ctx->last = h;
+      ctx->lastL = ctx->L;
+      ctx->last_valid = (h.err == 0);
+    }
+    if (prof && !h.err)
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    if (!h.err) {
+      for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = h.bb_min[d]; ctx->bb_max[d] = h.bb_max[d]; }
+      ctx->bbox_valid = true;
+      return MPM_OK;
+    }
+    // a substep refused to run: nothing was modified past `done`
+    ctx->bbox_valid = false;
+    ctx->layout_valid = false;
+    if (h.err & ERR_BLOCK_CAPACITY) {
+      ctx->last.need_blocks = h.need_blocks;
+      char buf[160];
+      snprintf(buf, sizeof buf, "active leaf blocks (%d) exceed the bound capacity (%d)", h.need_blocks, ctx->max_blocks);
+      ctx->err = buf;
+      return MPM_E_BLOCK_CAPACITY;
+    }
+    // ERR_BBOX: particles left the sticky box inside the batch; rebuild it and go on
+  }
+  return fail(ctx, MPM_E_INVALID, "substep could not establish a key layout");
+}
+
+extern "C" int mpm_substep(mpm_ctx* ctx, double dt, double t, void* stream) {
+  return mpm_substeps(ctx, dt, t, 1, stream);
+}
+
+extern "C" int mpm_get_stats(mpm_ctx* ctx, mpm_stats* o) {
+  if (!ctx || !o) return MPM_E_INVALID;
+  memset(o, 0, sizeof(*o));
+  o->n_particles = ctx->n;
+  o->n_particle_blocks = ctx->last.npb;
+  o->n_grid_blocks = std::max(ctx->last.ngb, ctx->last.need_blocks);
+  o->max_blocks = ctx->max_blocks;
+  o->key_bits = ctx->L.key_bits;
+  for (int d = 0; d < 3; ++d) { o->bbox_min[d] = ctx->bb_min[d]; o->bbox_max[d] = ctx->bb_max[d]; }
+  uint32_t bits = ctx->last.maxv_all;
+  memcpy(&o->max_velocity, &bits, 4);
+  o->launches = ctx->launches;
+  o->substeps_done = ctx->done_last;
+  o->ms_sort = ctx->ms[0]; o->ms_p2g = ctx->ms[1]; o->ms_grid = ctx->ms[2]; o->ms_g2p = ctx->ms[3];
+  return MPM_OK;
+}
+extern "C" int mpm_set_profiling(mpm_ctx* ctx, int32_t enabled) {
+  if (!ctx) return MPM_E_INVALID;
+  ctx->profiling = enabled != 0;
+  return MPM_OK;
+}
+
+// ------------------------------------------------------------------ read-back
+extern "C" int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream) {
+  if (!ctx || field < 0 || field >= ctx->nf || begin < 0 || end < begin || end > ctx->n) return fail(ctx, MPM_E_INVALID, "mpm_gather: bad range/field");
+  if (end == begin) return MPM_OK;
+  if (!dst_dev) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t* st = ctx->state[ctx->cur];
+  const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
+  k_gather_field<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(st + (size_t)field * ctx->cap, st + (size_t)idf * ctx->cap,
+                                                                  (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
+extern "C" int mpm_download(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_host, void* stream) {
+  if (!ctx) return MPM_E_INVALID;
+  int rc = mpm_gather(ctx, field, begin, end, ctx->stage, stream);
+  if (rc || end == begin) return rc;
+  if (!dst_host) return MPM_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(dst_host, ctx->stage, (size_t)(end - begin) * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return MPM_OK;
+}
+
+
+// ------------------------------------------------------------------ mesh seeding
+extern "C" int mpm_voxelize(int32_t device, const double* tris_dev, int64_t ntri, const int32_t* res, double dx,
+                            int32_t padding, const int32_t* lo, const int32_t* hi, int32_t* vox, void* stream) {
+  if (!res || !lo || !hi || ntri < 0 || (ntri > 0 && (!tris_dev || !vox))) return MPM_E_INVALID;
+  if (ntri == 0) return MPM_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return MPM_E_CUDA;
+  VoxArgs a{};
+  a.tris = tris_dev; a.ntri = ntri; a.dx = dx; a.inv_dx = 1.0 / dx; a.padding = padding; a.vox = vox;
+  for (int d = 0; d < 3; ++d) { a.res[d] = res[d]; a.lo[d] = lo[d]; a.hi[d] = hi[d]; }
+  int blocks = (int)std::min<int64_t>((ntri * 32 + 255) / 256, 148 * 16);
+  k_voxelize<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? MPM_OK : MPM_E_CUDA;
+}
+
+extern "C" int mpm_voxel_sample(int32_t device, const int32_t* vox, const int32_t* res, const int32_t* lo,
+                                const int32_t* hi, int32_t sample_density, int32_t super_sample, double cell,
+                                const double* translation, int32_t grid_size, int32_t padding, uint64_t seed,
+                                int32_t pass, int32_t* counts, const int64_t* offsets, float* x_out, void* stream) {
+  if (!vox || !res || !lo || !hi || sample_density < 0 || super_sample < 1) return MPM_E_INVALID;
+  if (pass == 0 ? !counts : (!offsets || !x_out)) return MPM_E_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return MPM_E_CUDA;
+  VoxSampleArgs a{};
+  a.vox = vox; a.sample_density = sample_density; a.super_sample = super_sample;
+  a.s = (float)((double)sample_density / ((double)super_sample * super_sample * super_sample));
+  a.cell = (float)cell;
+  a.grid_size = grid_size; a.padding = padding; a.seed = seed;
+  a.counts = counts; a.offsets = offsets; a.x_out = x_out; a.pass = pass;
+  size_t total = 1;
+  for (int d = 0; d < 3; ++d) {
+    a.res[d] = res[d]; a.lo[d] = lo[d]; a.hi[d] = hi[d];
+    a.trans[d] = translation ? (float)translation[d] : 0.f;
+    if (hi[d] <= lo[d]) return MPM_OK;
+    total *= (size_t)(hi[d] - lo[d]);
+  }
+  int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  k_voxel_sample<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? MPM_OK : MPM_E_CUDA;
+}
+
+// ------------------------------------------------------------------ debug
+extern "C" int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream) {
+  if (!ctx || !block_host) return MPM_E_INVALID;
+  if (ctx->n == 0) return MPM_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int* out = (int*)ctx->state[ctx->cur ^ 1];   // the idle set is free between substeps
+  const int half = ctx->P.grid_size / 2;
+  int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
+  if (ctx->dim == 3) k_debug_binning<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, out);
+  else k_debug_binning<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(block_host, out, (size_t)ctx->n * ctx->dim * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return MPM_OK;
+}
+
+static void decode_block(const mpm_ctx* ctx, const KeyLayout& L, uint32_t lin, int* out) {
+  for (int d = ctx->dim - 1; d >= 0; --d) {
+    out[d] = (int)(lin % (uint32_t)L.eb[d]) + L.ob[d];
+    lin /= (uint32_t)L.eb[d];
+  }
+}
+
+extern "C" int mpm_debug_blocks(mpm_ctx* ctx, int32_t* pb_coords, int32_t* pb_counts, int32_t* npb_out,
+                                int32_t* gb_coords, int32_t* ngb_out) {
+  if (!ctx) return MPM_E_INVALID;
+  if (!ctx->last_valid) return fail(ctx, MPM_E_INVALID, "no completed substep to inspect");
+  CK(cudaSetDevice(ctx->P.device));
+  const int npb = ctx->last.npb, ngb = ctx->last.ngb;
+  if (npb_out) *npb_out = npb;
+  if (ngb_out) *ngb_out = ngb;
+  CK(cudaDeviceSynchronize());
+  if (pb_coords || pb_counts) {
+    std::vector<int> start(npb + 1);
+    CK(cudaMemcpy(start.data(), ctx->pb_start, (size_t)(npb + 1) * 4, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < npb; ++b) {
+      if (pb_counts) pb_counts[b] = start[b + 1] - start[b];
+      if (pb_coords) {
+        uint32_t key;
+        CK(cudaMemcpy(&key, ctx->last_keys + start[b], 4, cudaMemcpyDeviceToHost));
+        decode_block(ctx, ctx->lastL, key >> ctx->cb, pb_coords + (size_t)b * ctx->dim);
+      }
+    }
+  }
+  if (gb_coords) {
+    std::vector<uint32_t> k(ngb);
+    CK(cudaMemcpy(k.data(), ctx->gb_key, (size_t)ngb * 4, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < ngb; ++g) decode_block(ctx, ctx->lastL, k[g], gb_coords + (size_t)g * ctx->dim);
+  }
+  return MPM_OK;
+}
+
+extern "C" int mpm_debug_grid(mpm_ctx* ctx, int32_t* cell_host, float* vm_host, int64_t max_cells, int64_t* ncell) {
+  if (!ctx) return MPM_E_INVALID;
+  if (!ctx->last_valid) return fail(ctx, MPM_E_INVALID, "no completed substep to inspect");
+  CK(cudaSetDevice(ctx->P.device));
+  const int ngb = ctx->last.ngb;
+  const int64_t total = (int64_t)ngb * ctx->cells;
+  if (ncell) *ncell = total;
+  if (!cell_host || !vm_host) return MPM_OK;
+  if (max_cells < total) return fail(ctx, MPM_E_INVALID, "mpm_debug_grid: buffer too small");
+  CK(cudaDeviceSynchronize());
+  std::vector<uint32_t> k(ngb);
+  CK(cudaMemcpy(k.data(), ctx->gb_key, (size_t)ngb * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vm_host, ctx->grid, (size_t)total * 16, cudaMemcpyDeviceToHost));
+  const int half = ctx->P.grid_size / 2, ll = ctx->log_leaf, leaf = 1 << ll;
+  for (int g = 0; g < ngb; ++g) {
+    int blk[3] = {0, 0, 0};
+    decode_block(ctx, ctx->lastL, k[g], blk);
+    for (int c = 0; c < ctx->cells; ++c) {
+      int32_t* o = cell_host + ((size_t)g * ctx->cells + c) * ctx->dim;
+      for (int d = 0; d < ctx->dim; ++d) {
+        int lc = (c >> (ll * (ctx->dim - 1 - d))) & (leaf - 1);
+        o[d] = (blk[d] << ll) + lc - half;
+      }
+    }
+  }
+  return MPM_OK;
+}
+
+extern "C" int mpm_debug_particle_update(mpm_ctx* ctx, double dt, int64_t n, const int32_t* mat_h, float* F_h,
+                                         const float* C_h, float* Jp_h, float* aff_h, float* mass_h) {
+  if (!ctx || n < 0) return MPM_E_INVALID;
+  if (n == 0) return MPM_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  const size_t dd = (size_t)ctx->dim * ctx->dim;
+  // debug-only path: uses the idle state set as scratch
+  const size_t need = (size_t)n * (3 * dd + 3);
+  if (need > (size_t)ctx->nf * ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_debug_particle_update: n too large for scratch");
+  float* base = (float*)ctx->state[ctx->cur ^ 1];
+  float *F = base, *C = F + n * dd, *A = C + n * dd, *Jp = A + n * dd, *M = Jp + n;
+  int* mat = (int*)(M + n);
+  CK(cudaMemcpy(F, F_h, n * dd * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(C, C_h, n * dd * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(Jp, Jp_h, n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(mat, mat_h, n * 4, cudaMemcpyHostToDevice));
+  int blocks = gs_blocks(n, 128, ctx->sm_count);
+  if (ctx->dim == 3) k_debug_update<3><<<blocks, 128>>>(ctx->K, (float)dt, (int)n, mat, F, C, Jp, A, M);
+  else k_debug_update<2><<<blocks, 128>>>(ctx->K, (float)dt, (int)n, mat, F, C, Jp, A, M);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(F_h, F, n * dd * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(aff_h, A, n * dd * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(Jp_h, Jp, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(mass_h, M, n * 4, cudaMemcpyDeviceToHost));
+  return MPM_OK;
+}

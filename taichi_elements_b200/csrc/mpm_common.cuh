@@ -1,0 +1,84 @@
+// Shared declarations of libmpm_b200: geometry traits, key layout, the device
+// status block and the workspace carve-up.  See include/mpm_b200.h for the ABI
+// and DESIGN.md for the data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mpm_math.cuh"
+
+namespace mpm {
+
+// Leaf-block geometry of the reference's sparse grid
+// (engine/mpm_solver.py:154-186): 4^3 leaves in 3D, 16^2 in 2D.
+template <int D> struct Geo;
+template <> struct Geo<3> {
+  static constexpr int LEAF = 4, LOG_LEAF = 2, CELLS = 64, CB = 6;   // CB = cell bits in a key
+  static constexpr int T = LEAF + 2, TN = T * T * T, NO = 8;         // staged tile, octants
+  static constexpr int NF = 2 * 3 + 2 * 9 + 5;
+};
+template <> struct Geo<2> {
+  static constexpr int LEAF = 16, LOG_LEAF = 4, CELLS = 256, CB = 8;
+  static constexpr int T = LEAF + 2, TN = T * T, NO = 4;
+  static constexpr int NF = 2 * 2 + 2 * 4 + 5;
+};
+
+// Field (word) indices inside one state set, SoA with stride = capacity.
+template <int D> struct Fld {
+  static constexpr int X = 0, V = D, F = 2 * D, C = 2 * D + D * D, JP = 2 * D + 2 * D * D,
+                       MAT = JP + 1, COLOR = JP + 2, ID = JP + 3, EMIT = JP + 4, N = JP + 5;
+};
+
+static constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
+
+// Sort-key layout for one substep: leaf-block coordinates relative to a
+// host-maintained ("sticky") bounding box, row-major with x slowest, then the
+// cell index inside the leaf.
+struct KeyLayout {
+  int ob[3];   // origin of the box, absolute leaf-block coords (0 .. grid_size/leaf)
+  int eb[3];   // extent in blocks (includes the +1 upper neighbour ring)
+  int half;    // grid_size/2: global signed cell index = absolute cell - half
+  int key_bits;
+};
+
+enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2 };
+
+// Device-resident status block, copied to pinned host memory after each batch.
+struct Status {
+  int npb;          // particle blocks of this substep
+  int ngb_raw;      // unique candidates incl. possibly INVALID_KEY
+  int ngb;          // grid (active) blocks of this substep
+  int err;          // ErrBits, sticky within a batch
+  int done;         // substeps completed in this batch
+  int work_p2g, work_g2p;
+  unsigned maxv_bits;
+  int bb_min[3], bb_max[3];
+  int need_blocks;  // max(npb, ngb) seen, for capacity growth
+  unsigned maxv_all; // max of maxv_bits over the batch
+  int pad[2];
+};
+
+struct Grav { float g[3]; };
+
+struct ColliderDev {
+  int kind, surface;
+  float a[3], b[3];
+  float r2;        // sphere: radius*radius rounded once to f32
+  float friction;
+  int unbounded;
+};
+static constexpr int MAX_COLLIDERS = 64;
+struct ColliderTable {
+  int n;
+  ColliderDev c[MAX_COLLIDERS];
+};
+
+struct GridCfg {
+  int res[3];
+  int padding;
+  int grid_size;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace mpm

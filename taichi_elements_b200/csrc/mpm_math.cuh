@@ -1,0 +1,355 @@
+// Per-particle constitutive math of the MLS-MPM P2G step, written once as
+// __host__ __device__ so the same code is unit-tested on the CPU (tests/ build
+// a host harness from this header) and runs inside the sm_100a kernels.
+//
+// Follows /root/reference/engine/mpm_solver.py:506-574 (F update, hardening,
+// SVD, plasticity, stress, affine) and :321-342 (sand_projection).  ti.svd is
+// external to the reference tree (Taichi 1.1.0); its convention -- U, V proper
+// rotations, sign of det F on the last singular value -- is restated here.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MPM_HD __host__ __device__ __forceinline__
+#else
+#define MPM_HD inline
+#endif
+
+namespace mpm {
+
+enum Material { WATER = 0, ELASTIC = 1, SNOW = 2, SAND = 3, STATIONARY = 4 };
+
+struct Consts {
+  float dx, inv_dx;
+  float p_vol, p_mass;
+  float mu_0, lambda_0;
+  float alpha;            // sand friction coefficient (:208-210)
+  float sand_coef;        // (dim*lambda_0 + 2 mu_0) / (2 mu_0)  (:336-337)
+  float water_density;
+  float inv_dx2;          // inv_dx**2 as one f32 constant (:569)
+  float four_inv_dx;      // 4*inv_dx as one f32 constant (:721)
+  int support_plasticity;
+};
+
+MPM_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// 2x2 SVD, Taichi's closed form.  Row-major 2x2.
+// ---------------------------------------------------------------------------
+MPM_HD void svd2(const float* F, float* U, float* sig, float* V) {
+  float a = F[0] + F[3];
+  float b = F[2] - F[1];
+  float s = 1.0f / sqrtf(a * a + b * b);
+  float rc = a * s, rs = b * s;
+  // R = [[rc,-rs],[rs,rc]],  S = R^T F (symmetric)
+  float S00 = rc * F[0] + rs * F[2];
+  float S01 = rc * F[1] + rs * F[3];
+  float S11 = -rs * F[1] + rc * F[3];
+  float c = 1.0f, sn = 0.0f, s1 = S00, s2 = S11;
+  if (fabsf(S01) >= 1e-5f) {
+    float tau = 0.5f * (S00 - S11);
+    float w = sqrtf(tau * tau + S01 * S01);
+    float t = tau > 0.0f ? S01 / (tau + w) : S01 / (tau - w);
+    c = 1.0f / sqrtf(t * t + 1.0f);
+    sn = -t * c;
+    float c2 = c * c, sn2 = sn * sn, cs2 = 2.0f * c * sn * S01;
+    s1 = c2 * S00 - cs2 + sn2 * S11;
+    s2 = sn2 * S00 + cs2 + c2 * S11;
+  }
+  float v00, v01, v10, v11;
+  if (s1 < s2) {
+    sig[0] = s2; sig[1] = s1;
+    v00 = -sn; v01 = c; v10 = -c; v11 = -sn;
+  } else {
+    sig[0] = s1; sig[1] = s2;
+    v00 = c; v01 = sn; v10 = -sn; v11 = c;
+  }
+  V[0] = v00; V[1] = v01; V[2] = v10; V[3] = v11;
+  U[0] = rc * v00 - rs * v10; U[1] = rc * v01 - rs * v11;
+  U[2] = rs * v00 + rc * v10; U[3] = rs * v01 + rc * v11;
+}
+
+// ---------------------------------------------------------------------------
+// 3x3 SVD: cyclic Jacobi on S = F^T F (exact rotations, fixed sweep count so
+// warps stay convergent), eigenvalues sorted descending, then U and sigma from
+// B = F V by re-orthogonalised Gram-Schmidt with u2 = u0 x u1 so that U is a
+// rotation and sigma[2] carries the sign of det F (Sifakis/Taichi convention).
+// Row-major 3x3.
+// ---------------------------------------------------------------------------
+MPM_HD void jacobi_rot(float& app, float& aqq, float& apq, float& arp, float& arq,
+                       float* V, int p, int q) {
+  // rotate in the (p,q) plane so that apq -> 0; r is the third index
+  float c = 1.0f, s = 0.0f;
+  if (fabsf(apq) > 1e-30f) {
+    float theta = (aqq - app) / (2.0f * apq);
+    float t = 1.0f / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    t = theta < 0.0f ? -t : t;
+    c = rsqrt_(t * t + 1.0f);
+    s = t * c;
+    float tpq = t * apq;
+    app -= tpq;
+    aqq += tpq;
+    apq = 0.0f;
+    float nrp = c * arp - s * arq;
+    float nrq = s * arp + c * arq;
+    arp = nrp; arq = nrq;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float vp = V[k * 3 + p], vq = V[k * 3 + q];
+      V[k * 3 + p] = c * vp - s * vq;
+      V[k * 3 + q] = s * vp + c * vq;
+    }
+  }
+}
+
+MPM_HD void svd3(const float* F, float* U, float* sig, float* V) {
+  // S = F^T F
+  float a00 = F[0] * F[0] + F[3] * F[3] + F[6] * F[6];
+  float a11 = F[1] * F[1] + F[4] * F[4] + F[7] * F[7];
+  float a22 = F[2] * F[2] + F[5] * F[5] + F[8] * F[8];
+  float a01 = F[0] * F[1] + F[3] * F[4] + F[6] * F[7];
+  float a02 = F[0] * F[2] + F[3] * F[5] + F[6] * F[8];
+  float a12 = F[1] * F[2] + F[4] * F[5] + F[7] * F[8];
+  V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 5; ++sweep) {
+    jacobi_rot(a00, a11, a01, a02, a12, V, 0, 1);
+    jacobi_rot(a00, a22, a02, a01, a12, V, 0, 2);
+    jacobi_rot(a11, a22, a12, a01, a02, V, 1, 2);
+  }
+  // sort eigenvalues descending; a column swap is paired with a sign flip so
+  // det V stays +1
+#define MPM_SWAPCOL(i, j, ei, ej)                      \
+  if (ei < ej) {                                       \
+    float te = ei; ei = ej; ej = te;                   \
+    for (int k = 0; k < 3; ++k) {                      \
+      float tv = V[k * 3 + i];                         \
+      V[k * 3 + i] = V[k * 3 + j];                     \
+      V[k * 3 + j] = -tv;                              \
+    }                                                  \
+  }
+  MPM_SWAPCOL(0, 1, a00, a11)
+  MPM_SWAPCOL(0, 2, a00, a22)
+  MPM_SWAPCOL(1, 2, a11, a22)
+#undef MPM_SWAPCOL
+  // B = F V
+  float B[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      B[i * 3 + j] = F[i * 3 + 0] * V[0 * 3 + j] + F[i * 3 + 1] * V[1 * 3 + j] +
+                     F[i * 3 + 2] * V[2 * 3 + j];
+  // u0 = b0 / |b0|
+  float n0 = sqrtf(B[0] * B[0] + B[3] * B[3] + B[6] * B[6]);
+  float u00, u10, u20;
+  if (n0 > 1e-30f) { float r = 1.0f / n0; u00 = B[0] * r; u10 = B[3] * r; u20 = B[6] * r; }
+  else { u00 = 1; u10 = 0; u20 = 0; }
+  // u1 = normalise(b1 - (u0.b1) u0)
+  float d01 = u00 * B[1] + u10 * B[4] + u20 * B[7];
+  float w0 = B[1] - d01 * u00, w1 = B[4] - d01 * u10, w2 = B[7] - d01 * u20;
+  float n1 = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+  float u01, u11, u21;
+  if (n1 > 1e-12f * n0 && n1 > 1e-30f) { float r = 1.0f / n1; u01 = w0 * r; u11 = w1 * r; u21 = w2 * r; }
+  else {
+    // rank <= 1: any unit vector orthogonal to u0
+    float ax = fabsf(u00), ay = fabsf(u10), az = fabsf(u20);
+    float ex = (ax <= ay && ax <= az) ? 1.0f : 0.0f;
+    float ey = (ex == 0.0f && ay <= az) ? 1.0f : 0.0f;
+    float ez = (ex == 0.0f && ey == 0.0f) ? 1.0f : 0.0f;
+    float dd = ex * u00 + ey * u10 + ez * u20;
+    w0 = ex - dd * u00; w1 = ey - dd * u10; w2 = ez - dd * u20;
+    float r = 1.0f / sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+    u01 = w0 * r; u11 = w1 * r; u21 = w2 * r;
+  }
+  // u2 = u0 x u1
+  float u02 = u10 * u21 - u20 * u11;
+  float u12 = u20 * u01 - u00 * u21;
+  float u22 = u00 * u11 - u10 * u01;
+  U[0] = u00; U[1] = u01; U[2] = u02;
+  U[3] = u10; U[4] = u11; U[5] = u12;
+  U[6] = u20; U[7] = u21; U[8] = u22;
+  sig[0] = n0;
+  sig[1] = u01 * B[1] + u11 * B[4] + u21 * B[7];
+  sig[2] = u02 * B[2] + u12 * B[5] + u22 * B[8];
+}
+
+template <int D> MPM_HD void svd(const float* F, float* U, float* sig, float* V);
+template <> MPM_HD void svd<2>(const float* F, float* U, float* sig, float* V) { svd2(F, U, sig, V); }
+template <> MPM_HD void svd<3>(const float* F, float* U, float* sig, float* V) { svd3(F, U, sig, V); }
+
+template <int D> MPM_HD float det(const float* A);
+template <> MPM_HD float det<2>(const float* A) { return A[0] * A[3] - A[1] * A[2]; }
+template <> MPM_HD float det<3>(const float* A) {
+  return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+         A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+
+// C = A * B
+template <int D> MPM_HD void matmul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s += A[i * D + k] * B[k * D + j];
+      C[i * D + j] = s;
+    }
+}
+// C = A * B^T
+template <int D> MPM_HD void matmul_nt(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s += A[i * D + k] * B[j * D + k];
+      C[i * D + j] = s;
+    }
+}
+// C = U diag(s) V^T
+template <int D> MPM_HD void usvt(const float* U, const float* s, const float* V, float* C) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) a += U[i * D + k] * s[k] * V[j * D + k];
+      C[i * D + j] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sand_projection (engine/mpm_solver.py:321-342).  sig in/out, Jp in/out.
+// ---------------------------------------------------------------------------
+template <int D> MPM_HD void sand_projection(const Consts& K, float* sig, float& Jp) {
+  float eps[D], tr = 0.0f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) { eps[i] = logf(fmaxf(fabsf(sig[i]), 1e-4f)); tr += eps[i]; }
+  tr += Jp;
+  float nrm = 0.0f, eh[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { eh[i] = eps[i] - tr / (float)D; nrm += eh[i] * eh[i]; }
+  nrm = sqrtf(nrm) + 1e-20f;
+  if (tr >= 0.0f) {
+    Jp = tr;
+#pragma unroll
+    for (int i = 0; i < D; ++i) sig[i] = 1.0f;
+  } else {
+    Jp = 0.0f;
+    float dg = nrm + K.sand_coef * tr * K.alpha;
+    float f = fmaxf(0.0f, dg) / nrm;
+#pragma unroll
+    for (int i = 0; i < D; ++i) sig[i] = expf(eps[i] - f * eh[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The per-particle part of p2g (engine/mpm_solver.py:506-574).
+//   in : F (stored), C, Jp, material, dt
+//   out: F (new stored), Jp (new), affine = stress + mass*C, mass
+// ---------------------------------------------------------------------------
+template <int D>
+MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, const float* C,
+                            float& Jp, float* affine, float& mass) {
+  constexpr int DD = D * D;
+  float Fin[DD];
+  if (material == WATER) {                                   // :508-511
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Fin[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) Fin[i * D + i] = 1.0f;
+    if (K.support_plasticity) Fin[0] = Jp;
+  } else {
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Fin[i] = F[i];
+  }
+  float A[DD];                                               // I + dt*C  (:513)
+#pragma unroll
+  for (int i = 0; i < DD; ++i) A[i] = dt * C[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i) A[i * D + i] += 1.0f;
+  float Fn[DD];
+  matmul<D>(A, Fin, Fn);
+
+  float h = 1.0f;                                            // :515-521
+  if (K.support_plasticity && material != WATER) h = expf(10.0f * (1.0f - Jp));
+  if (material == ELASTIC) h = 0.3f;
+  float mu = K.mu_0 * h, la = K.lambda_0 * h;
+  if (material == WATER) mu = 0.0f;
+
+  float stress[DD];
+  mass = K.p_mass;
+  if (material == WATER) {
+    // mu = 0: only J = prod(sigma) = det F is needed.
+    float J = det<D>(Fn);
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Fn[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) Fn[i * D + i] = 1.0f;
+    Fn[0] = J;                                               // :537-542
+    if (K.support_plasticity) Jp = J;
+    float p = la * J * (J - 1.0f);
+#pragma unroll
+    for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) stress[i * D + i] = p;
+    mass *= K.water_density;                                 // :571-573
+  } else {
+    float U[DD], V[DD], sig[D];
+    svd<D>(Fn, U, sig, V);                                   // :525
+    if (material != SAND) {
+      float J = 1.0f;                                        // :527-536
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float ns = sig[d];
+        if (material == SNOW) ns = fminf(fmaxf(sig[d], 1.0f - 2.5e-2f), 1.0f + 4.5e-3f);
+        if (K.support_plasticity) Jp *= sig[d] / ns;
+        sig[d] = ns;
+        J *= ns;
+      }
+      if (material == SNOW) usvt<D>(U, sig, V, Fn);          // :543-545
+      float R[DD], T[DD];
+      matmul_nt<D>(U, V, R);                                 // U V^T
+#pragma unroll
+      for (int i = 0; i < DD; ++i) T[i] = 2.0f * mu * (Fn[i] - R[i]);
+      matmul_nt<D>(T, Fn, stress);                           // (..) F^T (:550)
+      float p = la * J * (J - 1.0f);
+#pragma unroll
+      for (int i = 0; i < D; ++i) stress[i * D + i] += p;
+    } else if (K.support_plasticity) {                       // :553-566
+      sand_projection<D>(K, sig, Jp);
+      usvt<D>(U, sig, V, Fn);
+      float ls[D], center[D], lsum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { ls[i] = logf(sig[i]); lsum += ls[i]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float inv = 1.0f / sig[i];
+        center[i] = 2.0f * K.mu_0 * ls[i] * inv + K.lambda_0 * lsum * inv;
+      }
+      float T[DD];
+      usvt<D>(U, center, V, T);
+      matmul_nt<D>(T, Fn, stress);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DD; ++i) F[i] = Fn[i];                 // :567
+  float scale = -dt * K.p_vol * 4.0f * K.inv_dx2;            // :569
+#pragma unroll
+  for (int i = 0; i < DD; ++i) affine[i] = scale * stress[i] + mass * C[i];   // :574
+}
+
+}  // namespace mpm

@@ -1,0 +1,28 @@
+// Test-only host build of taichi_elements_b200/csrc/mpm_math.cuh: lets the CPU
+// test-suite check the exact device math (SVD, plasticity, stress) against the
+// oracle without a GPU.  Never loaded by the product package.
+#include "../taichi_elements_b200/csrc/mpm_math.cuh"
+extern "C" {
+void host_svd3(const float* F, int n, float* U, float* sig, float* V) {
+  for (int i = 0; i < n; ++i) mpm::svd3(F + 9 * i, U + 9 * i, sig + 3 * i, V + 9 * i);
+}
+void host_svd2(const float* F, int n, float* U, float* sig, float* V) {
+  for (int i = 0; i < n; ++i) mpm::svd2(F + 4 * i, U + 4 * i, sig + 2 * i, V + 4 * i);
+}
+// arrays are AoS row-major per particle
+void host_particle_update(int dim, const float* consts12, int support_plasticity, float dt, int n,
+                          const int* material, float* F, const float* C, float* Jp,
+                          float* affine, float* mass) {
+  mpm::Consts K;
+  K.dx = consts12[0]; K.inv_dx = consts12[1]; K.p_vol = consts12[2]; K.p_mass = consts12[3];
+  K.mu_0 = consts12[4]; K.lambda_0 = consts12[5]; K.alpha = consts12[6]; K.sand_coef = consts12[7];
+  K.water_density = consts12[8]; K.inv_dx2 = consts12[9]; K.four_inv_dx = consts12[10];
+  K.support_plasticity = support_plasticity;
+  for (int i = 0; i < n; ++i) {
+    if (dim == 2)
+      mpm::particle_update<2>(K, dt, material[i], F + 4 * i, C + 4 * i, Jp[i], affine + 4 * i, mass[i]);
+    else
+      mpm::particle_update<3>(K, dt, material[i], F + 9 * i, C + 9 * i, Jp[i], affine + 9 * i, mass[i]);
+  }
+}
+}
