@@ -57,7 +57,7 @@ struct mpm_ctx {
   int launches = 0;
   int done_last = 0;
   bool profiling = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev;   // 5 per profiled substep
   float ms[4] = {0, 0, 0, 0};
   std::string err;
 };
@@ -182,7 +182,6 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<2>, G2P_THREADS, 0);
     ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
   }
-  for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
   *out = ctx;
   return MPM_OK;
 }
@@ -191,8 +190,7 @@ extern "C" int mpm_destroy(mpm_ctx* ctx) {
   if (!ctx) return MPM_E_INVALID;
   cudaSetDevice(ctx->P.device);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
-  for (int i = 0; i < 5; ++i)
-    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   delete ctx;
   return MPM_OK;
 }
@@ -390,14 +388,15 @@ static int update_layout(mpm_ctx* ctx) {
 }
 
 template <int D>
-static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, bool prof) {
+static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
+  const bool prof = ev != nullptr;
   using G = Geo<D>;
   const int n = (int)ctx->n;
   const int sm = ctx->sm_count;
   Status* st = ctx->d_status;
   const uint32_t* src = ctx->state[cur];
   uint32_t* dst = ctx->state[cur ^ 1];
-  if (prof) cudaEventRecord(ctx->ev[0], s);
+  if (prof) cudaEventRecord(ev[0], s);
   k_reset<<<1, 1, 0, s>>>(st);
   k_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->vals_a, st);
   cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
@@ -422,19 +421,19 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, bool
   k_nbr<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->pb_mask, ctx->gb_key,
                                                                             ctx->L, ctx->pb_nbr, st);
   k_clear_grid<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(ctx->grid, st);
-  if (prof) cudaEventRecord(ctx->ev[1], s);
+  if (prof) cudaEventRecord(ev[1], s);
   SubstepArgs<D> a{};
   a.src = src; a.dst = dst; a.cap = ctx->cap; a.keys = keys; a.perm = perm;
   a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = st;
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
   k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
-  if (prof) cudaEventRecord(ctx->ev[2], s);
+  if (prof) cudaEventRecord(ev[2], s);
   k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
       ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
-  if (prof) cudaEventRecord(ctx->ev[3], s);
+  if (prof) cudaEventRecord(ev[3], s);
   k_g2p<D><<<ctx->grid_g2p, G2P_THREADS, 0, s>>>(a);
   k_end<<<1, 1, 0, s>>>(st);
-  if (prof) cudaEventRecord(ctx->ev[4], s);
+  if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
   ctx->launches += 11;   // our own kernels; CUB's internal launches are not counted
   ctx->last_keys = keys;
@@ -459,10 +458,18 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     const int cur0 = ctx->cur;
-    const bool prof = ctx->profiling && count == 1;
+    const bool prof = ctx->profiling && count <= 4096;
+    if (prof)
+      while ((int)ctx->ev.size() < 5 * count) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->ev.push_back(e);
+      }
+    const int enq = count;
     for (int i = 0; i < count; ++i) {
-      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), s, prof)
-                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), s, prof);
+      cudaEvent_t* ev = prof ? ctx->ev.data() + 5 * i : nullptr;
+      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), s, ev)
+                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), s, ev);
       if (rc) return rc;
     }
     CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
@@ -476,8 +483,15 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
       ctx->lastL = ctx->L;
       ctx->last_valid = (h.err == 0);
     }
-    if (prof && !h.err)
-      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    if (prof && !h.err) {   // per-phase device time, averaged over the batch
+      for (int i = 0; i < 4; ++i) ctx->ms[i] = 0.f;
+      for (int k = 0; k < enq; ++k)
+        for (int i = 0; i < 4; ++i) {
+          float t = 0.f;
+          cudaEventElapsedTime(&t, ctx->ev[5 * k + i], ctx->ev[5 * k + i + 1]);
+          ctx->ms[i] += t / enq;
+        }
+    }
     if (!h.err) {
       for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = h.bb_min[d]; ctx->bb_max[d] = h.bb_max[d]; }
       ctx->bbox_valid = true;

@@ -33,12 +33,25 @@ def build_pair(dim, scene, res=32, colliders=(), gravity=None, unbounded=False, 
     return o, s
 
 
-def rel_err(a, b):
-    """max over particles of ||a-b||_inf / max(1, ||b||_inf) per particle."""
+def rel_err(a, b, scale=0.0):
+    """max over particles of ||a_p - b_p||_inf / max(||b_p||_inf, scale): relative to the
+    particle's own magnitude, floored by the characteristic scale of the field."""
     a = np.asarray(a, np.float64).reshape(len(a), -1)
     b = np.asarray(b, np.float64).reshape(len(b), -1)
     if a.shape[0] == 0:
         return 0.0
     num = np.abs(a - b).max(axis=1)
-    den = np.maximum(np.abs(b).max(axis=1), 1e-30)
+    den = np.maximum(np.abs(b).max(axis=1), max(scale, 1e-30))
     return float((num / den).max())
+
+
+def state_errors(s, o):
+    """Per-field error of the CUDA solver `s` against oracle `o` (insertion order)."""
+    vs = max(float(np.abs(o.v).max()), 1e-6)
+    return {
+        'x': rel_err(s.x.to_numpy(), o.x, 1.0),
+        'v': rel_err(s.v.to_numpy(), o.v, vs),
+        'F': rel_err(s.F.to_numpy(), o.F, 1.0),
+        'C': rel_err(s.C.to_numpy(), o.C, 4 * o.inv_dx * vs),
+        'Jp': float(np.abs(s.Jp.to_numpy() - o.Jp).max()),
+    }
