@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/mpm_b200.h"
-#include "mpm_kernels.cuh"
+#include "mpm_p2g.cuh"
 
 using namespace mpm;
 
@@ -53,7 +53,8 @@ struct mpm_ctx {
   Grav grav{};
   GridCfg gcfg{};
   int sm_count = 148;
-  int grid_p2g = 148, grid_g2p = 148;
+  int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
+  int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;
   int done_last = 0;
   bool profiling = false;
@@ -182,6 +183,15 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<2>, G2P_THREADS, 0);
     ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
   }
+  if (p->dim == 3) {
+    cudaFuncSetAttribute(k_p2g_cell<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2g_smem_bytes<3>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<3>, P2GCfg<3>::THREADS, p2g_smem_bytes<3>());
+  } else {
+    cudaFuncSetAttribute(k_p2g_cell<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2g_smem_bytes<2>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<2>, P2GCfg<2>::THREADS, p2g_smem_bytes<2>());
+  }
+  ctx->grid_p2g_cell = ctx->sm_count * std::max(occ, 1);
+  if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
   return MPM_OK;
 }
@@ -426,7 +436,8 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cuda
   a.src = src; a.dst = dst; a.cap = ctx->cap; a.keys = keys; a.perm = perm;
   a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = st;
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
-  k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
+  if (ctx->p2g_variant == 0) k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
+  else k_p2g_cell<D><<<ctx->grid_p2g_cell, P2GCfg<D>::THREADS, p2g_smem_bytes<D>(), s>>>(a);
   if (prof) cudaEventRecord(ev[2], s);
   k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
       ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);

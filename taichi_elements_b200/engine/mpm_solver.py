@@ -552,6 +552,24 @@ class MPMSolver:
         write_point_cloud(fn, data)
 
     # ------------------------------------------------------------ parity getters (tests)
+    def _inject_state(self, x, v, F, C, Jp, material, color):
+        """Replace all particles by a full state (tests: start CUDA and oracle from the same bits)."""
+        n, d = x.shape
+        assert d == self.dim
+        self.clear_particles()
+        self._reserve(n)
+        rows = [np.asarray(x, np.float32).T, np.asarray(v, np.float32).T,
+                np.asarray(F, np.float32).reshape(n, d * d).T, np.asarray(C, np.float32).reshape(n, d * d).T,
+                np.asarray(Jp, np.float32)[None]]
+        fl = np.ascontiguousarray(np.concatenate(rows, axis=0)).view(np.int32)
+        ints = np.stack([np.asarray(material, np.int32), np.asarray(color, np.int32),
+                         np.arange(n, dtype=np.int32), np.zeros(n, np.int32)])
+        words = torch.from_numpy(np.ascontiguousarray(np.concatenate([fl, ints], axis=0))).to(self._device)
+        self._state[0, :, :n] = words
+        torch.cuda.synchronize(self._device)
+        self._n = n
+        self._check(self._lib.mpm_set_state(self._ctx, 0, n), 'mpm_set_state')
+
     def debug_binning(self):
         out = np.empty((self._n, self.dim), np.int32)
         self._check(self._lib.mpm_debug_binning(self._ctx, out.ctypes.data_as(ctypes.c_void_p), self._stream()),
