@@ -1,0 +1,69 @@
+"""The exact device math (csrc/mpm_math.cuh, compiled for the host by the
+test-only harness) against the oracle: SVD and the per-particle P2G update."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle.mpm_oracle import OracleMPM, svd2d, svd3d
+from scenes import mixed_scene
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_device_svd3_matches_lapack(host_math):
+    rng = np.random.default_rng(1)
+    n = 20000
+    Q = np.linalg.qr(rng.normal(size=(n, 3, 3)))[0]
+    S = np.exp(rng.normal(scale=0.5, size=(n, 3)))
+    F = ((Q * S[:, None, :]) @ np.linalg.qr(rng.normal(size=(n, 3, 3)))[0]).astype(np.float32)
+    F[:100] = np.eye(3, dtype=np.float32)
+    U, V, sig = np.empty_like(F), np.empty_like(F), np.empty((n, 3), np.float32)
+    host_math.host_svd3(P(F), n, P(U), P(sig), P(V))
+    rec = np.einsum('nik,nk,njk->nij', U, sig, V)
+    assert np.abs(rec - F).max() < 1e-5
+    assert np.abs(np.linalg.det(U) - 1).max() < 1e-5 and np.abs(np.linalg.det(V) - 1).max() < 1e-5
+    Uo, so, Vo = svd3d(F)
+    assert np.abs(sig - so).max() < 1e-5
+    assert np.abs(np.einsum('nik,njk->nij', U, V) - np.einsum('nik,njk->nij', Uo, Vo)).max() < 1e-5
+    assert np.array_equal(U[:100], np.tile(np.eye(3, dtype=np.float32), (100, 1, 1)))   # F = I is exact
+
+
+def test_device_svd2_is_the_closed_form(host_math):
+    rng = np.random.default_rng(2)
+    n = 5000
+    F = (rng.normal(size=(n, 2, 2)) + np.eye(2)).astype(np.float32)
+    U, V, sig = np.empty_like(F), np.empty_like(F), np.empty((n, 2), np.float32)
+    host_math.host_svd2(P(F), n, P(U), P(sig), P(V))
+    Uo, so, Vo = svd2d(F)
+    assert np.abs(U - Uo).max() < 1e-6 and np.abs(sig - so).max() < 1e-5 and np.abs(V - Vo).max() < 1e-6
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('plastic', [True, False])
+def test_particle_update_matches_oracle(host_math, dim, plastic):
+    o = OracleMPM((32, ) * dim, support_plasticity=plastic)
+    for p, m, vel in mixed_scene(dim, seed=5):
+        o.add_particles(p, m, velocity=vel)
+    rng = np.random.default_rng(6)
+    n = o.n_particles
+    o.C = (rng.normal(size=o.C.shape) * 5).astype(np.float32)
+    o.F = (o.F + 0.08 * rng.normal(size=o.F.shape)).astype(np.float32)
+    o.Jp = (o.Jp + 0.02 * rng.normal(size=n)).astype(np.float32)
+    F, C, Jp, mat = o.F.copy(), o.C.copy(), o.Jp.copy(), o.material.copy()
+    dt = o.default_dt
+    o.p2g(dt)
+    consts = np.array([o.dx, o.inv_dx, o.p_vol, o.p_mass, o.mu_0, o.lambda_0, o.alpha,
+                       (dim * o.lambda_0 + 2 * o.mu_0) / (2 * o.mu_0), o.water_density, o.inv_dx**2,
+                       4 * o.inv_dx, 0], np.float32)
+    aff, mass = np.empty_like(F), np.empty(n, np.float32)
+    host_math.host_particle_update(dim, P(consts), int(plastic), ctypes.c_float(dt), n, P(mat), P(F), P(C), P(Jp),
+                                   P(aff), P(mass))
+    assert np.abs(F - o.F).max() < 2e-5
+    assert np.abs(Jp - o.Jp).max() < 2e-5
+    assert np.array_equal(mass, o._mass)
+    # affine = stress*scale + mass*C: the stress part carries the f32 cancellation of (F - R)
+    scale = max(1.0, float(np.abs(o._affine).max()))
+    assert np.abs(aff - o._affine).max() < 2e-4 * scale
