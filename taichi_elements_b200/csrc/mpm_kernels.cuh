@@ -534,47 +534,74 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(SubstepArgs<D> a) {
         w[2][d] = 0.5f * (fx[d] - 0.5f) * (fx[d] - 0.5f);
       }
       const uint32_t mat = ldu(a.src, cap, FL::MAT, p);
-      float nv[D], nC[D * D];
+      // Tensor-product evaluation of sum_ijk w_i w_j w_k g_ijk and of its first
+      // moments (C = 4 inv_dx sum w g (x) (o - fx), :715-721): partial sums along
+      // z, then y, then x -- 279 FMAs instead of 27 x 23.
+      float nv[D], nC[D * D], mw[3][D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) nv[d] = 0.0f;
+      for (int d = 0; d < D; ++d)
 #pragma unroll
-      for (int i = 0; i < D * D; ++i) nC[i] = 0.0f;
+        for (int i = 0; i < 3; ++i) mw[i][d] = w[i][d] * ((float)i - fx[d]);
       if constexpr (D == 3) {
+        float cx[3] = {0.f, 0.f, 0.f}, cy[3] = {0.f, 0.f, 0.f}, cz[3] = {0.f, 0.f, 0.f};
+        nv[0] = nv[1] = nv[2] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+          float B00[3] = {0.f, 0.f, 0.f}, B10[3] = {0.f, 0.f, 0.f}, B01[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 3; ++j)
+          for (int j = 0; j < 3; ++j) {
+            float A0[3] = {0.f, 0.f, 0.f}, A1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const float4 g = tile[((l[0] + i) * G::T + (l[1] + j)) * G::T + (l[2] + k)];
-              const float wt = w[i][0] * w[j][1] * w[k][2];
-              const float dp[3] = {(float)i - fx[0], (float)j - fx[1], (float)k - fx[2]};
-              const float gv[3] = {g.x, g.y, g.z};
-              const float cw = a.K.four_inv_dx * wt;
-#pragma unroll
-              for (int r = 0; r < 3; ++r) {
-                nv[r] += wt * gv[r];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) nC[r * 3 + c] += cw * (gv[r] * dp[c]);
-              }
+              A0[0] += w[k][2] * g.x; A0[1] += w[k][2] * g.y; A0[2] += w[k][2] * g.z;
+              A1[0] += mw[k][2] * g.x; A1[1] += mw[k][2] * g.y; A1[2] += mw[k][2] * g.z;
             }
-      } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+            for (int r = 0; r < 3; ++r) {
+              B00[r] += w[j][1] * A0[r];
+              B10[r] += mw[j][1] * A0[r];
+              B01[r] += w[j][1] * A1[r];
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            nv[r] += w[i][0] * B00[r];
+            cx[r] += mw[i][0] * B00[r];
+            cy[r] += w[i][0] * B10[r];
+            cz[r] += w[i][0] * B01[r];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          nC[r * 3 + 0] = a.K.four_inv_dx * cx[r];
+          nC[r * 3 + 1] = a.K.four_inv_dx * cy[r];
+          nC[r * 3 + 2] = a.K.four_inv_dx * cz[r];
+        }
+      } else {
+        float cx[2] = {0.f, 0.f}, cy[2] = {0.f, 0.f};
+        nv[0] = nv[1] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float A0[2] = {0.f, 0.f}, A1[2] = {0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const float4 g = tile[(l[0] + i) * G::T + (l[1] + j)];
-            const float wt = w[i][0] * w[j][1];
-            const float dp[2] = {(float)i - fx[0], (float)j - fx[1]};
-            const float gv[2] = {g.x, g.y};
-            const float cw = a.K.four_inv_dx * wt;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              nv[r] += wt * gv[r];
-#pragma unroll
-              for (int c = 0; c < 2; ++c) nC[r * 2 + c] += cw * (gv[r] * dp[c]);
-            }
+            A0[0] += w[j][1] * g.x; A0[1] += w[j][1] * g.y;
+            A1[0] += mw[j][1] * g.x; A1[1] += mw[j][1] * g.y;
           }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            nv[r] += w[i][0] * A0[r];
+            cx[r] += mw[i][0] * A0[r];
+            cy[r] += w[i][0] * A1[r];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          nC[r * 2 + 0] = a.K.four_inv_dx * cx[r];
+          nC[r * 2 + 1] = a.K.four_inv_dx * cy[r];
+        }
       }
       if (mat == (uint32_t)STATIONARY) {                       // :722
 #pragma unroll

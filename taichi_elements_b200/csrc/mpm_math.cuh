@@ -31,11 +31,29 @@ struct Consts {
   int support_plasticity;
 };
 
+// Approximate (MUFU-based, ~1-2 ulp) division / reciprocal square root on the
+// device: IEEE division and sqrt carry slow-path subroutines that ncu showed to
+// be 13% of P2G's instructions; every use below is far inside the 1e-4 parity
+// budget.  On the host (test harness) they are the exact operations.
 MPM_HD float rsqrt_(float x) {
 #if defined(__CUDA_ARCH__)
   return rsqrtf(x);
 #else
   return 1.0f / sqrtf(x);
+#endif
+}
+MPM_HD float fdiv_(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+MPM_HD float sqrt_pos_(float x) {   // x >= 0, normal range
+#if defined(__CUDA_ARCH__)
+  return x * rsqrtf(fmaxf(x, 1e-37f));
+#else
+  return sqrtf(x);
 #endif
 }
 
@@ -87,8 +105,8 @@ MPM_HD void jacobi_rot(float& app, float& aqq, float& apq, float& arp, float& ar
   // rotate in the (p,q) plane so that apq -> 0; r is the third index
   float c = 1.0f, s = 0.0f;
   if (fabsf(apq) > 1e-30f) {
-    float theta = (aqq - app) / (2.0f * apq);
-    float t = 1.0f / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    float theta = fdiv_(aqq - app, 2.0f * apq);
+    float t = fdiv_(1.0f, fabsf(theta) + sqrt_pos_(theta * theta + 1.0f));
     t = theta < 0.0f ? -t : t;
     c = rsqrt_(t * t + 1.0f);
     s = t * c;
@@ -118,7 +136,7 @@ MPM_HD void svd3(const float* F, float* U, float* sig, float* V) {
   float a12 = F[1] * F[2] + F[4] * F[5] + F[7] * F[8];
   V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1;
 #pragma unroll 1
-  for (int sweep = 0; sweep < 5; ++sweep) {
+  for (int sweep = 0; sweep < 4; ++sweep) {
     jacobi_rot(a00, a11, a01, a02, a12, V, 0, 1);
     jacobi_rot(a00, a22, a02, a01, a12, V, 0, 2);
     jacobi_rot(a11, a22, a12, a01, a02, V, 1, 2);
@@ -147,16 +165,18 @@ MPM_HD void svd3(const float* F, float* U, float* sig, float* V) {
       B[i * 3 + j] = F[i * 3 + 0] * V[0 * 3 + j] + F[i * 3 + 1] * V[1 * 3 + j] +
                      F[i * 3 + 2] * V[2 * 3 + j];
   // u0 = b0 / |b0|
-  float n0 = sqrtf(B[0] * B[0] + B[3] * B[3] + B[6] * B[6]);
+  float n0sq = B[0] * B[0] + B[3] * B[3] + B[6] * B[6];
+  float n0 = sqrt_pos_(n0sq);
   float u00, u10, u20;
-  if (n0 > 1e-30f) { float r = 1.0f / n0; u00 = B[0] * r; u10 = B[3] * r; u20 = B[6] * r; }
+  if (n0 > 1e-30f) { float r = rsqrt_(n0sq); u00 = B[0] * r; u10 = B[3] * r; u20 = B[6] * r; }
   else { u00 = 1; u10 = 0; u20 = 0; }
   // u1 = normalise(b1 - (u0.b1) u0)
   float d01 = u00 * B[1] + u10 * B[4] + u20 * B[7];
   float w0 = B[1] - d01 * u00, w1 = B[4] - d01 * u10, w2 = B[7] - d01 * u20;
-  float n1 = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+  float n1sq = w0 * w0 + w1 * w1 + w2 * w2;
+  float n1 = sqrt_pos_(n1sq);
   float u01, u11, u21;
-  if (n1 > 1e-12f * n0 && n1 > 1e-30f) { float r = 1.0f / n1; u01 = w0 * r; u11 = w1 * r; u21 = w2 * r; }
+  if (n1 > 1e-12f * n0 && n1 > 1e-30f) { float r = rsqrt_(n1sq); u01 = w0 * r; u11 = w1 * r; u21 = w2 * r; }
   else {
     // rank <= 1: any unit vector orthogonal to u0
     float ax = fabsf(u00), ay = fabsf(u10), az = fabsf(u20);
@@ -165,7 +185,7 @@ MPM_HD void svd3(const float* F, float* U, float* sig, float* V) {
     float ez = (ex == 0.0f && ey == 0.0f) ? 1.0f : 0.0f;
     float dd = ex * u00 + ey * u10 + ez * u20;
     w0 = ex - dd * u00; w1 = ey - dd * u10; w2 = ez - dd * u20;
-    float r = 1.0f / sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+    float r = rsqrt_(w0 * w0 + w1 * w1 + w2 * w2);
     u01 = w0 * r; u11 = w1 * r; u21 = w2 * r;
   }
   // u2 = u0 x u1
@@ -189,6 +209,46 @@ template <> MPM_HD float det<2>(const float* A) { return A[0] * A[3] - A[1] * A[
 template <> MPM_HD float det<3>(const float* A) {
   return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
          A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+
+
+// ---------------------------------------------------------------------------
+// Polar rotation R = U V^T of a 3x3 F with det F > 0 by Newton's iteration
+// R <- (R + R^-T)/2 (quadratic convergence; singular values s -> (s + 1/s)/2).
+// ELASTIC / STATIONARY particles need only R and J = det F (SURVEY Appendix B:
+// sigma/new_sigma == 1 exactly, so Jp and F are untouched), which replaces the
+// ~2500-instruction Jacobi SVD ncu measured on that path.  Returns false when F
+// is (near) singular, inverted or the iteration does not settle: the caller then
+// takes the SVD path, whose convention handles reflections.
+// ---------------------------------------------------------------------------
+MPM_HD bool polar3_newton(const float* F, float* R, float& J) {
+  J = F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+  float nf = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { R[i] = F[i]; nf += F[i] * F[i]; }
+  if (!(J > 1e-4f * nf * sqrt_pos_(nf) * 0.19245f)) return false;   // det <= 1e-4 * (||F||_F/sqrt3)^3
+  bool ok = false;
+#pragma unroll 1
+  for (int it = 0; it < 12; ++it) {
+    float c[9];
+    c[0] = R[4] * R[8] - R[5] * R[7]; c[1] = R[5] * R[6] - R[3] * R[8]; c[2] = R[3] * R[7] - R[4] * R[6];
+    c[3] = R[2] * R[7] - R[1] * R[8]; c[4] = R[0] * R[8] - R[2] * R[6]; c[5] = R[1] * R[6] - R[0] * R[7];
+    c[6] = R[1] * R[5] - R[2] * R[4]; c[7] = R[2] * R[3] - R[0] * R[5]; c[8] = R[0] * R[4] - R[1] * R[3];
+    float d = R[0] * c[0] + R[1] * c[1] + R[2] * c[2];
+    float h = fdiv_(0.5f, d);
+    float delta = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      float rn = 0.5f * R[i] + h * c[i];     // cofactor / det = R^-T
+      delta = fmaxf(delta, fabsf(rn - R[i]));
+      R[i] = rn;
+    }
+    if (delta < 3e-4f) {                      // the next step squares the error: one more, then stop
+      if (ok || delta < 1e-7f) { ok = true; break; }
+      ok = true;
+    }
+  }
+  return ok;
 }
 
 // C = A * B
@@ -305,6 +365,21 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
     for (int i = 0; i < D; ++i) stress[i * D + i] = p;
     mass *= K.water_density;                                 // :571-573
   } else {
+    float Rp[DD], Jpol = 1.0f;
+    bool fast = false;
+    if constexpr (D == 3) {
+      // ELASTIC / STATIONARY: polar rotation only (no sigma clamp, Jp *= 1)
+      if (material == ELASTIC || material == STATIONARY) fast = polar3_newton(Fn, Rp, Jpol);
+    }
+    if (fast) {
+      float T[DD];
+#pragma unroll
+      for (int i = 0; i < DD; ++i) T[i] = 2.0f * mu * (Fn[i] - Rp[i]);
+      matmul_nt<D>(T, Fn, stress);                           // :550
+      float p = la * Jpol * (Jpol - 1.0f);
+#pragma unroll
+      for (int i = 0; i < D; ++i) stress[i * D + i] += p;
+    } else {
     float U[DD], V[DD], sig[D];
     svd<D>(Fn, U, sig, V);                                   // :525
     if (material != SAND) {
@@ -343,6 +418,7 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
     } else {
 #pragma unroll
       for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
+    }
     }
   }
 #pragma unroll

@@ -54,10 +54,8 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
   const int npb = a.st->npb;
   const int tid = threadIdx.x;
   const size_t cap = a.cap;
-  const int cell = tid / P::SL, sl = tid % P::SL;
-  int cl[D];                                                          // local cell coords
-#pragma unroll
-  for (int d = 0; d < D; ++d) cl[d] = (cell >> (G::LOG_LEAF * (D - 1 - d))) & (G::LEAF - 1);
+  const int sl = tid % P::SL;
+  __shared__ int s_order[G::CELLS];                                   // cells by descending particle count
 
   for (;;) {
     if (tid == 0) s_b = atomicAdd(&a.st->work_p2g, 1);
@@ -77,6 +75,26 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
         for (int k = c + 1; k <= G::CELLS; ++k) cs[k] = cnt;
     }
     __syncthreads();
+    // Balance phase 2: a warp's trip count is the largest cell count among its
+    // lanes, so hand out cells in descending-count order (3D; the 256-cell 2D
+    // leaf keeps the natural order).
+    int cell = tid / P::SL;
+    if constexpr (D == 3) {
+      if (tid < G::CELLS) {
+        const int mine = cs[tid + 1] - cs[tid];
+        int rank = 0;
+        for (int c = 0; c < G::CELLS; ++c) {
+          const int other = cs[c + 1] - cs[c];
+          rank += (other > mine) || (other == mine && c < tid);
+        }
+        s_order[rank] = tid;
+      }
+      __syncthreads();
+      cell = s_order[tid / P::SL];
+    }
+    int cl[D];                                                        // local cell coords
+#pragma unroll
+    for (int d = 0; d < D; ++d) cl[d] = (cell >> (G::LOG_LEAF * (D - 1 - d))) & (G::LEAF - 1);
 
     for (int c0 = 0; c0 < cnt; c0 += CH) {
       const int cn = min(CH, cnt - c0);
