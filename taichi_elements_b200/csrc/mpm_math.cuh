@@ -106,7 +106,8 @@ MPM_HD void jacobi_rot(float& app, float& aqq, float& apq, float& arp, float& ar
   float c = 1.0f, s = 0.0f;
   if (fabsf(apq) > 1e-30f) {
     float theta = fdiv_(aqq - app, 2.0f * apq);
-    float t = fdiv_(1.0f, fabsf(theta) + sqrt_pos_(theta * theta + 1.0f));
+    float at = fminf(fabsf(theta), 1e18f);   // keeps theta^2 finite (rsqrt-based sqrt maps inf to NaN)
+    float t = fdiv_(1.0f, at + sqrt_pos_(at * at + 1.0f));
     t = theta < 0.0f ? -t : t;
     c = rsqrt_(t * t + 1.0f);
     s = t * c;
