@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/mpm_b200.h"
+#include "mpm_bin.cuh"
 #include "mpm_p2g.cuh"
 
 using namespace mpm;
@@ -34,7 +35,11 @@ struct mpm_ctx {
   int* pb_start = nullptr;
   uint32_t* pb_mask = nullptr;
   int* pb_nbr = nullptr;
-  uint32_t *cand_a = nullptr, *cand_b = nullptr, *gb_key = nullptr;
+  uint32_t *cand_a = nullptr, *cand_b = nullptr, *gb_key = nullptr, *pb_key = nullptr;
+  int *flags = nullptr, *fscan = nullptr, *cellcount = nullptr, *cellstart = nullptr;
+  int64_t table_cap = 0;
+  bool dense = false;   // counting-sort path usable for the current layout
+  int use_dense = 1;
   float4* grid = nullptr;
   Status* h_status = nullptr;   // pinned
   int cur = 0;
@@ -54,6 +59,7 @@ struct mpm_ctx {
   GridCfg gcfg{};
   int sm_count = 148;
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
+  int g2p_cfg = 0;
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;
   int done_last = 0;
@@ -85,10 +91,16 @@ static inline int gs_blocks(int64_t n, int threads, int sm) {
 // ------------------------------------------------------------------ sizes
 struct Carve {
   size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
-      off_cand_b, off_gb_key, off_grid, total, cub_bytes;
+      off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, total,
+      cub_bytes;
+  int64_t table_cap;
 };
 
-static size_t cub_temp_bytes(int64_t cap, int64_t ncand) {
+static int64_t table_capacity(int32_t max_blocks) {
+  return std::min<int64_t>(std::max<int64_t>((int64_t)128 * max_blocks, (int64_t)1 << 18), (int64_t)1 << 24);
+}
+
+static size_t cub_temp_bytes(int64_t cap, int64_t ncand, int64_t nscan) {
   size_t best = 0, b = 0;
   cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
   cub::DeviceRadixSort::SortPairs(nullptr, b, k, v, (int)std::max<int64_t>(cap, 1));
@@ -102,6 +114,8 @@ static size_t cub_temp_bytes(int64_t cap, int64_t ncand) {
   cub::DeviceSelect::Unique(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr,
                             (int)std::max<int64_t>(ncand, 1));
   best = std::max(best, b);
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)std::max<int64_t>(nscan, 1));
+  best = std::max(best, b);
   return best + 256;
 }
 
@@ -113,7 +127,8 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_status = take(sizeof(Status));
   c.off_ct = take(sizeof(ColliderTable));
   c.off_scratch = take((size_t)5 * cap * 4);
-  c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks);
+  c.table_cap = table_capacity(max_blocks);
+  c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks, std::max<int64_t>(c.table_cap, (int64_t)max_blocks * cells + 1));
   c.off_cub = take(c.cub_bytes);
   c.off_pb_start = take((size_t)(max_blocks + 2) * 4);
   c.off_pb_mask = take((size_t)max_blocks * 4);
@@ -122,6 +137,11 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_cand_b = take((size_t)max_blocks * no * 4);
   c.off_gb_key = take(((size_t)max_blocks * no + 1) * 4);
   c.off_grid = take((size_t)max_blocks * cells * sizeof(float4));
+  c.off_pb_key = take((size_t)max_blocks * 4);
+  c.off_flags = take((size_t)c.table_cap * 4);
+  c.off_fscan = take((size_t)c.table_cap * 4);
+  c.off_cellcount = take(((size_t)max_blocks * cells + 1) * 4);
+  c.off_cellstart = take(((size_t)max_blocks * cells + 1) * 4);
   c.total = o;
   return c;
 }
@@ -175,13 +195,11 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (p->dim == 3) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g<3>, P2G_THREADS, 0);
     ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<3>, G2P_THREADS, 0);
-    ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
+
   } else {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g<2>, P2G_THREADS, 0);
     ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<2>, G2P_THREADS, 0);
-    ctx->grid_g2p = ctx->sm_count * std::max(occ, 1);
+
   }
   if (p->dim == 3) {
     cudaFuncSetAttribute(k_p2g_cell<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2g_smem_bytes<3>());
@@ -191,6 +209,8 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<2>, P2GCfg<2>::THREADS, p2g_smem_bytes<2>());
   }
   ctx->grid_p2g_cell = ctx->sm_count * std::max(occ, 1);
+  if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
+  if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
   return MPM_OK;
@@ -236,6 +256,12 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->cand_b = (uint32_t*)(b + c.off_cand_b);
   ctx->gb_key = (uint32_t*)(b + c.off_gb_key);
   ctx->grid = (float4*)(b + c.off_grid);
+  ctx->pb_key = (uint32_t*)(b + c.off_pb_key);
+  ctx->flags = (int*)(b + c.off_flags);
+  ctx->fscan = (int*)(b + c.off_fscan);
+  ctx->cellcount = (int*)(b + c.off_cellcount);
+  ctx->cellstart = (int*)(b + c.off_cellstart);
+  ctx->table_cap = c.table_cap;
   ctx->ct_dirty = true;
   ctx->last_valid = false;
   return MPM_OK;
@@ -394,11 +420,37 @@ static int update_layout(mpm_ctx* ctx) {
     ctx->L = L;
     ctx->layout_valid = true;
   }
+  double nlin = 1.0;
+  for (int d = 0; d < ctx->dim; ++d) nlin *= (double)ctx->L.eb[d];
+  ctx->dense = ctx->use_dense && (2.0 * nlin + 1.0 <= (double)ctx->table_cap);
   return MPM_OK;
 }
 
+// G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
+template <int D, int T, int MB>
+static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  static int grid = 0;
+  if (!grid) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<D, T, MB>, T, 0);
+    grid = ctx->sm_count * std::max(occ, 1);
+  }
+  k_g2p<D, T, MB><<<grid, T, 0, s>>>(a);
+}
 template <int D>
-static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
+static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  switch (ctx->g2p_cfg) {
+    case 1: launch_g2p_cfg<D, 256, 4>(ctx, a, s); break;
+    case 2: launch_g2p_cfg<D, 128, 6>(ctx, a, s); break;
+    case 3: launch_g2p_cfg<D, 128, 8>(ctx, a, s); break;
+    case 4: launch_g2p_cfg<D, 128, 10>(ctx, a, s); break;
+    case 5: launch_g2p_cfg<D, 64, 16>(ctx, a, s); break;
+    default: launch_g2p_cfg<D, 256, 3>(ctx, a, s); break;
+  }
+}
+
+template <int D>
+static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
   const bool prof = ev != nullptr;
   using G = Geo<D>;
   const int n = (int)ctx->n;
@@ -407,34 +459,67 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cuda
   const uint32_t* src = ctx->state[cur];
   uint32_t* dst = ctx->state[cur ^ 1];
   if (prof) cudaEventRecord(ev[0], s);
-  k_reset<<<1, 1, 0, s>>>(st);
-  k_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->vals_a, st);
-  cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
-  size_t tb = ctx->cub_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, n, 0, ctx->L.key_bits, s));
-  const uint32_t* keys = dk.Current();
-  const uint32_t* perm = dv.Current();
-  tb = ctx->cub_bytes;
-  thrust::counting_iterator<int> it(0);
-  CK(cub::DeviceSelect::If(ctx->cub_temp, tb, it, BoundedOut{ctx->pb_start, ctx->max_blocks + 1}, &st->npb, n,
-                           HeadOp{keys, G::CB}, s));
-  k_pb_finalize<<<1, 1, 0, s>>>(st, ctx->pb_start, n, ctx->max_blocks);
-  k_pb_masks<D><<<gs_blocks((int64_t)ctx->max_blocks * 32, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->L, ctx->max_blocks,
-                                                                              ctx->pb_mask, ctx->cand_a, st);
-  const int ncand = ctx->max_blocks * G::NO;
-  cub::DoubleBuffer<uint32_t> dc(ctx->cand_a, ctx->cand_b);
-  tb = ctx->cub_bytes;
-  CK(cub::DeviceRadixSort::SortKeys(ctx->cub_temp, tb, dc, ncand, 0, 32, s));
-  tb = ctx->cub_bytes;
-  CK(cub::DeviceSelect::Unique(ctx->cub_temp, tb, dc.Current(), ctx->gb_key, &st->ngb_raw, ncand, s));
-  k_gb_finalize<<<1, 1, 0, s>>>(st, ctx->gb_key, ctx->max_blocks);
-  k_nbr<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->pb_mask, ctx->gb_key,
-                                                                            ctx->L, ctx->pb_nbr, st);
+  const uint32_t* keys = nullptr;
+  const uint32_t* perm = nullptr;
+  const int* cellstart = nullptr;
+  size_t tb;
+  if (ctx->dense) {
+    // ---- counting sort on the (block, cell) key over a dense flag table (mpm_bin.cuh)
+    int nlin = 1;
+    for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+    const int ncell = ctx->max_blocks * G::CELLS + 1;
+    CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+    CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
+    k_bin_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->flags,
+                                                       nlin, commit_prev, st);
+    tb = ctx->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
+    k_bin_rank<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, n, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
+                                                       ctx->max_blocks, st);
+    tb = ctx->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->cellcount, ctx->cellstart, ncell, s));
+    k_bin_scatter<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, n, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
+    k_bin_finish<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(
+        ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr, ctx->gb_key, n,
+        ctx->max_blocks, st);
+    keys = ctx->keys_a;
+    perm = ctx->vals_b;
+    cellstart = ctx->cellstart;
+    ctx->launches += 4;
+  } else {
+    // ---- fallback: multi-pass LSD radix sort + sorted-candidate block list
+    if (commit_prev) k_end<<<1, 1, 0, s>>>(st);
+    k_reset<<<1, 1, 0, s>>>(st);
+    k_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->vals_a, st);
+    cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
+    tb = ctx->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, n, 0, ctx->L.key_bits, s));
+    keys = dk.Current();
+    perm = dv.Current();
+    tb = ctx->cub_bytes;
+    thrust::counting_iterator<int> it(0);
+    CK(cub::DeviceSelect::If(ctx->cub_temp, tb, it, BoundedOut{ctx->pb_start, ctx->max_blocks + 1}, &st->npb, n,
+                             HeadOp{keys, G::CB}, s));
+    k_pb_finalize<<<1, 1, 0, s>>>(st, ctx->pb_start, n, ctx->max_blocks);
+    k_pb_masks<D><<<gs_blocks((int64_t)ctx->max_blocks * 32, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->L, ctx->max_blocks,
+                                                                                ctx->pb_mask, ctx->cand_a, ctx->pb_key, st);
+    const int ncand = ctx->max_blocks * G::NO;
+    cub::DoubleBuffer<uint32_t> dc(ctx->cand_a, ctx->cand_b);
+    tb = ctx->cub_bytes;
+    CK(cub::DeviceRadixSort::SortKeys(ctx->cub_temp, tb, dc, ncand, 0, 32, s));
+    tb = ctx->cub_bytes;
+    CK(cub::DeviceSelect::Unique(ctx->cub_temp, tb, dc.Current(), ctx->gb_key, &st->ngb_raw, ncand, s));
+    k_gb_finalize<<<1, 1, 0, s>>>(st, ctx->gb_key, ctx->max_blocks);
+    k_nbr<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(keys, ctx->pb_start, ctx->pb_mask, ctx->gb_key,
+                                                                              ctx->L, ctx->pb_nbr, st);
+    ctx->launches += 7 + (commit_prev ? 1 : 0);
+  }
   k_clear_grid<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(ctx->grid, st);
   if (prof) cudaEventRecord(ev[1], s);
   SubstepArgs<D> a{};
   a.src = src; a.dst = dst; a.cap = ctx->cap; a.keys = keys; a.perm = perm;
   a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = st;
+  a.pb_key = ctx->pb_key; a.cellstart = cellstart;
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
   if (ctx->p2g_variant == 0) k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
   else k_p2g_cell<D><<<ctx->grid_p2g_cell, P2GCfg<D>::THREADS, p2g_smem_bytes<D>(), s>>>(a);
@@ -442,11 +527,10 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cuda
   k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
       ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
   if (prof) cudaEventRecord(ev[3], s);
-  k_g2p<D><<<ctx->grid_g2p, G2P_THREADS, 0, s>>>(a);
-  k_end<<<1, 1, 0, s>>>(st);
+  launch_g2p<D>(ctx, a, s);
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
-  ctx->launches += 11;   // our own kernels; CUB's internal launches are not counted
+  ctx->launches += 4;   // clear, p2g, grid op, g2p; CUB's internal launches are not counted
   ctx->last_keys = keys;
   return MPM_OK;
 }
@@ -479,10 +563,12 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     const int enq = count;
     for (int i = 0; i < count; ++i) {
       cudaEvent_t* ev = prof ? ctx->ev.data() + 5 * i : nullptr;
-      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), s, ev)
-                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), s, ev);
+      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev)
+                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev);
       if (rc) return rc;
     }
+    k_end<<<1, 1, 0, s>>>(ctx->d_status);   // commit of the last substep
+    ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const Status& h = *ctx->h_status;
@@ -651,13 +737,12 @@ extern "C" int mpm_debug_blocks(mpm_ctx* ctx, int32_t* pb_coords, int32_t* pb_co
   if (pb_coords || pb_counts) {
     std::vector<int> start(npb + 1);
     CK(cudaMemcpy(start.data(), ctx->pb_start, (size_t)(npb + 1) * 4, cudaMemcpyDeviceToHost));
-    for (int b = 0; b < npb; ++b) {
+    for (int b = 0; b < npb; ++b)
       if (pb_counts) pb_counts[b] = start[b + 1] - start[b];
-      if (pb_coords) {
-        uint32_t key;
-        CK(cudaMemcpy(&key, ctx->last_keys + start[b], 4, cudaMemcpyDeviceToHost));
-        decode_block(ctx, ctx->lastL, key >> ctx->cb, pb_coords + (size_t)b * ctx->dim);
-      }
+    if (pb_coords) {
+      std::vector<uint32_t> pk(npb);
+      CK(cudaMemcpy(pk.data(), ctx->pb_key, (size_t)npb * 4, cudaMemcpyDeviceToHost));
+      for (int b = 0; b < npb; ++b) decode_block(ctx, ctx->lastL, pk[b], pb_coords + (size_t)b * ctx->dim);
     }
   }
   if (gb_coords) {

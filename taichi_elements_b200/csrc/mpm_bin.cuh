@@ -1,0 +1,155 @@
+// Binning (build_pid, /root/reference/engine/mpm_solver.py:344-361) as a
+// single-digit radix (counting) sort on the (leaf block, cell) key.
+//
+// Particles are stored in the previous substep's sorted order and move less
+// than a cell per substep, so a full multi-pass LSD radix sort re-derives an
+// order that is already almost there.  With a dense flag table over the
+// block-aligned particle box (the key layout's eb[0]*eb[1]*eb[2] entries) one
+// pass suffices:
+//   k_bin_keys     key per particle; flag its leaf block and every leaf block
+//                  its 3^D stencil touches (the reference's active-block set)
+//   ExclusiveSum   over [particle-block flags | grid-block flags]: dense slots
+//                  in key order
+//   k_bin_rank     rank of the particle inside its (block, cell) bucket by a
+//                  warp-aggregated atomic counter
+//   ExclusiveSum   over the bucket counts: bucket starts (= block starts and
+//                  the per-cell ranges P2G needs, for free)
+//   k_bin_scatter  perm[start + rank] = particle
+//   k_bin_finish   per particle block: start, key, the 2^D neighbour slots;
+//                  grid-block keys; counts and per-substep status reset
+// Bin index per particle, per-block counts and the active-block set are
+// bit-identical to the oracle; the order inside a cell is arbitrary, as in the
+// reference (ti.append is an atomic).  Boxes too large for the flag table fall
+// back to the multi-pass radix sort in mpm_api.cu.
+#pragma once
+#include "mpm_kernels.cuh"
+
+namespace mpm {
+
+template <int D> __device__ __forceinline__ int oct_delta(const KeyLayout& L, int o) {
+  if constexpr (D == 3) return ((o & 1) ? L.eb[1] * L.eb[2] : 0) + ((o & 2) ? L.eb[2] : 0) + ((o & 4) ? 1 : 0);
+  else return ((o & 1) ? L.eb[1] : 0) + ((o & 2) ? 1 : 0);
+}
+
+__device__ __forceinline__ void commit_substep(Status* st) {
+  if (!st->err) {
+    st->done += 1;
+    if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
+  }
+}
+
+template <int D>
+__global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, KeyLayout L,
+                           uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, int commit_prev,
+                           Status* st) {
+  using G = Geo<D>;
+  if (commit_prev && blockIdx.x == 0 && threadIdx.x == 0) commit_substep(st);
+  if (st->err) return;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
+    uint32_t lin = 0, cell = 0, sp = 0;
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
+      int rel = (g >> G::LOG_LEAF) - L.ob[d];
+      if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
+      lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
+      const uint32_t lc = (uint32_t)(g & (G::LEAF - 1));
+      cell = (cell << G::LOG_LEAF) | lc;
+      sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
+    }
+    keys[p] = (lin << G::CB) | cell;
+    if (bad) { atomicOr(&st->err, ERR_BBOX); continue; }
+    if (flags[lin] == 0) flags[lin] = 1;
+    int* gf = flags + nlin;
+#pragma unroll
+    for (int o = 0; o < G::NO; ++o)
+      if ((o & ~sp) == 0) {
+        const int t = (int)lin + oct_delta<D>(L, o);
+        if (gf[t] == 0) gf[t] = 1;
+      }
+  }
+}
+
+template <int D>
+__global__ void k_bin_rank(const uint32_t* __restrict__ keys, int n, const int* __restrict__ fscan,
+                           int* __restrict__ cellcount, uint32_t* __restrict__ rank, uint32_t* __restrict__ pb_key,
+                           int max_blocks, Status* st) {
+  using G = Geo<D>;
+  if (st->err) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+    const bool valid = p < (uint32_t)n;
+    uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
+    if (valid) {
+      const uint32_t key = keys[p];
+      lin = key >> G::CB;
+      const int b = fscan[lin];
+      if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
+      else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
+    }
+    const bool live = idx < 0xFFFFFF00u;
+    // one atomic per distinct bucket in the warp (neighbouring particles share cells)
+    const unsigned grp = __match_any_sync(0xffffffffu, idx);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (live && lane == leader) base = atomicAdd(&cellcount[idx], __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) {
+      const uint32_t r = (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+      rank[p] = r;
+      if (r == 0) pb_key[idx / G::CELLS] = lin;
+    }
+  }
+}
+
+template <int D>
+__global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, int n,
+                              const int* __restrict__ fscan, const int* __restrict__ cellstart,
+                              uint32_t* __restrict__ perm, const Status* st) {
+  using G = Geo<D>;
+  if (st->err) return;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
+    const uint32_t key = keys[p];
+    const int b = fscan[key >> G::CB];
+    perm[cellstart[(size_t)b * G::CELLS + (key & (G::CELLS - 1))] + rank[p]] = p;
+  }
+}
+
+template <int D>
+__global__ void k_bin_finish(const int* __restrict__ flags, const int* __restrict__ fscan, int nlin, KeyLayout L,
+                             const uint32_t* __restrict__ pb_key, const int* __restrict__ cellstart,
+                             int* __restrict__ pb_start, int* __restrict__ pb_nbr, uint32_t* __restrict__ gb_key,
+                             int n, int max_blocks, Status* st) {
+  using G = Geo<D>;
+  if (st->err) return;
+  const int npb = fscan[nlin];
+  const int ngb = fscan[2 * nlin] - npb;
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+  if (first && max(npb, ngb) > st->need_blocks) st->need_blocks = max(npb, ngb);
+  if (npb > max_blocks || ngb > max_blocks) {
+    if (first) st->err |= ERR_BLOCK_CAPACITY;
+    return;
+  }
+  if (first) {
+    st->npb = npb; st->ngb = ngb; st->ngb_raw = ngb;
+    pb_start[npb] = n;
+    st->work_p2g = 0; st->work_g2p = 0;
+    st->maxv_bits = 0;
+    for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npb * G::NO; i += gridDim.x * blockDim.x) {
+    const int b = i / G::NO, o = i % G::NO;
+    const int t = (int)pb_key[b] + oct_delta<D>(L, o);
+    int slot = -1;
+    if (flags[nlin + t]) {
+      slot = fscan[nlin + t] - npb;
+      gb_key[slot] = (uint32_t)t;
+    }
+    pb_nbr[i] = slot;
+    if (o == 0) pb_start[b] = cellstart[(size_t)b * G::CELLS];
+  }
+}
+
+}  // namespace mpm

@@ -160,7 +160,7 @@ __global__ void k_pb_finalize(Status* st, int* pb_start, int n, int max_blocks) 
 template <int D>
 __global__ void k_pb_masks(const uint32_t* __restrict__ keys, const int* __restrict__ pb_start,
                            KeyLayout L, int max_blocks, uint32_t* __restrict__ pb_mask,
-                           uint32_t* __restrict__ cand, Status* st) {
+                           uint32_t* __restrict__ cand, uint32_t* __restrict__ pb_key, Status* st) {
   using G = Geo<D>;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -186,7 +186,7 @@ __global__ void k_pb_masks(const uint32_t* __restrict__ keys, const int* __restr
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-      if (lane == 0) pb_mask[b] = m;
+      if (lane == 0) { pb_mask[b] = m; pb_key[b] = keys[start] >> G::CB; }
       if (lane < G::NO && ((m >> lane) & 1u)) {
         int rel[D];
         key_to_rel<D>(L, keys[start] >> G::CB, rel);
@@ -267,6 +267,8 @@ template <int D> struct SubstepArgs {
   const uint32_t* perm;  // sorted position -> slot in src
   const int* pb_start;
   const int* pb_nbr;
+  const uint32_t* pb_key;   // linear leaf-block key of each particle block
+  const int* cellstart;     // [npb*CELLS+1] first sorted position of every cell (counting-sort path), or null
   float4* grid;
   Status* st;
   KeyLayout L;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
     int org[D];   // absolute cell coordinate of the block origin
     {
       int rel[D];
-      key_to_rel<D>(a.L, a.keys[start] >> G::CB, rel);
+      key_to_rel<D>(a.L, a.pb_key[b], rel);
 #pragma unroll
       for (int d = 0; d < D; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
     }
@@ -481,9 +483,8 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
 // Gather from the staged velocity tile, update v, C, x (engine/mpm_solver.py:
 // 694-724), write the particle to its sorted slot in the other state set, and
 // fold compute_max_velocity (:726-735) and the next bounding box into the pass.
-constexpr int G2P_THREADS = 256;
-template <int D>
-__global__ void __launch_bounds__(G2P_THREADS) k_g2p(SubstepArgs<D> a) {
+template <int D, int G2P_THREADS, int G2P_MINB>
+__global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
   __shared__ float4 tile[G::TN];
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(SubstepArgs<D> a) {
     int org[D];
     {
       int rel[D];
-      key_to_rel<D>(a.L, a.keys[start] >> G::CB, rel);
+      key_to_rel<D>(a.L, a.pb_key[b], rel);
 #pragma unroll
       for (int d = 0; d < D; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
     }

@@ -66,13 +66,18 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
     const int cnt = end - start;
     for (int n = tid; n < P::SL * G::TN; n += T) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
-    // phase 0: first sorted position of every cell (keys are sorted by block, then cell)
-    for (int q = tid; q < cnt; q += T) {
-      const int c = (int)(a.keys[start + q] & (G::CELLS - 1));
-      const int cp = q > 0 ? (int)(a.keys[start + q - 1] & (G::CELLS - 1)) : -1;
-      for (int k = cp + 1; k <= c; ++k) cs[k] = q;
-      if (q == cnt - 1)
-        for (int k = c + 1; k <= G::CELLS; ++k) cs[k] = cnt;
+    // phase 0: first sorted position of every cell of the block: straight from the
+    // counting sort's bucket starts, or (radix fallback) from the sorted keys
+    if (a.cellstart) {
+      for (int c = tid; c <= G::CELLS; c += T) cs[c] = a.cellstart[(size_t)b * G::CELLS + c] - start;
+    } else {
+      for (int q = tid; q < cnt; q += T) {
+        const int c = (int)(a.keys[start + q] & (G::CELLS - 1));
+        const int cp = q > 0 ? (int)(a.keys[start + q - 1] & (G::CELLS - 1)) : -1;
+        for (int k = cp + 1; k <= c; ++k) cs[k] = q;
+        if (q == cnt - 1)
+          for (int k = c + 1; k <= G::CELLS; ++k) cs[k] = cnt;
+      }
     }
     __syncthreads();
     // Balance phase 2: a warp's trip count is the largest cell count among its

@@ -104,22 +104,33 @@ def test_multi_substep_tracking(dim):
     assert np.isfinite(s.x.to_numpy()).all()
 
 
-def test_p2g_variants_agree():
-    """The cell-owner P2G and the first shared-atomic P2G give the same grid."""
+def _run_variant(env_extra, tag):
     import os
     import subprocess
     import sys
     code = (
         "import sys, numpy as np; sys.path.insert(0, 'tests');"
         "from scenes import build_pair, mixed_scene;"
-        "o, s = build_pair(3, mixed_scene(3, seed=5));"
+        "o, s = build_pair(3, mixed_scene(3, seed=5), unbounded=True);"
         "s._run_substeps(o.default_dt, 3);"
-        "np.save(sys.argv[1], s.v.to_numpy())")
-    outs = []
-    for variant in ('atomic', 'cell'):
-        fn = f'/tmp/p2g_{variant}.npy'
-        env = dict(os.environ, MPM_P2G=variant)
-        subprocess.run([sys.executable, '-c', code, fn], check=True, env=env,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        outs.append(np.load(fn))
-    assert np.abs(outs[0] - outs[1]).max() <= 1e-3 * max(1.0, np.abs(outs[0]).max())
+        "pb, cnt, gb = s.debug_blocks();"
+        "np.savez(sys.argv[1], v=s.v.to_numpy(), x=s.x.to_numpy(), pb=pb[np.lexsort(pb.T[::-1])], "
+        "gb=gb[np.lexsort(gb.T[::-1])], cnt=np.sort(cnt))")
+    fn = f'/tmp/variant_{tag}.npz'
+    env = dict(os.environ, **env_extra)
+    subprocess.run([sys.executable, '-c', code, fn], check=True, env=env,
+                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    return np.load(fn)
+
+
+def test_kernel_variants_agree():
+    """Default build (counting-sort binning, cell-owner P2G) against the radix-sort
+    fallback and the first shared-atomic P2G: same block structure, same physics."""
+    base = _run_variant({}, 'default')
+    for tag, env in (('radix', {'MPM_SORT': 'radix'}), ('atomic', {'MPM_P2G': 'atomic'})):
+        alt = _run_variant(env, tag)
+        assert np.array_equal(base['pb'], alt['pb']) and np.array_equal(base['gb'], alt['gb'])
+        assert np.array_equal(base['cnt'], alt['cnt'])
+        scale = max(1.0, float(np.abs(base['v']).max()))
+        assert np.abs(base['v'] - alt['v']).max() <= 1e-3 * scale
+        assert np.abs(base['x'] - alt['x']).max() <= 1e-5
