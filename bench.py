@@ -36,14 +36,22 @@ def workload(name, rank=0, world=1, seed=2):
         side, res = 0.16, 256
     elif name == 'cube_drop_small':      # smoke-sized
         side, res = 0.0625, 256
+    elif name == 'cube_drop_32m':        # 2 x 128^3 cells x 8 at res 512
+        side, res = 0.25, 512
+    elif name == 'cube_drop_100m':       # 2 x 184^3 cells x 8 = 99.7 M at res 512
+        side, res = 0.359375, 512
     else:
         raise ValueError(name)
     n_side = int(round(side * res))
     n_each = n_side**3 * 8               # 8 particles per cell
     lo_e = np.array([0.5 - side / 2, 0.55, 0.5 - side / 2], np.float32)
     lo_w = np.array([0.5 - side / 2, 0.15, 0.5 - side / 2], np.float32)
-    xe = (rng.random((n_each, 3), dtype=np.float32) * np.float32(side) + lo_e).astype(np.float32)
-    xw = (rng.random((n_each, 3), dtype=np.float32) * np.float32(side) + lo_w).astype(np.float32)
+    xe = rng.random((n_each, 3), dtype=np.float32)
+    xe *= np.float32(side)
+    xe += lo_e
+    xw = rng.random((n_each, 3), dtype=np.float32)
+    xw *= np.float32(side)
+    xw += lo_w
     return dict(res=(res, ) * 3, gravity=(0, -20, 0), frame_dt=3e-3, parts=[(xe, 1), (xw, 0)],
                 n=2 * n_each, name=name)
 
@@ -195,6 +203,8 @@ def main():
         mpm.add_particles(x, m)
     n_local = mpm.n_particles[None]
     dt = w['frame_dt'] / (int(w['frame_dt'] / mpm.default_dt) + 1)
+    if w['res'][0] != 256:
+        dt = mpm.default_dt
     lib, ctx = mpm._lib, mpm._ctx
     stream = torch.cuda.current_stream(dev)
 

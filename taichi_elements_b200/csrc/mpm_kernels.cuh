@@ -498,11 +498,12 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
   int lo[D], hi[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) { lo[d] = INT_MAX; hi[d] = INT_MIN; }
-  for (;;) {
-    if (tid == 0) s_b = atomicAdd(&a.st->work_g2p, 1);
-    __syncthreads();
-    const int b = s_b;
-    if (b >= npb) break;
+  __shared__ int s_next;
+  if (tid == 0) s_b = atomicAdd(&a.st->work_g2p, 1);
+  __syncthreads();
+  int b = s_b;
+  while (b < npb) {
+    if (tid == 0) s_next = atomicAdd(&a.st->work_g2p, 1);   // one block ahead, for the prefetch below
     const int start = a.pb_start[b], end = a.pb_start[b + 1];
     if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
     int org[D];
@@ -520,6 +521,24 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       tile[n] = slot >= 0 ? a.grid[(size_t)slot * G::CELLS + cell] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
+    {   // next block's particle rows and grid tiles towards L2 while this one computes
+      const int nb = s_next;
+      if (nb < npb) {
+        const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
+        const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
+        for (int i = tid; i < 8 * lines; i += G2P_THREADS) {
+          const int k = i / lines, l = i % lines;
+          const int f = k < D ? FL::X + k : (k == 3 ? FL::MAT : (k == 4 ? FL::COLOR : (k == 5 ? FL::ID : FL::EMIT)));
+          if (k == 7 || (D == 2 && k == 2)) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.perm + ns + l * 32)); continue; }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.src + (size_t)f * cap + ns + l * 32));
+        }
+        for (int i = tid; i < G::NO * (G::CELLS * 16 / 128); i += G2P_THREADS) {
+          const int o = i / (G::CELLS * 16 / 128), l = i % (G::CELLS * 16 / 128);
+          const int slot = a.pb_nbr[nb * G::NO + o];
+          if (slot >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.grid + (size_t)slot * G::CELLS + l * 8));
+        }
+      }
+    }
     for (int s = start + tid; s < end; s += G2P_THREADS) {
       const uint32_t p = a.perm[s];
       float x[D], fx[D], w[3][D];
@@ -628,6 +647,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       stu(a.dst, cap, FL::ID, s, ldu(a.src, cap, FL::ID, p));
       stu(a.dst, cap, FL::EMIT, s, ldu(a.src, cap, FL::EMIT, p));
     }
+    b = s_next;
     __syncthreads();
   }
   // CTA-wide reductions, once per CTA lifetime

@@ -57,11 +57,12 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
   const int sl = tid % P::SL;
   __shared__ int s_order[G::CELLS];                                   // cells by descending particle count
 
-  for (;;) {
-    if (tid == 0) s_b = atomicAdd(&a.st->work_p2g, 1);
-    __syncthreads();
-    const int b = s_b;
-    if (b >= npb) break;
+  __shared__ int s_next;
+  if (tid == 0) s_b = atomicAdd(&a.st->work_p2g, 1);
+  __syncthreads();
+  int b = s_b;
+  while (b < npb) {
+    if (tid == 0) s_next = atomicAdd(&a.st->work_p2g, 1);   // claimed one block ahead, for the prefetch below
     const int start = a.pb_start[b], end = a.pb_start[b + 1];
     const int cnt = end - start;
     for (int n = tid; n < P::SL * G::TN; n += T) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,6 +137,21 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
         pay[(2 * D + D * D) * CH + q] = mass;
       }
       __syncthreads();
+      // While this block's arithmetic runs, pull the next block's particle state
+      // towards L2.  Storage order is last substep's sorted order, so the rows
+      // [start, end) of the next block are (almost) where `perm` will point.
+      if (c0 == 0) {
+        const int nb = s_next;
+        if (nb < npb) {
+          const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
+          const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
+          for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
+            const int f = i / lines, l = i % lines;
+            const uint32_t* ptr = (f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + l * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      }
       // ---- phase 2: per-(cell, slice) register accumulation
       float acc[P::NPT][D + 1];
 #pragma unroll
@@ -223,6 +239,7 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
         if (slot >= 0) red_add_v4(a.grid + (size_t)slot * G::CELLS + cellg, val);
       }
     }
+    b = s_next;
     __syncthreads();
   }
 }
