@@ -154,6 +154,40 @@ int mpm_download(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* 
 int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream);
 
 
+
+/* ---- multi-GPU slab decomposition along x (no reference counterpart: the
+ * reference is single-device; SURVEY.md 8(e), DESIGN.md "Multi-GPU") ----
+ * One process per GPU.  A rank owns leaf-block columns [lo, hi) (absolute block
+ * x = (cell + grid_size/2) / leaf).  The host interleaves these phase calls with
+ * the two neighbour exchanges (NCCL send/recv of the fixed-capacity buffers):
+ *   mpm_batch_begin
+ *   per substep: [exchange migration buffers] mpm_phase_unpack, mpm_phase_p2g,
+ *                mpm_phase_halo_pack, [exchange halo buffers], mpm_phase_halo_add,
+ *                mpm_phase_g2p
+ *   mpm_batch_end        (the only host synchronisation)
+ * Message buffers (device, 32-bit words): 16-word header (word 0 = count), then
+ *   migration: [field][capacity] rows of the particle state layout above
+ *   halo:      keys[capacity] ((by << 16) | bz), then records[capacity][cells] float4 */
+int mpm_set_slab(mpm_ctx* ctx, int32_t enabled, int32_t lo_block, int32_t hi_block);
+/* bytes of a message buffer: kind 0 = migration (capacity in particles), 1 = halo (capacity in leaf blocks) */
+size_t mpm_comm_bytes(int32_t dim, int32_t kind, int32_t capacity);
+/* send buffers of the -x (lo) and +x (hi) side; NULL where there is no neighbour */
+int mpm_bind_comm(mpm_ctx* ctx, void* mig_lo_dev, void* mig_hi_dev, int32_t mig_capacity, void* halo_lo_dev,
+                  void* halo_hi_dev, int32_t halo_capacity);
+/* particle base-cell bounding box of this rank (INT_MAX/INT_MIN when it holds none); synchronises */
+int mpm_get_bbox(mpm_ctx* ctx, int32_t* bb_min, int32_t* bb_max, void* stream);
+/* key-layout box common to all ranks (the all-reduced bounding box), global signed cell indices */
+int mpm_set_layout_box(mpm_ctx* ctx, int32_t enabled, const int32_t* bb_min, const int32_t* bb_max);
+int mpm_batch_begin(mpm_ctx* ctx, void* stream);
+int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo_dev, const void* from_hi_dev, void* stream);
+int mpm_phase_p2g(mpm_ctx* ctx, double dt, void* stream);
+int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream);
+int mpm_phase_halo_add(mpm_ctx* ctx, const void* from_lo_dev, const void* from_hi_dev, void* stream);
+int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream);
+int mpm_batch_end(mpm_ctx* ctx, void* stream);
+/* rows [0, n) of one state word in storage order (pair with the `id` word) */
+int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream);
+
 /* ---- mesh seeding (setup path of add_mesh, engine/mpm_solver.py:1049-1079) ---- */
 /* Voxelizer.voxelize_triangles (engine/voxelizer.py:46-109): signed winding
  * count per voxel of the super-sampled grid, rasterised in f64.  `res` is the

@@ -83,6 +83,19 @@ SYMBOLS = [
     ('mpm_set_profiling', _i32, [_vp, _i32]),
     ('mpm_download', _i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     ('mpm_gather', _i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
+    ('mpm_set_slab', _i32, [_vp, _i32, _i32, _i32]),
+    ('mpm_comm_bytes', ctypes.c_size_t, [_i32, _i32, _i32]),
+    ('mpm_bind_comm', _i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32]),
+    ('mpm_get_bbox', _i32, [_vp, _vp, _vp, _vp]),
+    ('mpm_set_layout_box', _i32, [_vp, _i32, _vp, _vp]),
+    ('mpm_batch_begin', _i32, [_vp, _vp]),
+    ('mpm_phase_unpack', _i32, [_vp, _vp, _vp, _vp]),
+    ('mpm_phase_p2g', _i32, [_vp, _dbl, _vp]),
+    ('mpm_phase_halo_pack', _i32, [_vp, _vp]),
+    ('mpm_phase_halo_add', _i32, [_vp, _vp, _vp, _vp]),
+    ('mpm_phase_g2p', _i32, [_vp, _dbl, _vp]),
+    ('mpm_batch_end', _i32, [_vp, _vp]),
+    ('mpm_download_raw', _i32, [_vp, _i32, _vp, _vp]),
     ('mpm_voxelize', _i32, [_i32, _vp, _i64, _vp, _dbl, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_voxel_sample', _i32, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dp, _i32, _i32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_debug_binning', _i32, [_vp, _vp, _vp]),

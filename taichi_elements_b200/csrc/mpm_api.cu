@@ -13,6 +13,7 @@
 
 #include "../../include/mpm_b200.h"
 #include "mpm_bin.cuh"
+#include "mpm_comm.cuh"
 #include "mpm_p2g.cuh"
 
 using namespace mpm;
@@ -39,6 +40,16 @@ struct mpm_ctx {
   int *flags = nullptr, *fscan = nullptr, *cellcount = nullptr, *cellstart = nullptr;
   int64_t table_cap = 0;
   bool dense = false;   // counting-sort path usable for the current layout
+  Slab slab{0, INT_MIN, INT_MAX};
+  CommBufs comm{{nullptr, nullptr}, {nullptr, nullptr}, 0, 0};
+  bool ext_box = false;          // layout box supplied by the host (global box of all ranks)
+  int box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
+  // state of the batch being enqueued (phase API)
+  bool in_batch = false;
+  int batch_cur0 = 0, batch_enq = 0;
+  const uint32_t* cur_keys = nullptr;
+  const uint32_t* cur_perm = nullptr;
+  const int* cur_cellstart = nullptr;
   int use_dense = 1;
   float4* grid = nullptr;
   Status* h_status = nullptr;   // pinned
@@ -392,12 +403,14 @@ static int refresh_bbox(mpm_ctx* ctx, cudaStream_t s) {
 // the number of radix passes) only changes when particles approach its faces.
 static int update_layout(mpm_ctx* ctx) {
   const int half = ctx->P.grid_size / 2, ll = ctx->log_leaf;
-  const int MARGIN = 2;
-  bool keep = ctx->layout_valid;
+  const int MARGIN = ctx->slab.enabled ? 3 : 2;
+  bool keep = ctx->layout_valid && !ctx->slab.enabled && !ctx->ext_box;
   int bmin[3], bmax[3];
   for (int d = 0; d < ctx->dim; ++d) {
-    bmin[d] = (ctx->bb_min[d] + half) >> ll;
-    bmax[d] = (ctx->bb_max[d] + half) >> ll;
+    const int lo = ctx->ext_box ? ctx->box_min[d] : ctx->bb_min[d];
+    const int hi = ctx->ext_box ? ctx->box_max[d] : ctx->bb_max[d];
+    bmin[d] = (lo + half) >> ll;
+    bmax[d] = (hi + half) >> ll;
     if (keep && !(bmin[d] >= ctx->L.ob[d] + 1 && bmax[d] <= ctx->L.ob[d] + ctx->L.eb[d] - 3)) keep = false;
   }
   if (!keep) {
@@ -406,8 +419,15 @@ static int update_layout(mpm_ctx* ctx) {
     double prod = 1.0;
     for (int d = 0; d < 3; ++d) { L.ob[d] = 0; L.eb[d] = 1; }
     for (int d = 0; d < ctx->dim; ++d) {
-      L.ob[d] = bmin[d] - MARGIN;
-      L.eb[d] = (bmax[d] + MARGIN + 1) - L.ob[d] + 1;
+      int first = bmin[d] - MARGIN, last = bmax[d] + MARGIN;   // particle blocks covered
+      if (d == 0 && ctx->slab.enabled) {
+        // this rank only bins blocks of its slab; +1 ring below covers the shared column `hi`
+        if (ctx->slab.lo > INT_MIN / 2) first = std::max(first, ctx->slab.lo);
+        if (ctx->slab.hi < INT_MAX / 2) last = std::min(last, ctx->slab.hi - 1);
+        if (last < first) last = first;
+      }
+      L.ob[d] = first;
+      L.eb[d] = (last + 1) - first + 1;
       prod *= (double)L.eb[d];
     }
     int bits = 0;
@@ -450,14 +470,25 @@ static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
 }
 
 template <int D>
-static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
+static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
+  SubstepArgs<D> a{};
+  a.src = ctx->state[cur]; a.dst = ctx->state[cur ^ 1]; a.cap = ctx->cap;
+  a.keys = ctx->cur_keys; a.perm = ctx->cur_perm;
+  a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = ctx->d_status;
+  a.pb_key = ctx->pb_key; a.cellstart = ctx->cur_cellstart;
+  a.L = ctx->L; a.K = ctx->K; a.dt = dt;
+  a.slab = ctx->slab; a.cb = ctx->comm;
+  return a;
+}
+
+template <int D>
+static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
   const bool prof = ev != nullptr;
   using G = Geo<D>;
   const int n = (int)ctx->n;
   const int sm = ctx->sm_count;
   Status* st = ctx->d_status;
   const uint32_t* src = ctx->state[cur];
-  uint32_t* dst = ctx->state[cur ^ 1];
   if (prof) cudaEventRecord(ev[0], s);
   const uint32_t* keys = nullptr;
   const uint32_t* perm = nullptr;
@@ -470,17 +501,17 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     const int ncell = ctx->max_blocks * G::CELLS + 1;
     CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
     CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
-    k_bin_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->flags,
+    k_bin_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
                                                        nlin, commit_prev, st);
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
-    k_bin_rank<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, n, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
+    k_bin_rank<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
                                                        ctx->max_blocks, st);
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->cellcount, ctx->cellstart, ncell, s));
-    k_bin_scatter<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, n, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
+    k_bin_scatter<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
     k_bin_finish<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(
-        ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr, ctx->gb_key, n,
+        ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr, ctx->gb_key,
         ctx->max_blocks, st);
     keys = ctx->keys_a;
     perm = ctx->vals_b;
@@ -516,23 +547,41 @@ static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
   }
   k_clear_grid<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(ctx->grid, st);
   if (prof) cudaEventRecord(ev[1], s);
-  SubstepArgs<D> a{};
-  a.src = src; a.dst = dst; a.cap = ctx->cap; a.keys = keys; a.perm = perm;
-  a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = st;
-  a.pb_key = ctx->pb_key; a.cellstart = cellstart;
-  a.L = ctx->L; a.K = ctx->K; a.dt = dt;
+  ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
+  SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
   if (ctx->p2g_variant == 0) k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
   else k_p2g_cell<D><<<ctx->grid_p2g_cell, P2GCfg<D>::THREADS, p2g_smem_bytes<D>(), s>>>(a);
   if (prof) cudaEventRecord(ev[2], s);
+  CK(cudaGetLastError());
+  ctx->launches += 2;   // clear, p2g; CUB's internal launches are not counted
+  ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
+  ctx->last_keys = keys;
+  return MPM_OK;
+}
+
+template <int D>
+static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
+  using G = Geo<D>;
+  const bool prof = ev != nullptr;
+  const int sm = ctx->sm_count;
+  Status* st = ctx->d_status;
+  SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
   k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
       ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
   if (prof) cudaEventRecord(ev[3], s);
   launch_g2p<D>(ctx, a, s);
+  if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, st); ctx->launches += 1; }
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
-  ctx->launches += 4;   // clear, p2g, grid op, g2p; CUB's internal launches are not counted
-  ctx->last_keys = keys;
+  ctx->launches += 2;   // grid op, g2p
   return MPM_OK;
+}
+
+template <int D>
+static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
+  int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, ev);
+  if (rc) return rc;
+  return enqueue_grid_g2p<D>(ctx, dt, cur, s, ev);
 }
 
 extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, void* stream) {
@@ -552,6 +601,7 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     rc = update_layout(ctx);
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+    k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
     const int cur0 = ctx->cur;
     const bool prof = ctx->profiling && count <= 4096;
     if (prof)
@@ -611,6 +661,203 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
 
 extern "C" int mpm_substep(mpm_ctx* ctx, double dt, double t, void* stream) {
   return mpm_substeps(ctx, dt, t, 1, stream);
+}
+
+
+// ------------------------------------------------------------------ phase API (multi-GPU driver)
+extern "C" int mpm_set_slab(mpm_ctx* ctx, int32_t enabled, int32_t lo_block, int32_t hi_block) {
+  if (!ctx || (enabled && lo_block >= hi_block)) return fail(ctx, MPM_E_INVALID, "mpm_set_slab: empty slab");
+  ctx->slab.enabled = enabled ? 1 : 0;
+  ctx->slab.lo = enabled ? lo_block : INT_MIN;
+  ctx->slab.hi = enabled ? hi_block : INT_MAX;
+  ctx->layout_valid = false;
+  return MPM_OK;
+}
+
+extern "C" size_t mpm_comm_bytes(int32_t dim, int32_t kind, int32_t capacity) {
+  if ((dim != 2 && dim != 3) || capacity < 0) return 0;
+  const size_t nf = (size_t)mpm_state_fields(dim), cells = dim == 3 ? 64 : 256;
+  if (kind == 0) return 4 * (COMM_HEADER + nf * (size_t)capacity);
+  return 4 * (COMM_HEADER + (size_t)capacity + (size_t)capacity * cells * 4);
+}
+
+extern "C" int mpm_bind_comm(mpm_ctx* ctx, void* mig_lo, void* mig_hi, int32_t mig_cap, void* halo_lo, void* halo_hi,
+                             int32_t halo_cap) {
+  if (!ctx || mig_cap < 0 || halo_cap < 0) return MPM_E_INVALID;
+  ctx->comm.mig[0] = (uint32_t*)mig_lo; ctx->comm.mig[1] = (uint32_t*)mig_hi; ctx->comm.mig_cap = mig_cap;
+  ctx->comm.halo[0] = (uint32_t*)halo_lo; ctx->comm.halo[1] = (uint32_t*)halo_hi; ctx->comm.halo_cap = halo_cap;
+  return MPM_OK;
+}
+
+extern "C" int mpm_get_bbox(mpm_ctx* ctx, int32_t* bb_min, int32_t* bb_max, void* stream) {
+  if (!ctx || !bb_min || !bb_max) return MPM_E_INVALID;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  CK(cudaSetDevice(ctx->P.device));
+  if (ctx->n == 0) {
+    for (int d = 0; d < 3; ++d) { bb_min[d] = INT_MAX; bb_max[d] = INT_MIN; }
+    return MPM_OK;
+  }
+  int rc = refresh_bbox(ctx, (cudaStream_t)stream);
+  if (rc) return rc;
+  for (int d = 0; d < 3; ++d) { bb_min[d] = ctx->bb_min[d]; bb_max[d] = ctx->bb_max[d]; }
+  return MPM_OK;
+}
+
+extern "C" int mpm_set_layout_box(mpm_ctx* ctx, int32_t enabled, const int32_t* bb_min, const int32_t* bb_max) {
+  if (!ctx || (enabled && (!bb_min || !bb_max))) return MPM_E_INVALID;
+  ctx->ext_box = enabled != 0;
+  for (int d = 0; d < 3 && enabled; ++d) { ctx->box_min[d] = bb_min[d]; ctx->box_max[d] = bb_max[d]; }
+  ctx->layout_valid = false;
+  return MPM_OK;
+}
+
+extern "C" int mpm_batch_begin(mpm_ctx* ctx, void* stream) {
+  if (!ctx) return MPM_E_INVALID;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ctx->launches = 0;
+  ctx->done_last = 0;
+  int rc = upload_colliders(ctx, s);
+  if (rc) return rc;
+  if (!ctx->ext_box) {
+    if (ctx->n == 0) return fail(ctx, MPM_E_INVALID, "mpm_batch_begin: no particles and no layout box");
+    rc = refresh_bbox(ctx, s);
+    if (rc) return rc;
+  }
+  rc = update_layout(ctx);
+  if (rc) return rc;
+  if (!ctx->dense) return fail(ctx, MPM_E_INVALID, "phase API needs the counting-sort path (box too large for the flag table)");
+  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
+  ctx->in_batch = true;
+  ctx->batch_cur0 = ctx->cur;
+  ctx->batch_enq = 0;
+  return MPM_OK;
+}
+
+#define REQUIRE_BATCH()                                                                   \
+  if (!ctx) return MPM_E_INVALID;                                                         \
+  if (!ctx->in_batch) return fail(ctx, MPM_E_INVALID, "phase call outside mpm_batch_begin/end"); \
+  CK(cudaSetDevice(ctx->P.device));                                                       \
+  cudaStream_t s = (cudaStream_t)stream;
+
+extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* from_hi, void* stream) {
+  REQUIRE_BATCH();
+  if (!from_lo && !from_hi) return MPM_OK;
+  const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
+  const int blocks = gs_blocks((int64_t)ctx->comm.mig_cap * ctx->nf, 256, ctx->sm_count);
+  if (ctx->dim == 3)
+    k_mig_unpack<3><<<blocks, 256, 0, s>>>(ctx->state[cur], ctx->cap, (const uint32_t*)from_lo, (const uint32_t*)from_hi,
+                                           ctx->comm.mig_cap, ctx->d_status);
+  else
+    k_mig_unpack<2><<<blocks, 256, 0, s>>>(ctx->state[cur], ctx->cap, (const uint32_t*)from_lo, (const uint32_t*)from_hi,
+                                           ctx->comm.mig_cap, ctx->d_status);
+  k_mig_commit<<<1, 1, 0, s>>>((const uint32_t*)from_lo, (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  return MPM_OK;
+}
+
+extern "C" int mpm_phase_p2g(mpm_ctx* ctx, double dt, void* stream) {
+  REQUIRE_BATCH();
+  const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
+  return ctx->dim == 3 ? enqueue_bin_p2g<3>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, nullptr)
+                       : enqueue_bin_p2g<2>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, nullptr);
+}
+
+extern "C" int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream) {
+  REQUIRE_BATCH();
+  if (!ctx->slab.enabled) return MPM_OK;
+  const int blocks = gs_blocks((int64_t)ctx->max_blocks * 32, 256, ctx->sm_count);
+  for (int side = 0; side < 2; ++side) {
+    if (!ctx->comm.halo[side]) continue;
+    const int bx = side == 0 ? ctx->slab.lo : ctx->slab.hi;
+    if (ctx->dim == 3)
+      k_halo_pack<3><<<blocks, 256, 0, s>>>(ctx->grid, ctx->gb_key, ctx->L, bx, ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status);
+    else
+      k_halo_pack<2><<<blocks, 256, 0, s>>>(ctx->grid, ctx->gb_key, ctx->L, bx, ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status);
+    ctx->launches += 1;
+  }
+  k_halo_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->d_status);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
+extern "C" int mpm_phase_halo_add(mpm_ctx* ctx, const void* from_lo, const void* from_hi, void* stream) {
+  REQUIRE_BATCH();
+  if (!ctx->slab.enabled) return MPM_OK;
+  int nlin = 1;
+  for (int d = 0; d < ctx->dim; ++d) nlin *= ctx->L.eb[d];
+  const int blocks = gs_blocks((int64_t)ctx->comm.halo_cap * 32, 256, ctx->sm_count);
+  const void* from[2] = {from_lo, from_hi};
+  for (int side = 0; side < 2; ++side) {
+    if (!from[side]) continue;
+    const int bx = side == 0 ? ctx->slab.lo : ctx->slab.hi;
+    if (ctx->dim == 3)
+      k_halo_add<3><<<blocks, 256, 0, s>>>(ctx->grid, ctx->flags, ctx->fscan, nlin, ctx->L, bx, (const uint32_t*)from[side], ctx->comm.halo_cap, ctx->d_status);
+    else
+      k_halo_add<2><<<blocks, 256, 0, s>>>(ctx->grid, ctx->flags, ctx->fscan, nlin, ctx->L, bx, (const uint32_t*)from[side], ctx->comm.halo_cap, ctx->d_status);
+    ctx->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
+extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
+  REQUIRE_BATCH();
+  const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
+  int rc = ctx->dim == 3 ? enqueue_grid_g2p<3>(ctx, (float)dt, cur, s, nullptr)
+                         : enqueue_grid_g2p<2>(ctx, (float)dt, cur, s, nullptr);
+  if (rc) return rc;
+  ctx->batch_enq += 1;
+  return MPM_OK;
+}
+
+extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
+  REQUIRE_BATCH();
+  ctx->in_batch = false;
+  k_end<<<1, 1, 0, s>>>(ctx->d_status);
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const Status& h = *ctx->h_status;
+  ctx->cur = ctx->batch_cur0 ^ (h.done & 1);
+  ctx->done_last = h.done;
+  if (h.done > 0) {
+    ctx->last = h;
+    ctx->lastL = ctx->L;
+    ctx->last_valid = (h.err == 0);
+  }
+  ctx->bbox_valid = false;
+  if (!h.err) {
+    ctx->n = h.n_cur;
+    if (h.n_cur > 0 && h.done > 0) {
+      for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = h.bb_min[d]; ctx->bb_max[d] = h.bb_max[d]; }
+      ctx->bbox_valid = true;
+    }
+    return MPM_OK;
+  }
+  ctx->layout_valid = false;
+  char buf[200];
+  snprintf(buf, sizeof buf, "batch stopped after %d of %d substeps: device error bits 0x%x (1 block capacity %d/%d, 2 box, "
+           "4 message capacity, 8 particle capacity)", h.done, ctx->batch_enq, h.err, h.need_blocks, ctx->max_blocks);
+  ctx->err = buf;
+  if (h.err == ERR_BLOCK_CAPACITY) { ctx->last.need_blocks = h.need_blocks; return MPM_E_BLOCK_CAPACITY; }
+  return MPM_E_INVALID;
+}
+
+// local rows [0, n) of one state word in storage order (no id un-permutation)
+extern "C" int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream) {
+  if (!ctx || field < 0 || field >= ctx->nf) return MPM_E_INVALID;
+  if (ctx->n == 0) return MPM_OK;
+  if (!dst_host) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(dst_host, ctx->state[ctx->cur] + (size_t)field * ctx->cap, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return MPM_OK;
 }
 
 extern "C" int mpm_get_stats(mpm_ctx* ctx, mpm_stats* o) {

@@ -39,18 +39,20 @@ __device__ __forceinline__ void commit_substep(Status* st) {
 }
 
 template <int D>
-__global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, KeyLayout L,
+__global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float inv_dx, KeyLayout L, Slab slab,
                            uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, int commit_prev,
                            Status* st) {
   using G = Geo<D>;
   if (commit_prev && blockIdx.x == 0 && threadIdx.x == 0) commit_substep(st);
   if (st->err) return;
+  const int n = st->n_cur;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
     uint32_t lin = 0, cell = 0, sp = 0;
-    bool bad = false;
+    bool bad = false, mine = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
+      if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = bx >= slab.lo && bx < slab.hi; }
       int rel = (g >> G::LOG_LEAF) - L.ob[d];
       if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
       lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
@@ -58,6 +60,9 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, int n
       cell = (cell << G::LOG_LEAF) | lc;
       sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
     }
+    // a particle whose base block left this rank's slab has already been handed
+    // to the neighbour (G2P packs it): it is dropped from the local sort
+    if (!mine) { keys[p] = INVALID_KEY; continue; }
     keys[p] = (lin << G::CB) | cell;
     if (bad) { atomicOr(&st->err, ERR_BBOX); continue; }
     if (flags[lin] == 0) flags[lin] = 1;
@@ -72,18 +77,19 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, int n
 }
 
 template <int D>
-__global__ void k_bin_rank(const uint32_t* __restrict__ keys, int n, const int* __restrict__ fscan,
+__global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restrict__ fscan,
                            int* __restrict__ cellcount, uint32_t* __restrict__ rank, uint32_t* __restrict__ pb_key,
                            int max_blocks, Status* st) {
   using G = Geo<D>;
   if (st->err) return;
+  const int n = st->n_cur;
   const int lane = threadIdx.x & 31;
   const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
     const bool valid = p < (uint32_t)n;
     uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
-    if (valid) {
-      const uint32_t key = keys[p];
+    const uint32_t key = valid ? keys[p] : INVALID_KEY;
+    if (key != INVALID_KEY) {
       lin = key >> G::CB;
       const int b = fscan[lin];
       if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
@@ -105,13 +111,15 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, int n, const int* 
 }
 
 template <int D>
-__global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, int n,
+__global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
                               const int* __restrict__ fscan, const int* __restrict__ cellstart,
                               uint32_t* __restrict__ perm, const Status* st) {
   using G = Geo<D>;
   if (st->err) return;
+  const int n = st->n_cur;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
     const uint32_t key = keys[p];
+    if (key == INVALID_KEY) continue;
     const int b = fscan[key >> G::CB];
     perm[cellstart[(size_t)b * G::CELLS + (key & (G::CELLS - 1))] + rank[p]] = p;
   }
@@ -121,7 +129,7 @@ template <int D>
 __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restrict__ fscan, int nlin, KeyLayout L,
                              const uint32_t* __restrict__ pb_key, const int* __restrict__ cellstart,
                              int* __restrict__ pb_start, int* __restrict__ pb_nbr, uint32_t* __restrict__ gb_key,
-                             int n, int max_blocks, Status* st) {
+                             int max_blocks, Status* st) {
   using G = Geo<D>;
   if (st->err) return;
   const int npb = fscan[nlin];
@@ -134,7 +142,11 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
   }
   if (first) {
     st->npb = npb; st->ngb = ngb; st->ngb_raw = ngb;
-    pb_start[npb] = n;
+    const int n_live = cellstart[(size_t)npb * G::CELLS];   // particles that were ranked
+    pb_start[npb] = n_live;
+    st->n_live = n_live;
+    st->mig_cnt[0] = st->mig_cnt[1] = 0;
+    st->halo_cnt[0] = st->halo_cnt[1] = 0;
     st->work_p2g = 0; st->work_g2p = 0;
     st->maxv_bits = 0;
     for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }

@@ -1,0 +1,133 @@
+// Multi-GPU slab decomposition: device side of the two neighbour exchanges
+// (no counterpart in the reference, which is single-device).
+//
+// Rank r owns leaf-block columns [lo, hi) along x.  A particle belongs to the
+// rank that owns its BASE block, so its 3^D stencil spills at most into block
+// column `hi`, the first column of rank r+1.  Per substep:
+//   after P2G   both ranks hold partial (momentum, mass) sums of that shared
+//               column: each packs its copy (k_halo_pack), the buffers are
+//               exchanged (NCCL send/recv, issued by the host between kernels)
+//               and added (k_halo_add).  a + b == b + a bit for bit, so both
+//               then run the grid op on identical sums and no velocities need
+//               to travel back.
+//   in G2P      a particle whose new base block left [lo, hi) is also written,
+//               complete (all state words), to the migration buffer of that
+//               side; the next substep's binning drops it locally
+//               (k_bin_keys) and the neighbour appends it (k_mig_unpack).
+// Buffers have a fixed capacity so no message size ever depends on a device
+// value (no host synchronisation inside a batch); word 0 of each is the count.
+#pragma once
+#include "mpm_kernels.cuh"
+
+namespace mpm {
+
+// (by, bz) of a leaf block, absolute coordinates (each < 2^15), in one word
+__device__ __forceinline__ uint32_t halo_key(int by, int bz) { return ((uint32_t)by << 16) | ((uint32_t)bz & 0xFFFFu); }
+
+// one warp per active grid block: copy the blocks of column `bx_abs` to `buf`
+template <int D>
+__global__ void k_halo_pack(const float4* __restrict__ grid, const uint32_t* __restrict__ gb_key, KeyLayout L,
+                            int bx_abs, uint32_t* __restrict__ buf, int halo_cap, int side, Status* st) {
+  using G = Geo<D>;
+  if (st->err) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const int ngb = st->ngb;
+  for (int g = warp; g < ngb; g += nwarp) {
+    int rel[D];
+    key_to_rel<D>(L, gb_key[g], rel);
+    if (rel[0] + L.ob[0] != bx_abs) continue;
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&st->halo_cnt[side], 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= halo_cap) continue;            // counted; k_comm_headers raises the error
+    if (lane == 0) buf[COMM_HEADER + idx] = halo_key(rel[1] + L.ob[1], D == 3 ? rel[D - 1] + L.ob[D - 1] : 0);
+    float4* out = reinterpret_cast<float4*>(buf + COMM_HEADER + halo_cap) + (size_t)idx * G::CELLS;
+    for (int c = lane; c < G::CELLS; c += 32) out[c] = grid[(size_t)g * G::CELLS + c];
+  }
+}
+
+// one warp per received block: add it to the local copy of column `bx_abs`
+// (blocks this rank does not have active are not needed here and are skipped)
+template <int D>
+__global__ void k_halo_add(float4* __restrict__ grid, const int* __restrict__ flags, const int* __restrict__ fscan,
+                           int nlin, KeyLayout L, int bx_abs, const uint32_t* __restrict__ buf, int halo_cap,
+                           const Status* st) {
+  using G = Geo<D>;
+  if (st->err) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const int cnt = min((int)buf[0], halo_cap);
+  const int npb = st->npb;
+  for (int i = warp; i < cnt; i += nwarp) {
+    const uint32_t k = buf[COMM_HEADER + i];
+    int rel[D];
+    rel[0] = bx_abs - L.ob[0];
+    rel[1] = (int)(k >> 16) - L.ob[1];
+    if constexpr (D == 3) rel[2] = (int)(k & 0xFFFFu) - L.ob[2];
+    bool inside = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) inside = inside && rel[d] >= 0 && rel[d] < L.eb[d];
+    if (!inside) continue;
+    const int lin = (int)rel_to_key<D>(L, rel);
+    if (!flags[nlin + lin]) continue;
+    const int slot = fscan[nlin + lin] - npb;
+    const float4* in = reinterpret_cast<const float4*>(buf + COMM_HEADER + halo_cap) + (size_t)i * G::CELLS;
+    float4* dst = grid + (size_t)slot * G::CELLS;
+    for (int c = lane; c < G::CELLS; c += 32) {
+      float4 a = dst[c];
+      const float4 b = in[c];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      dst[c] = a;
+    }
+  }
+}
+
+// message headers (one thread): counts, overflow detection
+__global__ void k_halo_headers(CommBufs cb, Status* st) {
+  for (int s = 0; s < 2; ++s) {
+    if (!cb.halo[s]) continue;
+    int c = st->err ? 0 : st->halo_cnt[s];
+    if (c > cb.halo_cap) { st->err |= ERR_COMM_CAPACITY; c = 0; }
+    cb.halo[s][0] = (uint32_t)c;
+  }
+}
+__global__ void k_mig_headers(CommBufs cb, Status* st) {
+  for (int s = 0; s < 2; ++s) {
+    if (!cb.mig[s]) continue;
+    int c = st->err ? 0 : st->mig_cnt[s];
+    if (c > cb.mig_cap) { st->err |= ERR_COMM_CAPACITY; c = 0; }
+    cb.mig[s][0] = (uint32_t)c;
+  }
+  if (!st->err) st->n_cur = st->n_live;    // rows of the set G2P just wrote
+}
+
+// append the particles received from the -x and +x neighbours to the live set
+template <int D>
+__global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uint32_t* __restrict__ from_lo,
+                             const uint32_t* __restrict__ from_hi, int mig_cap, Status* st) {
+  constexpr int NF = Fld<D>::N;
+  if (st->err) return;
+  const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
+  const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
+  const int base = st->n_cur;
+  if ((size_t)base + c0 + c1 > cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->err |= ERR_PARTICLE_CAPACITY;
+    return;
+  }
+  const int total = (c0 + c1) * NF;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i / (c0 + c1), r = i % (c0 + c1);
+    const uint32_t v = r < c0 ? from_lo[COMM_HEADER + (size_t)f * mig_cap + r]
+                              : from_hi[COMM_HEADER + (size_t)f * mig_cap + (r - c0)];
+    state[(size_t)f * cap + base + r] = v;
+  }
+}
+__global__ void k_mig_commit(const uint32_t* from_lo, const uint32_t* from_hi, int mig_cap, Status* st) {
+  if (st->err) return;
+  const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
+  const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
+  st->n_cur += c0 + c1;
+}
+
+}  // namespace mpm

@@ -41,7 +41,7 @@ struct KeyLayout {
   int key_bits;
 };
 
-enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2 };
+enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2, ERR_COMM_CAPACITY = 4, ERR_PARTICLE_CAPACITY = 8 };
 
 // Device-resident status block, copied to pinned host memory after each batch.
 struct Status {
@@ -55,7 +55,26 @@ struct Status {
   int bb_min[3], bb_max[3];
   int need_blocks;  // max(npb, ngb) seen, for capacity growth
   unsigned maxv_all; // max of maxv_bits over the batch
+  int n_cur;        // rows of the live set in use (includes particles that left this rank's slab)
+  int n_live;       // particles binned this substep (= rows of the other set after G2P)
+  int mig_cnt[2];   // particles leaving to the -x / +x neighbour rank (filled by G2P)
+  int halo_cnt[2];  // packed boundary-column grid blocks (-x / +x side)
   int pad[2];
+};
+
+// Slab decomposition along x (multi-GPU): this rank owns leaf-block columns
+// [lo, hi) in absolute block coordinates.  Disabled = owns everything.
+struct Slab {
+  int enabled, lo, hi;
+};
+// Fixed-capacity message buffers (32-bit words, 16-word header, word 0 = count).
+//   migration: header | field-major rows  [field][mig_cap]
+//   halo:      header | keys [halo_cap] | node records [halo_cap][CELLS] float4
+static constexpr int COMM_HEADER = 16;
+struct CommBufs {
+  uint32_t* mig[2];
+  uint32_t* halo[2];
+  int mig_cap, halo_cap;
 };
 
 struct Grav { float g[3]; };

@@ -58,6 +58,7 @@ __global__ void k_reset(Status* st) {
   st->maxv_bits = 0;
   for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
 }
+__global__ void k_batch_begin(Status* st, int n) { st->n_cur = n; st->n_live = n; }
 __global__ void k_end(Status* st) {
   if (!st->err) {
     st->done += 1;
@@ -274,6 +275,8 @@ template <int D> struct SubstepArgs {
   KeyLayout L;
   Consts K;
   float dt;
+  Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
+  CommBufs cb;    // multi-GPU: migration / halo send buffers
 };
 
 // ------------------------------------------------------------------ P2G
@@ -642,6 +645,33 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       }
 #pragma unroll
       for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::C + i, s, nC[i]);
+      if (a.slab.enabled) {
+        // slab decomposition: the particle now belongs to a neighbour rank -> hand it over
+        const int nbx = (base_index(x[0], a.K.inv_dx) + a.L.half) >> G::LOG_LEAF;
+        const int dir = nbx < a.slab.lo ? 0 : (nbx >= a.slab.hi ? 1 : -1);
+        if (dir >= 0 && a.cb.mig[dir]) {
+          const int idx = atomicAdd(&a.st->mig_cnt[dir], 1);
+          if (idx < a.cb.mig_cap) {
+            uint32_t* m = a.cb.mig[dir] + COMM_HEADER + idx;
+            const size_t mc = (size_t)a.cb.mig_cap;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              m[(FL::X + d) * mc] = __float_as_uint(x[d]);
+              m[(FL::V + d) * mc] = __float_as_uint(nv[d]);
+            }
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) {
+              m[(FL::F + i) * mc] = a.dst[(size_t)(FL::F + i) * cap + s];   // written by P2G
+              m[(FL::C + i) * mc] = __float_as_uint(nC[i]);
+            }
+            m[FL::JP * mc] = a.dst[(size_t)FL::JP * cap + s];
+            m[FL::MAT * mc] = mat;
+            m[FL::COLOR * mc] = ldu(a.src, cap, FL::COLOR, p);
+            m[FL::ID * mc] = ldu(a.src, cap, FL::ID, p);
+            m[FL::EMIT * mc] = ldu(a.src, cap, FL::EMIT, p);
+          }
+        }
+      }
       stu(a.dst, cap, FL::MAT, s, mat);
       stu(a.dst, cap, FL::COLOR, s, ldu(a.src, cap, FL::COLOR, p));
       stu(a.dst, cap, FL::ID, s, ldu(a.src, cap, FL::ID, p));
