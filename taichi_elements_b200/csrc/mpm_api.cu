@@ -818,8 +818,10 @@ extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
 extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
   REQUIRE_BATCH();
   ctx->in_batch = false;
-  k_end<<<1, 1, 0, s>>>(ctx->d_status);
-  ctx->launches += 1;
+  if (ctx->batch_enq > 0) {   // commit of the last substep (none in a pure delivery batch)
+    k_end<<<1, 1, 0, s>>>(ctx->d_status);
+    ctx->launches += 1;
+  }
   CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const Status& h = *ctx->h_status;

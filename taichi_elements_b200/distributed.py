@@ -52,7 +52,13 @@ class SlabDecomposition:
         bx = np.sort((base + grid_size // 2) // leaf)
         cuts = []
         for k in range(1, world):
-            c = int(bx[min(len(bx) - 1, (len(bx) * k) // world)])
+            target = (len(bx) * k) // world
+            c = int(bx[min(len(bx) - 1, target)])
+            # a cut at c leaves count(bx < c) particles on the left: take c or c + 1, whichever is closer
+            below = int(np.searchsorted(bx, c, side='left'))
+            below_next = int(np.searchsorted(bx, c + 1, side='left'))
+            if abs(below_next - target) < abs(below - target):
+                c += 1
             if cuts and c <= cuts[-1]:
                 c = cuts[-1] + 1
             cuts.append(c)
