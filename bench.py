@@ -194,13 +194,36 @@ def main():
 
     def make_solver():
         with quiet:
-            s = MPMSolver(res=w['res'], size=1, unbounded=False, device=local)
+            if world == 1:
+                s = MPMSolver(res=w['res'], size=1, unbounded=False, device=local)
+            else:
+                from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
+                res = w['res'][0]
+                cuts = [int((math.floor((x0 + side * k) * res) + 2048) // 4) for k in range(1, world)]
+                s = DistributedMPMSolver(res=w['res'], cuts=cuts, size=1, unbounded=False, device=local,
+                                         mig_capacity=1 << 14, halo_capacity=1 << 11, substep_batch=20)
+                s.reserve_blocks(1 << 16)
         s.set_gravity(w['gravity'])
         return s
 
+    # N > 1: weak scaling -- one brick of the N=1 scene per rank, bricks contiguous along x so that
+    # every cut carries a shared grid column and migrating particles; every rank builds the same
+    # particle list and keeps its slab
+    import math
+    side = 0.25
+    x0 = 0.5 - side * world / 2
+    if world == 1:
+        bricks = [w['parts']]
+    else:
+        bricks = []
+        for r in range(world):
+            wr = workload(args.workload, rank=r, world=world)
+            shift = np.array([x0 + side * r - (0.5 - side / 2), 0, 0], np.float32)
+            bricks.append([(x + shift, m) for x, m in wr['parts']])
     mpm = make_solver()
-    for x, m in w['parts']:
-        mpm.add_particles(x, m)
+    for parts in bricks:
+        for x, m in parts:
+            mpm.add_particles(x, m)
     n_local = mpm.n_particles[None]
     dt = w['frame_dt'] / (int(w['frame_dt'] / mpm.default_dt) + 1)
     if w['res'][0] != 256:
@@ -216,7 +239,7 @@ def main():
     # ---------------- device-resident throughput (`value`) ----------------
     lib.mpm_set_profiling(ctx, 0)
     mpm._run_substeps(dt, args.warmup)
-    lib.mpm_set_profiling(ctx, 1)
+    lib.mpm_set_profiling(ctx, 1 if world == 1 else 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -241,12 +264,15 @@ def main():
     peak, peak_src = peaks()
     cells_active = int(st.n_grid_blocks) * 64
     b_alg_p2g = B_P2G_PARTICLE * n_local + B_P2G_CELL * cells_active
+    b_alg_step = B_PARTICLE * n_local + B_CELL * cells_active
     phases = {'sort+structure': st.ms_sort, 'p2g': st.ms_p2g, 'grid_op': st.ms_grid, 'g2p': st.ms_g2p}
     dom = max(phases, key=phases.get)
     achieved = b_alg_p2g / (st.ms_p2g * 1e-3) / 1e9 if st.ms_p2g > 0 else 0.0
-    b_alg_step = B_PARTICLE * n_local + B_CELL * cells_active
+    if world > 1:   # phase API: no per-kernel events; report the whole substep per GPU
+        achieved = b_alg_step / (ms_per_step * 1e-3) / 1e9
     roofline = {
-        'bound': 'hbm', 'kernel': 'k_p2g<3>', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'bound': 'hbm', 'kernel': 'k_p2g_cell<3>' if world == 1 else 'whole substep, per GPU (no per-kernel events in the multi-GPU phase path)',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
         'algorithmic_bytes_per_launch': b_alg_p2g,
         'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
@@ -259,7 +285,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         frames = max(1, min(3, args.steps // 40))
-        host_parts = [(torch.from_numpy(x).pin_memory().numpy(), m) for x, m in w['parts']]
+        host_parts = [(torch.from_numpy(x).pin_memory().numpy(), m) for parts in bricks for x, m in parts]
         sub_per_frame = 0
         with quiet:
             mpm2 = mpm
@@ -267,7 +293,11 @@ def main():
             for x, m in host_parts:        # warm-up of the same path
                 mpm2.add_particles(x, m)
             mpm2.step(w['frame_dt'])
-            mpm2.particle_info()
+            if world > 1:
+                mpm2.flush_migration()
+                mpm2.local_rows()
+            else:
+                mpm2.particle_info()
         barrier()
         t0 = time.perf_counter()
         d2h = 0
@@ -279,15 +309,19 @@ def main():
                 before = mpm2.total_substeps
                 mpm2.step(w['frame_dt'])
                 sub_per_frame = mpm2.total_substeps - before
-                info = mpm2.particle_info()
+                if world > 1:
+                    mpm2.flush_migration()
+                    info = mpm2.local_rows()
+                else:
+                    info = mpm2.particle_info()
                 d2h = sum(a.nbytes for a in info.values())
         barrier()
         el = time.perf_counter() - t0
-        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        te = torch.tensor([el, float(d2h)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        el = float(te.item())
-        h2d = sum(x.nbytes for x, _ in host_parts)
+        el, d2h = float(te[0].item()), float(te[1].item())
+        h2d = sum(x.nbytes for x, _ in host_parts) / world   # each rank uploads only its slab
         e2e = {'value': n_total * sub_per_frame * frames / el, 'unit': 'particle-substeps/s',
                'h2d_bytes_per_step': h2d / sub_per_frame, 'd2h_bytes_per_step': d2h / sub_per_frame,
                'what': f'{frames} x [clear_particles, add_particles(host arrays), step({w["frame_dt"]}) = '
@@ -308,7 +342,7 @@ def main():
                        'particles_per_gpu': n_local, 'l2': 'inputs (2 x 116 B x N particle state) exceed L2',
                        'active_blocks': int(st.n_grid_blocks), 'particle_blocks': int(st.n_particle_blocks)},
             'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches,
-            'gpu_launches_note': 'own kernels only (11 per substep); CUB sort/select launches not counted',
+            'gpu_launches_note': 'own kernels only (8 per substep + 1 per batch; more with slabs); CUB scan launches not counted',
             'roofline': roofline, 'cpu_baseline': cpu,
         }
         print(json.dumps(line))

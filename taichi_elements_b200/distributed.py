@@ -145,6 +145,13 @@ def _make_distributed_solver():
                 id_row = self._nf - 2          # x v F C Jp material color id emitter
                 self._state[cur.value, id_row, n0:n0 + len(ids)] = torch.from_numpy(ids).to(self._device)
 
+        def clear_particles(self):
+            super().clear_particles()
+            self._global_n = 0
+            for t in self._mig_send:
+                if t is not None:
+                    t[0] = 0
+
         def add_cube(self, *a, **k):
             raise NotImplementedError('seed through add_particles on the distributed solver')
 
