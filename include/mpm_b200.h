@@ -151,6 +151,8 @@ int mpm_set_profiling(mpm_ctx* ctx, int32_t enabled);
  * host memory (4 bytes per particle). */
 int mpm_download(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_host, void* stream);
 /* same, device destination */
+int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t begin, int64_t end, void* dst_dev,
+                    void* stream); /* rows dst[i][nwords] of consecutive words (copy_dynamic_nd, :1146-1150) */
 int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream);
 
 

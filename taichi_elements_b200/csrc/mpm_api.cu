@@ -71,6 +71,7 @@ struct mpm_ctx {
   int sm_count = 148;
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
   int g2p_cfg = 3;
+  int p2g_cfg = 0;
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;
   int done_last = 0;
@@ -212,15 +213,8 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
     ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
 
   }
-  if (p->dim == 3) {
-    cudaFuncSetAttribute(k_p2g_cell<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2g_smem_bytes<3>());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<3>, P2GCfg<3>::THREADS, p2g_smem_bytes<3>());
-  } else {
-    cudaFuncSetAttribute(k_p2g_cell<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2g_smem_bytes<2>());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<2>, P2GCfg<2>::THREADS, p2g_smem_bytes<2>());
-  }
-  ctx->grid_p2g_cell = ctx->sm_count * std::max(occ, 1);
   if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
+  if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
@@ -446,6 +440,34 @@ static int update_layout(mpm_ctx* ctx) {
   return MPM_OK;
 }
 
+// P2G (cell-owner) launch configurations: particles staged per pass, CTAs per SM; MPM_P2G_CFG picks one.
+template <int D, int CH, int MB>
+static void launch_p2g_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  static int grid = 0;
+  constexpr size_t smem = p2g_smem_bytes<D, CH>();
+  if (!grid) {
+    int occ = 1;
+    cudaFuncSetAttribute(k_p2g_cell<D, CH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<D, CH, MB>, P2GCfg<D>::THREADS, smem);
+    grid = ctx->sm_count * std::max(occ, 1);
+  }
+  k_p2g_cell<D, CH, MB><<<grid, P2GCfg<D>::THREADS, smem, s>>>(a);
+}
+template <int D>
+static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  if constexpr (D == 3) {
+    switch (ctx->p2g_cfg) {
+      case 1: launch_p2g_cfg<3, 512, 5>(ctx, a, s); break;
+      case 2: launch_p2g_cfg<3, 576, 4>(ctx, a, s); break;
+      case 3: launch_p2g_cfg<3, 384, 6>(ctx, a, s); break;
+      case 4: launch_p2g_cfg<3, 768, 3>(ctx, a, s); break;
+      default: launch_p2g_cfg<3, 640, 4>(ctx, a, s); break;
+    }
+  } else {
+    launch_p2g_cfg<2, 1280, 1>(ctx, a, s);
+  }
+}
+
 // G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
 template <int D, int T, int MB>
 static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
@@ -550,7 +572,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
   ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
   SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
   if (ctx->p2g_variant == 0) k_p2g<D><<<ctx->grid_p2g, P2G_THREADS, 0, s>>>(a);
-  else k_p2g_cell<D><<<ctx->grid_p2g_cell, P2GCfg<D>::THREADS, p2g_smem_bytes<D>(), s>>>(a);
+  else launch_p2g<D>(ctx, a, s);
   if (prof) cudaEventRecord(ev[2], s);
   CK(cudaGetLastError());
   ctx->launches += 2;   // clear, p2g; CUB's internal launches are not counted
@@ -895,6 +917,20 @@ extern "C" int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t en
   const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
   k_gather_field<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(st + (size_t)field * ctx->cap, st + (size_t)idf * ctx->cap,
                                                                   (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
+extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t begin, int64_t end,
+                               void* dst_dev, void* stream) {
+  if (!ctx || first_field < 0 || nwords < 1 || first_field + nwords > ctx->nf || begin < 0 || end < begin || end > ctx->n)
+    return fail(ctx, MPM_E_INVALID, "mpm_gather_rows: bad range/field");
+  if (end == begin) return MPM_OK;
+  if (!dst_dev) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
+  k_gather_rows<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      ctx->state[ctx->cur], ctx->cap, first_field, nwords, idf, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
   CK(cudaGetLastError());
   return MPM_OK;
 }

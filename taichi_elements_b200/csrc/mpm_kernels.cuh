@@ -516,6 +516,22 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
       for (int d = 0; d < D; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
     }
+    // software pipeline over this thread's particles: `perm` runs two iterations
+    // ahead and the position/material loads one iteration ahead of the arithmetic, so
+    // the dependent perm -> x latency chain overlaps the previous particle's math
+    // (and, for the first particle, the tile staging below)
+    int s = start + tid;
+    uint32_t p1 = s < end ? a.perm[s] : 0u;
+    uint32_t p2 = s + G2P_THREADS < end ? a.perm[s + G2P_THREADS] : 0u;
+    float xn[D];
+    uint32_t matn = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) xn[d] = 0.0f;
+    if (s < end) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) xn[d] = ldf(a.src, cap, FL::X + d, p1);
+      matn = ldu(a.src, cap, FL::MAT, p1);
+    }
     __syncthreads();
     for (int n = tid; n < G::TN; n += G2P_THREADS) {
       int oct, cell;
@@ -542,13 +558,24 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         }
       }
     }
-    for (int s = start + tid; s < end; s += G2P_THREADS) {
-      const uint32_t p = a.perm[s];
+    for (; s < end; s += G2P_THREADS) {
+      const uint32_t p = p1;
       float x[D], fx[D], w[3][D];
       int l[D];
 #pragma unroll
+      for (int d = 0; d < D; ++d) x[d] = xn[d];
+      const uint32_t mat = matn;
+      const uint32_t color = ldu(a.src, cap, FL::COLOR, p), pid = ldu(a.src, cap, FL::ID, p),
+                     emit = ldu(a.src, cap, FL::EMIT, p);
+      p1 = p2;
+      if (s + G2P_THREADS < end) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = ldf(a.src, cap, FL::X + d, p1);
+        matn = ldu(a.src, cap, FL::MAT, p1);
+      }
+      p2 = s + 2 * G2P_THREADS < end ? a.perm[s + 2 * G2P_THREADS] : 0u;
+#pragma unroll
       for (int d = 0; d < D; ++d) {
-        x[d] = ldf(a.src, cap, FL::X + d, p);
         int base = base_index(x[d], a.K.inv_dx);
         fx[d] = x[d] * a.K.inv_dx - (float)base;
         l[d] = min(max(base + a.L.half - org[d], 0), G::LEAF - 1);
@@ -556,7 +583,6 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         w[1][d] = 0.75f - (fx[d] - 1.0f) * (fx[d] - 1.0f);
         w[2][d] = 0.5f * (fx[d] - 0.5f) * (fx[d] - 0.5f);
       }
-      const uint32_t mat = ldu(a.src, cap, FL::MAT, p);
       // Tensor-product evaluation of sum_ijk w_i w_j w_k g_ijk and of its first
       // moments (C = 4 inv_dx sum w g (x) (o - fx), :715-721): partial sums along
       // z, then y, then x -- 279 FMAs instead of 27 x 23.
@@ -666,16 +692,16 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
             }
             m[FL::JP * mc] = a.dst[(size_t)FL::JP * cap + s];
             m[FL::MAT * mc] = mat;
-            m[FL::COLOR * mc] = ldu(a.src, cap, FL::COLOR, p);
-            m[FL::ID * mc] = ldu(a.src, cap, FL::ID, p);
-            m[FL::EMIT * mc] = ldu(a.src, cap, FL::EMIT, p);
+            m[FL::COLOR * mc] = color;
+            m[FL::ID * mc] = pid;
+            m[FL::EMIT * mc] = emit;
           }
         }
       }
       stu(a.dst, cap, FL::MAT, s, mat);
-      stu(a.dst, cap, FL::COLOR, s, ldu(a.src, cap, FL::COLOR, p));
-      stu(a.dst, cap, FL::ID, s, ldu(a.src, cap, FL::ID, p));
-      stu(a.dst, cap, FL::EMIT, s, ldu(a.src, cap, FL::EMIT, p));
+      stu(a.dst, cap, FL::COLOR, s, color);
+      stu(a.dst, cap, FL::ID, s, pid);
+      stu(a.dst, cap, FL::EMIT, s, emit);
     }
     b = s_next;
     __syncthreads();
@@ -905,6 +931,16 @@ __global__ void k_gather_field(const uint32_t* __restrict__ field, const uint32_
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
     int64_t id = ids[s];
     if (id >= begin && id < end) out[id - begin] = field[s];
+  }
+}
+
+// several consecutive state words of particles [begin, end) as rows out[id - begin][nwords]
+__global__ void k_gather_rows(const uint32_t* __restrict__ state, size_t cap, int first, int nwords, int idf,
+                              int n, int64_t begin, int64_t end, uint32_t* __restrict__ out) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    const int64_t id = state[(size_t)idf * cap + s];
+    if (id >= begin && id < end)
+      for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = state[(size_t)(first + w) * cap + s];
   }
 }
 

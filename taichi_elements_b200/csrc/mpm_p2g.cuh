@@ -25,25 +25,27 @@ namespace mpm {
 
 template <int D> struct P2GCfg;
 template <> struct P2GCfg<3> {
-  static constexpr int SL = 3, NPT = 9, PAY = 16, CHUNK = 640, THREADS = 192, MINB = 4;
+  static constexpr int SL = 3, NPT = 9, PAY = 16, THREADS = 192;
 };
 template <> struct P2GCfg<2> {
-  static constexpr int SL = 3, NPT = 3, PAY = 9, CHUNK = 1280, THREADS = 768, MINB = 1;
+  static constexpr int SL = 3, NPT = 3, PAY = 9, THREADS = 768;
 };
 
-template <int D> constexpr size_t p2g_smem_bytes() {
+template <int D, int CHUNK> constexpr size_t p2g_smem_bytes() {
   using G = Geo<D>;
   using P = P2GCfg<D>;
-  return (size_t)P::SL * G::TN * sizeof(float4) + (size_t)P::PAY * P::CHUNK * sizeof(float) +
+  return (size_t)P::SL * G::TN * sizeof(float4) + (size_t)P::PAY * CHUNK * sizeof(float) +
          (size_t)(G::CELLS + 1) * sizeof(int);
 }
 
-template <int D>
-__global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cell(SubstepArgs<D> a) {
+// CHUNK = particles staged per pass (shared-memory payload), MINB = CTAs per SM the
+// register allocation is bounded for
+template <int D, int CHUNK, int MINB>
+__global__ void __launch_bounds__(P2GCfg<D>::THREADS, MINB) k_p2g_cell(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
   using P = P2GCfg<D>;
-  constexpr int T = P::THREADS, CH = P::CHUNK;
+  constexpr int T = P::THREADS, CH = CHUNK;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);                 // [SL][TN]
   float* pay = reinterpret_cast<float*>(tile + P::SL * G::TN);        // [PAY][CH]
@@ -105,9 +107,17 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, P2GCfg<D>::MINB) k_p2g_cel
     for (int c0 = 0; c0 < cnt; c0 += CH) {
       const int cn = min(CH, cnt - c0);
       // ---- phase 1: constitutive update, payload to shared memory
+      // all of this thread's `perm` entries first: one exposed latency per chunk, not per particle
+      constexpr int NIT = (CH + T - 1) / T;
+      uint32_t pq[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
+#pragma unroll 1
       for (int q = tid; q < cn; q += T) {
         const int s = start + c0 + q;
-        const uint32_t p = a.perm[s];
+        const uint32_t p = pq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];   // rotate (keeps the loop body single-copy)
         float x[D], v[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {

@@ -60,13 +60,21 @@ class _Field:
         return _Field(self._s, self._w0 + off, (), self.dtype)
 
     def to_numpy(self, begin=0, end=None):
-        n = self._s.n_particles[None]
+        """Rows [begin, end) in insertion order: gathered on the device, one copy into pinned
+        host memory; the returned array is a fresh, caller-owned buffer."""
+        s = self._s
+        n = s.n_particles[None]
         end = n if end is None else end
-        cnt = end - begin
-        out = np.empty((self._words(), max(cnt, 0)), dtype=self.dtype)
-        for w in range(self._words()):
-            self._s._download_word(self._w0 + w, begin, end, out[w])
-        return np.ascontiguousarray(out.T.reshape((cnt, ) + self.shape_tail))
+        cnt = max(end - begin, 0)
+        tdt = torch.float32 if self.dtype == np.float32 else torch.int32
+        host = torch.empty((cnt, self._words()), dtype=tdt, pin_memory=cnt > 0)
+        if cnt:
+            with torch.cuda.device(s._device):
+                dev = torch.empty((cnt, self._words()), dtype=tdt, device=s._device)
+                s._check(s._lib.mpm_gather_rows(s._ctx, self._w0, self._words(), begin, end, dev.data_ptr(),
+                                                s._stream()), 'mpm_gather_rows')
+                host.copy_(dev)
+        return host.numpy().reshape((cnt, ) + self.shape_tail)
 
 
 class _ParticleNode:
