@@ -70,7 +70,7 @@ struct mpm_ctx {
   GridCfg gcfg{};
   int sm_count = 148;
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
-  int g2p_cfg = 3;
+  int g2p_cfg = 2;
   int p2g_cfg = 0;
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;

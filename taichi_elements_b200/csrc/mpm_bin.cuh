@@ -46,33 +46,48 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
   if (commit_prev && blockIdx.x == 0 && threadIdx.x == 0) commit_substep(st);
   if (st->err) return;
   const int n = st->n_cur;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
     uint32_t lin = 0, cell = 0, sp = 0;
-    bool bad = false, mine = true;
+    bool bad = false, mine = p < (uint32_t)n;
+    if (mine) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
-      if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = bx >= slab.lo && bx < slab.hi; }
-      int rel = (g >> G::LOG_LEAF) - L.ob[d];
-      if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
-      lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
-      const uint32_t lc = (uint32_t)(g & (G::LEAF - 1));
-      cell = (cell << G::LOG_LEAF) | lc;
-      sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
-    }
-    // a particle whose base block left this rank's slab has already been handed
-    // to the neighbour (G2P packs it): it is dropped from the local sort
-    if (!mine) { keys[p] = INVALID_KEY; continue; }
-    keys[p] = (lin << G::CB) | cell;
-    if (bad) { atomicOr(&st->err, ERR_BBOX); continue; }
-    if (flags[lin] == 0) flags[lin] = 1;
-    int* gf = flags + nlin;
-#pragma unroll
-    for (int o = 0; o < G::NO; ++o)
-      if ((o & ~sp) == 0) {
-        const int t = (int)lin + oct_delta<D>(L, o);
-        if (gf[t] == 0) gf[t] = 1;
+      for (int d = 0; d < D; ++d) {
+        int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
+        if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = bx >= slab.lo && bx < slab.hi; }
+        int rel = (g >> G::LOG_LEAF) - L.ob[d];
+        if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
+        lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
+        const uint32_t lc = (uint32_t)(g & (G::LEAF - 1));
+        cell = (cell << G::LOG_LEAF) | lc;
+        sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
       }
+      // a particle whose base block left this rank's slab has already been handed
+      // to the neighbour (G2P packs it): it is dropped from the local sort
+      keys[p] = mine ? ((lin << G::CB) | cell) : INVALID_KEY;
+      if (mine && bad) { atomicOr(&st->err, ERR_BBOX); mine = false; }
+    }
+    // Flag the particle's leaf block and the blocks its stencil reaches.  Neighbouring
+    // particles share blocks (storage is in sorted order), so one lane per distinct
+    // block of the warp does the marking for the union of its group's octant masks.
+    uint32_t om = 0;
+#pragma unroll
+    for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
+      if ((o & ~sp) == 0) om |= 1u << o;
+    const uint32_t tag = mine ? lin : (0xFFFFFFFFu - (uint32_t)lane);
+    const unsigned grp = __match_any_sync(0xffffffffu, tag);
+    om = __reduce_or_sync(grp, om);
+    if (mine && lane == __ffs(grp) - 1) {
+      if (flags[lin] == 0) flags[lin] = 1;
+      int* gf = flags + nlin;
+#pragma unroll
+      for (int o = 0; o < G::NO; ++o)
+        if ((om >> o) & 1u) {
+          const int t = (int)lin + oct_delta<D>(L, o);
+          if (gf[t] == 0) gf[t] = 1;
+        }
+    }
   }
 }
 
