@@ -523,15 +523,15 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     const int ncell = ctx->max_blocks * G::CELLS + 1;
     CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
     CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
-    k_bin_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
+    k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
                                                        nlin, commit_prev, st);
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
-    k_bin_rank<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
+    k_bin_rank<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
                                                        ctx->max_blocks, st);
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->cellcount, ctx->cellstart, ncell, s));
-    k_bin_scatter<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
+    k_bin_scatter<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
     k_bin_finish<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(
         ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr, ctx->gb_key,
         ctx->max_blocks, st);

@@ -6,7 +6,7 @@
 // order that is already almost there.  With a dense flag table over the
 // block-aligned particle box (the key layout's eb[0]*eb[1]*eb[2] entries) one
 // pass suffices:
-//   k_bin_keys     key per particle; flag its leaf block and every leaf block
+//   k_bin_keys     key per particle (4 particles per thread, 128-bit accesses); flag its leaf block and every leaf block
 //                  its 3^D stencil touches (the reference's active-block set)
 //   ExclusiveSum   over [particle-block flags | grid-block flags]: dense slots
 //                  in key order
@@ -38,6 +38,9 @@ __device__ __forceinline__ void commit_substep(Status* st) {
   }
 }
 
+// The three per-particle passes below are pure streaming kernels whose speed is set by
+// the number of bytes in flight, so every thread handles FOUR consecutive particles with
+// 128-bit loads/stores (capacity is a multiple of 64, rows are 16-byte aligned).
 template <int D>
 __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float inv_dx, KeyLayout L, Slab slab,
                            uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, int commit_prev,
@@ -46,16 +49,24 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
   if (commit_prev && blockIdx.x == 0 && threadIdx.x == 0) commit_substep(st);
   if (st->err) return;
   const int n = st->n_cur;
-  const int lane = threadIdx.x & 31;
-  const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-    uint32_t lin = 0, cell = 0, sp = 0;
-    bool bad = false, mine = p < (uint32_t)n;
-    if (mine) {
+  const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nquad; t += gridDim.x * blockDim.x) {
+    float4 xs[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      xs[d] = __ldg(reinterpret_cast<const float4*>(state + (size_t)(Fld<D>::X + d) * cap) + t);
+    uint32_t out[4];
+    uint32_t prev_lin = 0xFFFFFFFFu, prev_om = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t p = 4u * t + j;
+      uint32_t lin = 0, cell = 0, sp = 0;
+      bool bad = false, mine = p < (uint32_t)n;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
-        if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = bx >= slab.lo && bx < slab.hi; }
+        const float xv = j == 0 ? xs[d].x : (j == 1 ? xs[d].y : (j == 2 ? xs[d].z : xs[d].w));
+        int g = base_index(xv, inv_dx) + L.half;
+        if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = mine && bx >= slab.lo && bx < slab.hi; }
         int rel = (g >> G::LOG_LEAF) - L.ob[d];
         if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
         lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
@@ -63,31 +74,30 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
         cell = (cell << G::LOG_LEAF) | lc;
         sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
       }
-      // a particle whose base block left this rank's slab has already been handed
-      // to the neighbour (G2P packs it): it is dropped from the local sort
-      keys[p] = mine ? ((lin << G::CB) | cell) : INVALID_KEY;
+      // a particle whose base block left this rank's slab has already been handed to the
+      // neighbour (G2P packs it): it is dropped from the local sort
+      out[j] = mine ? ((lin << G::CB) | cell) : INVALID_KEY;
       if (mine && bad) { atomicOr(&st->err, ERR_BBOX); mine = false; }
-    }
-    // Flag the particle's leaf block and the blocks its stencil reaches.  Neighbouring
-    // particles share blocks (storage is in sorted order), so one lane per distinct
-    // block of the warp does the marking for the union of its group's octant masks.
-    uint32_t om = 0;
+      if (!mine) continue;
+      // flag the leaf block and the blocks the stencil reaches; consecutive particles
+      // mostly repeat the previous one's block and octants
+      uint32_t om = 0;
 #pragma unroll
-    for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
-      if ((o & ~sp) == 0) om |= 1u << o;
-    const uint32_t tag = mine ? lin : (0xFFFFFFFFu - (uint32_t)lane);
-    const unsigned grp = __match_any_sync(0xffffffffu, tag);
-    om = __reduce_or_sync(grp, om);
-    if (mine && lane == __ffs(grp) - 1) {
+      for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
+        if ((o & ~sp) == 0) om |= 1u << o;
+      if (lin == prev_lin && (om & ~prev_om) == 0) continue;
+      prev_om = lin == prev_lin ? (prev_om | om) : om;
+      prev_lin = lin;
       if (flags[lin] == 0) flags[lin] = 1;
       int* gf = flags + nlin;
 #pragma unroll
       for (int o = 0; o < G::NO; ++o)
         if ((om >> o) & 1u) {
-          const int t = (int)lin + oct_delta<D>(L, o);
-          if (gf[t] == 0) gf[t] = 1;
+          const int tt = (int)lin + oct_delta<D>(L, o);
+          if (gf[tt] == 0) gf[tt] = 1;
         }
     }
+    reinterpret_cast<uint4*>(keys)[t] = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -99,29 +109,34 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
   if (st->err) return;
   const int n = st->n_cur;
   const int lane = threadIdx.x & 31;
-  const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-    const bool valid = p < (uint32_t)n;
-    uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
-    const uint32_t key = valid ? keys[p] : INVALID_KEY;
-    if (key != INVALID_KEY) {
-      lin = key >> G::CB;
-      const int b = fscan[lin];
-      if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
-      else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
+  const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
+  const uint32_t nround = (nquad + 31u) & ~31u;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+    uint4 kq = make_uint4(INVALID_KEY, INVALID_KEY, INVALID_KEY, INVALID_KEY);
+    if (t < nquad) kq = __ldg(reinterpret_cast<const uint4*>(keys) + t);
+    const uint32_t kk[4] = {kq.x, kq.y, kq.z, kq.w};
+    uint32_t rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t key = kk[j];
+      uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
+      if (key != INVALID_KEY) {
+        lin = key >> G::CB;
+        const int b = fscan[lin];
+        if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
+        else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
+      }
+      const bool live = idx < 0xFFFFFF00u;
+      // one atomic per distinct bucket in the warp (neighbouring particles share cells)
+      const unsigned grp = __match_any_sync(0xffffffffu, idx);
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (live && lane == leader) base = atomicAdd(&cellcount[idx], __popc(grp));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      rr[j] = (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+      if (live && rr[j] == 0) pb_key[idx / G::CELLS] = lin;
     }
-    const bool live = idx < 0xFFFFFF00u;
-    // one atomic per distinct bucket in the warp (neighbouring particles share cells)
-    const unsigned grp = __match_any_sync(0xffffffffu, idx);
-    const int leader = __ffs(grp) - 1;
-    int base = 0;
-    if (live && lane == leader) base = atomicAdd(&cellcount[idx], __popc(grp));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (live) {
-      const uint32_t r = (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-      rank[p] = r;
-      if (r == 0) pb_key[idx / G::CELLS] = lin;
-    }
+    if (t < nquad) reinterpret_cast<uint4*>(rank)[t] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
   }
 }
 
@@ -132,11 +147,17 @@ __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t*
   using G = Geo<D>;
   if (st->err) return;
   const int n = st->n_cur;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
-    const uint32_t key = keys[p];
-    if (key == INVALID_KEY) continue;
-    const int b = fscan[key >> G::CB];
-    perm[cellstart[(size_t)b * G::CELLS + (key & (G::CELLS - 1))] + rank[p]] = p;
+  const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nquad; t += gridDim.x * blockDim.x) {
+    const uint4 kq = __ldg(reinterpret_cast<const uint4*>(keys) + t);
+    const uint4 rq = __ldg(reinterpret_cast<const uint4*>(rank) + t);
+    const uint32_t kk[4] = {kq.x, kq.y, kq.z, kq.w}, rr[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (kk[j] == INVALID_KEY) continue;
+      const int b = fscan[kk[j] >> G::CB];
+      perm[cellstart[(size_t)b * G::CELLS + (kk[j] & (G::CELLS - 1))] + rr[j]] = 4u * t + j;
+    }
   }
 }
 
