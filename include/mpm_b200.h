@@ -187,6 +187,18 @@ int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream);
 int mpm_phase_halo_add(mpm_ctx* ctx, const void* from_lo_dev, const void* from_hi_dev, void* stream);
 int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream);
 int mpm_batch_end(mpm_ctx* ctx, void* stream);
+/* Peer path: the producing kernels (halo pack, G2P) write their records directly into the
+ * neighbour's receive buffers over NVLink (CUDA IPC mapping) and publish a per-substep epoch
+ * with a system-scope release store; the consumer spins on its local epoch word (4 s
+ * time-out).  No NCCL call and no host work per substep.  mpm_peer_alloc makes the one
+ * cudaMalloc block this library owns (IPC needs a whole allocation); the 64-byte handle is
+ * exchanged by the host (all_gather) and opened with mpm_peer_open (side 0 = -x neighbour). */
+int mpm_peer_alloc(mpm_ctx* ctx, int32_t mig_capacity, int32_t halo_capacity);
+int mpm_peer_handle(mpm_ctx* ctx, void* out64);
+int mpm_peer_open(mpm_ctx* ctx, int32_t side, const void* handle64);
+/* `count` substeps (or, deliver_only != 0, just the pending particle delivery) inside
+ * mpm_batch_begin/mpm_batch_end; every rank must call it with the same arguments */
+int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t deliver_only, void* stream);
 /* rows [0, n) of one state word in storage order (pair with the `id` word) */
 int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream);
 

@@ -96,6 +96,10 @@ SYMBOLS = [
     ('mpm_phase_halo_add', _i32, [_vp, _vp, _vp, _vp]),
     ('mpm_phase_g2p', _i32, [_vp, _dbl, _vp]),
     ('mpm_batch_end', _i32, [_vp, _vp]),
+    ('mpm_peer_alloc', _i32, [_vp, _i32, _i32]),
+    ('mpm_peer_handle', _i32, [_vp, _vp]),
+    ('mpm_peer_open', _i32, [_vp, _i32, _vp]),
+    ('mpm_peer_substeps', _i32, [_vp, _dbl, _i32, _i32, _vp]),
     ('mpm_download_raw', _i32, [_vp, _i32, _vp, _vp]),
     ('mpm_voxelize', _i32, [_i32, _vp, _i64, _vp, _dbl, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_voxel_sample', _i32, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dp, _i32, _i32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp]),

@@ -41,7 +41,12 @@ struct mpm_ctx {
   int64_t table_cap = 0;
   bool dense = false;   // counting-sort path usable for the current layout
   Slab slab{0, INT_MIN, INT_MAX};
-  CommBufs comm{{nullptr, nullptr}, {nullptr, nullptr}, 0, 0};
+  CommBufs comm{{nullptr, nullptr}, {nullptr, nullptr}, 0, 0, {nullptr, nullptr}, {nullptr, nullptr}};
+  // peer path (NVLink writes into the neighbour's buffers)
+  uint32_t* peer_region = nullptr;     // cudaMalloc'ed by mpm_peer_alloc: flags + the four receive buffers
+  size_t peer_mig_words = 0, peer_halo_words = 0;
+  void* peer_open[2] = {nullptr, nullptr};
+  uint32_t epoch = 0;                  // substeps completed since mpm_peer_alloc (same on every rank)
   bool ext_box = false;          // layout box supplied by the host (global box of all ranks)
   int box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
   // state of the batch being enqueued (phase API)
@@ -221,9 +226,11 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   return MPM_OK;
 }
 
+static void peer_close(mpm_ctx* ctx);
 extern "C" int mpm_destroy(mpm_ctx* ctx) {
   if (!ctx) return MPM_E_INVALID;
   cudaSetDevice(ctx->P.device);
+  peer_close(ctx);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   delete ctx;
@@ -592,7 +599,7 @@ static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cud
       ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
   if (prof) cudaEventRecord(ev[3], s);
   launch_g2p<D>(ctx, a, s);
-  if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, st); ctx->launches += 1; }
+  if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, st); ctx->launches += 1; }
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
   ctx->launches += 2;   // grid op, g2p
@@ -775,7 +782,7 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
   else
     k_mig_unpack<2><<<blocks, 256, 0, s>>>(ctx->state[cur], ctx->cap, (const uint32_t*)from_lo, (const uint32_t*)from_hi,
                                            ctx->comm.mig_cap, ctx->d_status);
-  k_mig_commit<<<1, 1, 0, s>>>((const uint32_t*)from_lo, (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status);
+  k_mig_commit<<<1, 1, 0, s>>>((uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status);
   CK(cudaGetLastError());
   ctx->launches += 2;
   return MPM_OK;
@@ -801,7 +808,7 @@ extern "C" int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream) {
       k_halo_pack<2><<<blocks, 256, 0, s>>>(ctx->grid, ctx->gb_key, ctx->L, bx, ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status);
     ctx->launches += 1;
   }
-  k_halo_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->d_status);
+  k_halo_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return MPM_OK;
@@ -870,6 +877,93 @@ extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
   ctx->err = buf;
   if (h.err == ERR_BLOCK_CAPACITY) { ctx->last.need_blocks = h.need_blocks; return MPM_E_BLOCK_CAPACITY; }
   return MPM_E_INVALID;
+}
+
+
+// ------------------------------------------------------------------ peer path (NVLink P2P, no NCCL per substep)
+// Region layout (32-bit words): [16 flag words][mig from lo][mig from hi][halo from lo][halo from hi]
+//   flag 0/1: migration epoch published by the lo/hi neighbour, flag 2/3: halo epoch
+static uint32_t* region_mig(mpm_ctx* c, uint32_t* base, int from_side) { return base + 16 + (size_t)from_side * c->peer_mig_words; }
+static uint32_t* region_halo(mpm_ctx* c, uint32_t* base, int from_side) { return base + 16 + 2 * c->peer_mig_words + (size_t)from_side * c->peer_halo_words; }
+
+extern "C" int mpm_peer_alloc(mpm_ctx* ctx, int32_t mig_cap, int32_t halo_cap) {
+  if (!ctx || mig_cap < 1 || halo_cap < 1) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  if (ctx->peer_region) return fail(ctx, MPM_E_INVALID, "mpm_peer_alloc: already allocated");
+  ctx->peer_mig_words = mpm_comm_bytes(ctx->dim, 0, mig_cap) / 4;
+  ctx->peer_halo_words = mpm_comm_bytes(ctx->dim, 1, halo_cap) / 4;
+  const size_t words = 16 + 2 * ctx->peer_mig_words + 2 * ctx->peer_halo_words;
+  // the one allocation this library owns: it has to be a whole cudaMalloc block to be exported over CUDA IPC
+  CK(cudaMalloc((void**)&ctx->peer_region, words * 4));
+  CK(cudaMemset(ctx->peer_region, 0, words * 4));
+  ctx->comm.mig_cap = mig_cap;
+  ctx->comm.halo_cap = halo_cap;
+  ctx->epoch = 0;
+  return MPM_OK;
+}
+extern "C" int mpm_peer_handle(mpm_ctx* ctx, void* out64) {
+  if (!ctx || !out64 || !ctx->peer_region) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->peer_region));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(out64, &h, 64);
+  return MPM_OK;
+}
+// side 0: handle of the -x neighbour, side 1: of the +x neighbour
+extern "C" int mpm_peer_open(mpm_ctx* ctx, int32_t side, const void* handle64) {
+  if (!ctx || (side != 0 && side != 1) || !handle64 || !ctx->peer_region) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->peer_open[side] = base;
+  uint32_t* pb = (uint32_t*)base;
+  // what I send to my -x neighbour arrives there as "from hi" (index 1), and vice versa
+  const int there = 1 - side;
+  ctx->comm.mig[side] = region_mig(ctx, pb, there);
+  ctx->comm.halo[side] = region_halo(ctx, pb, there);
+  ctx->comm.flag_mig[side] = pb + there;
+  ctx->comm.flag_halo[side] = pb + 2 + there;
+  return MPM_OK;
+}
+static void peer_close(mpm_ctx* ctx) {
+  for (int s = 0; s < 2; ++s)
+    if (ctx->peer_open[s]) { cudaIpcCloseMemHandle(ctx->peer_open[s]); ctx->peer_open[s] = nullptr; }
+  if (ctx->peer_region) { cudaFree(ctx->peer_region); ctx->peer_region = nullptr; }
+}
+
+// `count` substeps inside an open batch; every rank calls it with the same count
+extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t deliver_only, void* stream) {
+  REQUIRE_BATCH();
+  if (!ctx->peer_region || !ctx->slab.enabled) return fail(ctx, MPM_E_INVALID, "mpm_peer_substeps: peer path not set up");
+  uint32_t* me = ctx->peer_region;
+  const bool has[2] = {ctx->peer_open[0] != nullptr, ctx->peer_open[1] != nullptr};
+  uint32_t* mig_from[2] = {has[0] ? region_mig(ctx, me, 0) : nullptr, has[1] ? region_mig(ctx, me, 1) : nullptr};
+  uint32_t* halo_from[2] = {has[0] ? region_halo(ctx, me, 0) : nullptr, has[1] ? region_halo(ctx, me, 1) : nullptr};
+  const int n_iter = deliver_only ? 1 : count;
+  for (int i = 0; i < n_iter; ++i) {
+    // leavers of the neighbours' last G2P (epoch = substeps completed so far)
+    k_wait_flags<<<1, 1, 0, s>>>(has[0] ? me + 0 : nullptr, has[1] ? me + 1 : nullptr, ctx->epoch, ctx->d_status);
+    ctx->launches += 1;
+    int rc = mpm_phase_unpack(ctx, mig_from[0], mig_from[1], stream);
+    if (rc) return rc;
+    if (deliver_only) break;
+    rc = mpm_phase_p2g(ctx, dt, stream);
+    if (rc) return rc;
+    rc = mpm_phase_halo_pack(ctx, stream);          // records + epoch go straight to the neighbours
+    if (rc) return rc;
+    k_wait_flags<<<1, 1, 0, s>>>(has[0] ? me + 2 : nullptr, has[1] ? me + 3 : nullptr, ctx->epoch + 1, ctx->d_status);
+    ctx->launches += 1;
+    rc = mpm_phase_halo_add(ctx, halo_from[0], halo_from[1], stream);
+    if (rc) return rc;
+    rc = mpm_phase_g2p(ctx, dt, stream);            // leavers + epoch go straight to the neighbours
+    if (rc) return rc;
+    ctx->epoch += 1;
+  }
+  CK(cudaGetLastError());
+  return MPM_OK;
 }
 
 // local rows [0, n) of one state word in storage order (no id un-permutation)

@@ -44,6 +44,7 @@ __global__ void k_halo_pack(const float4* __restrict__ grid, const uint32_t* __r
     if (lane == 0) buf[COMM_HEADER + idx] = halo_key(rel[1] + L.ob[1], D == 3 ? rel[D - 1] + L.ob[D - 1] : 0);
     float4* out = reinterpret_cast<float4*>(buf + COMM_HEADER + halo_cap) + (size_t)idx * G::CELLS;
     for (int c = lane; c < G::CELLS; c += 32) out[c] = grid[(size_t)g * G::CELLS + c];
+    __threadfence_system();   // peer path: the records may live in the neighbour's memory
   }
 }
 
@@ -83,21 +84,53 @@ __global__ void k_halo_add(float4* __restrict__ grid, const int* __restrict__ fl
   }
 }
 
-// message headers (one thread): counts, overflow detection
-__global__ void k_halo_headers(CommBufs cb, Status* st) {
+// ---- peer path: producer kernels write straight into the neighbour's receive buffers
+// over NVLink; a release-store of the substep epoch tells the neighbour the data is
+// complete, an acquire-spin on the local epoch word (with a time-out) gates its consumer.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread: wait until both neighbours have published `epoch` (null = no neighbour)
+__global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t epoch, Status* st) {
+  const unsigned long long t0 = global_ns();
+  const uint32_t* f[2] = {f0, f1};
+  for (int s = 0; s < 2; ++s) {
+    if (!f[s]) continue;
+    while ((int32_t)(ld_acquire_sys(f[s]) - epoch) < 0) {
+      if (global_ns() - t0 > 4000000000ull) { st->err |= ERR_COMM_TIMEOUT; return; }   // 4 s: the peer is gone
+      __nanosleep(200);
+    }
+  }
+}
+
+// message headers (one thread): counts, overflow detection, and (peer path) the signal.
+// They run even after a device error so that a neighbour never waits for ever.
+__global__ void k_halo_headers(CommBufs cb, uint32_t epoch, Status* st) {
   for (int s = 0; s < 2; ++s) {
     if (!cb.halo[s]) continue;
     int c = st->err ? 0 : st->halo_cnt[s];
     if (c > cb.halo_cap) { st->err |= ERR_COMM_CAPACITY; c = 0; }
     cb.halo[s][0] = (uint32_t)c;
+    if (cb.flag_halo[s]) { __threadfence_system(); st_release_sys(cb.flag_halo[s], epoch); }
   }
 }
-__global__ void k_mig_headers(CommBufs cb, Status* st) {
+__global__ void k_mig_headers(CommBufs cb, uint32_t epoch, Status* st) {
   for (int s = 0; s < 2; ++s) {
     if (!cb.mig[s]) continue;
     int c = st->err ? 0 : st->mig_cnt[s];
     if (c > cb.mig_cap) { st->err |= ERR_COMM_CAPACITY; c = 0; }
     cb.mig[s][0] = (uint32_t)c;
+    if (cb.flag_mig[s]) { __threadfence_system(); st_release_sys(cb.flag_mig[s], epoch); }
   }
   if (!st->err) st->n_cur = st->n_live;    // rows of the set G2P just wrote
 }
@@ -123,11 +156,13 @@ __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uin
     state[(size_t)f * cap + base + r] = v;
   }
 }
-__global__ void k_mig_commit(const uint32_t* from_lo, const uint32_t* from_hi, int mig_cap, Status* st) {
+__global__ void k_mig_commit(uint32_t* from_lo, uint32_t* from_hi, int mig_cap, Status* st) {
   if (st->err) return;
   const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
   const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
   st->n_cur += c0 + c1;
+  if (from_lo) from_lo[0] = 0;   // consumed: a second unpack of the same message appends nothing
+  if (from_hi) from_hi[0] = 0;
 }
 
 }  // namespace mpm

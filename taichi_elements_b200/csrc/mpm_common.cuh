@@ -41,7 +41,7 @@ struct KeyLayout {
   int key_bits;
 };
 
-enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2, ERR_COMM_CAPACITY = 4, ERR_PARTICLE_CAPACITY = 8 };
+enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2, ERR_COMM_CAPACITY = 4, ERR_PARTICLE_CAPACITY = 8, ERR_COMM_TIMEOUT = 16 };
 
 // Device-resident status block, copied to pinned host memory after each batch.
 struct Status {
@@ -72,9 +72,11 @@ struct Slab {
 //   halo:      header | keys [halo_cap] | node records [halo_cap][CELLS] float4
 static constexpr int COMM_HEADER = 16;
 struct CommBufs {
-  uint32_t* mig[2];
-  uint32_t* halo[2];
+  uint32_t* mig[2];        // where leavers to the -x / +x rank are written: a local send buffer (NCCL
+  uint32_t* halo[2];       //   path) or the neighbour's receive buffer mapped over NVLink (peer path)
   int mig_cap, halo_cap;
+  uint32_t* flag_mig[2];   // peer path: the neighbour's "data ready" epoch words to release-store
+  uint32_t* flag_halo[2];
 };
 
 struct Grav { float g[3]; };

@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
             m[FL::COLOR * mc] = color;
             m[FL::ID * mc] = pid;
             m[FL::EMIT * mc] = emit;
+            __threadfence_system();   // peer path: the row may live in the neighbour's memory
           }
         }
       }

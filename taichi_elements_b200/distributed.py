@@ -103,9 +103,13 @@ def _make_distributed_solver():
         world-1 cut planes in absolute leaf-block units (see SlabDecomposition)."""
 
         def __init__(self, res, cuts, group=None, mig_capacity=1 << 16, halo_capacity=1 << 12, substep_batch=8,
-                     world=None, rank=None, **kw):
+                     world=None, rank=None, comm='auto', **kw):
             super().__init__(res, **kw)
             self.group = group
+            # 'peer': kernels write into the neighbour's buffers over NVLink (CUDA IPC), no NCCL per
+            # substep; 'nccl': packed buffers travel by torch.distributed send/recv; 'auto': peer when a
+            # process group with the nccl backend is up, else nccl/gloo
+            self.comm = comm
             # world/rank may be given explicitly (single-process loop-back tests drive several slabs by hand)
             self.world = dist.get_world_size(group) if world is None else world
             self.rank = dist.get_rank(group) if rank is None else rank
@@ -130,6 +134,27 @@ def _make_distributed_solver():
             self._check(
                 lib.mpm_bind_comm(self._ctx, ptr(self._mig_send[0]), ptr(self._mig_send[1]), self._mig_cap,
                                   ptr(self._halo_send[0]), ptr(self._halo_send[1]), self._halo_cap), 'mpm_bind_comm')
+            if self.comm == 'auto':
+                use_peer = (world is None and self.world > 1 and dist.is_initialized()
+                            and dist.get_backend(group) == 'nccl')
+                self.comm = 'peer' if use_peer else 'nccl'
+            if self.comm == 'peer':
+                self._setup_peer()
+
+        def _setup_peer(self):
+            """Exchange CUDA IPC handles of the receive regions and map the neighbours' ones."""
+            lib, ctx = self._lib, self._ctx
+            self._check(lib.mpm_peer_alloc(ctx, self._mig_cap, self._halo_cap), 'mpm_peer_alloc')
+            h = (ctypes.c_uint8 * 64)()
+            self._check(lib.mpm_peer_handle(ctx, h), 'mpm_peer_handle')
+            mine = torch.tensor(list(h), dtype=torch.uint8, device=self._device)
+            allh = [torch.empty(64, dtype=torch.uint8, device=self._device) for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=self.group)
+            for side, peer in ((0, self.slab.left), (1, self.slab.right)):
+                if peer is not None:
+                    buf = (ctypes.c_uint8 * 64)(*allh[peer].cpu().tolist())
+                    self._check(lib.mpm_peer_open(ctx, side, buf), 'mpm_peer_open')
+            dist.barrier(group=self.group)
 
         # ---- seeding: same call on every rank, each keeps its slab -------------
         def add_particles(self, particles, material, color=0xFFFFFF, velocity=None):
@@ -146,6 +171,8 @@ def _make_distributed_solver():
                 self._state[cur.value, id_row, n0:n0 + len(ids)] = torch.from_numpy(ids).to(self._device)
 
         def clear_particles(self):
+            if self.comm == 'peer' and self._n > 0:
+                self.flush_migration()       # drain what the last substep published to the neighbours
             super().clear_particles()
             self._global_n = 0
             for t in self._mig_send:
@@ -224,11 +251,15 @@ def _make_distributed_solver():
                 if glo[0] > ghi[0]:
                     return self.stats()          # no particles anywhere
                 self._batch_begin(glo, ghi)
-                for _ in range(nb):
-                    self._exchange_migration()
-                    self._substep_pre(dt)
-                    self._exchange_halo()
-                    self._substep_post(dt)
+                if self.comm == 'peer':
+                    self._check(self._lib.mpm_peer_substeps(self._ctx, dt, nb, 0, self._stream()),
+                                'mpm_peer_substeps')
+                else:
+                    for _ in range(nb):
+                        self._exchange_migration()
+                        self._substep_pre(dt)
+                        self._exchange_halo()
+                        self._substep_post(dt)
                 rc = self._batch_end()
                 # every rank must agree on success before the next batch is enqueued
                 flag = torch.tensor([abs(rc)], dtype=torch.int32, device=self._device)
@@ -253,6 +284,11 @@ def _make_distributed_solver():
             if glo[0] > ghi[0]:
                 return
             self._batch_begin(glo, ghi)
+            if self.comm == 'peer':
+                self._check(self._lib.mpm_peer_substeps(self._ctx, 0.0, 0, 1, self._stream()), 'mpm_peer_substeps')
+                if self._batch_end() != 0:
+                    raise _lib.MPMError('flush_migration: ' + self._lib.mpm_last_error(self._ctx).decode())
+                return
             if exchange is None:
                 self._exchange_migration()
             else:

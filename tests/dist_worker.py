@@ -19,6 +19,7 @@ def main():
     from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
     from taichi_elements_b200.engine.mpm_solver import MPMSolver
     dim, res, steps = 3, 32, 24
+    comm = os.environ.get('MPM_COMM', 'auto')
     scene = []
     for i, (p, m, vel) in enumerate(mixed_scene(dim, n_per=500, seed=11)):
         vel = list(vel)
@@ -27,7 +28,7 @@ def main():
     allx = np.concatenate([p for p, _, _ in scene])
     s = DistributedMPMSolver((res, ) * dim, cuts=[0] * 0 if world == 1 else
                              SlabDecomposition.balanced_cuts(allx[:, 0], world, 4, 4096, float(res)),
-                             mig_capacity=4096, halo_capacity=512, substep_batch=6, device=local)
+                             mig_capacity=4096, halo_capacity=512, substep_batch=6, device=local, comm=comm)
     for p, m, vel in scene:
         s.add_particles(p, m, velocity=vel)
     s.reserve_blocks(4096)
@@ -46,7 +47,7 @@ def main():
         ok = (len(got['id']) == n and np.array_equal(got['id'], np.arange(n))
               and np.abs(got['x'] - ref.x.to_numpy()).max() <= 2e-5
               and np.abs(got['v'] - ref.v.to_numpy()).max() <= 5e-3 * vs)
-        print('max dx', np.abs(got['x'] - ref.x.to_numpy()).max(), 'max dv', np.abs(got['v'] - ref.v.to_numpy()).max())
+        print('comm', s.comm, 'max dx', np.abs(got['x'] - ref.x.to_numpy()).max(), 'max dv', np.abs(got['v'] - ref.v.to_numpy()).max())
     flag = torch.tensor([int(ok)], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -131,11 +131,13 @@ def test_phase_api_equals_substeps_single_rank():
     assert np.abs(got['v'] - ref.v.to_numpy()).max() <= 1e-4 * float(np.abs(ref.v.to_numpy()).max())
 
 
-def test_nccl_two_ranks_match_single_domain():
+@pytest.mark.parametrize('comm', ['peer', 'nccl'])
+def test_two_ranks_match_single_domain(comm):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    port = 29600 + os.getpid() % 1000
+    os.environ['MPM_COMM'] = comm
+    port = 29600 + os.getpid() % 1000 + (7 if comm == 'peer' else 0)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
            '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'dist_worker.py')]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
