@@ -171,8 +171,8 @@ def _make_distributed_solver():
                 self._state[cur.value, id_row, n0:n0 + len(ids)] = torch.from_numpy(ids).to(self._device)
 
         def clear_particles(self):
-            if self.comm == 'peer' and self._n > 0:
-                self.flush_migration()       # drain what the last substep published to the neighbours
+            if self.comm == 'peer':
+                self.flush_migration()       # collective: drain what the last substep published to the neighbours
             super().clear_particles()
             self._global_n = 0
             for t in self._mig_send:
