@@ -173,7 +173,7 @@ class MPMSolver:
         self.writers = []
         self.rng_seed = 0          # base of the counter-based seeding generator
         self._seed_calls = 0
-        self.substep_batch = 0     # >0: enqueue that many substeps per host sync
+        self.substep_batch = 16    # substeps enqueued per host synchronisation (1 = the reference's per-substep read-back)
 
         # ---- native engine -------------------------------------------------
         if not torch.cuda.is_available():
