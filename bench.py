@@ -170,6 +170,7 @@ def main():
     ap.add_argument('--workload', default='cube_drop_4m')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--strong', action='store_true', help='N > 1: split the N=1 scene over the ranks (strong scaling)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return main_reference(args)
@@ -199,7 +200,11 @@ def main():
             else:
                 from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
                 res = w['res'][0]
-                cuts = [int((math.floor((x0 + side * k) * res) + 2048) // 4) for k in range(1, world)]
+                if args.strong:
+                    allx = np.concatenate([x[:, 0] for x, _ in w['parts']])
+                    cuts = SlabDecomposition.balanced_cuts(allx, world, 4, 4096, float(res))
+                else:
+                    cuts = [int((math.floor((x0 + side * k) * res) + 2048) // 4) for k in range(1, world)]
                 s = DistributedMPMSolver(res=w['res'], cuts=cuts, size=1, unbounded=False, device=local,
                                          mig_capacity=1 << 14, halo_capacity=1 << 11, substep_batch=20,
                                          comm=os.environ.get('MPM_COMM', 'auto'))
@@ -213,7 +218,7 @@ def main():
     import math
     side = 0.25
     x0 = 0.5 - side * world / 2
-    if world == 1:
+    if world == 1 or args.strong:
         bricks = [w['parts']]
     else:
         bricks = []
@@ -344,7 +349,7 @@ def main():
         line = {
             'metric': 'particle-substeps/sec', 'value': value, 'unit': 'particle-substeps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f"configs[1] 3D cube drop, res 256^3 bounded, {n_total} particles "
                                    f"(ELASTIC cube over WATER cube, 8 per cell), g=(0,-20,0), dt=3e-3/39"
                                    if args.workload == 'cube_drop_4m' else args.workload,
