@@ -410,6 +410,11 @@ static int update_layout(mpm_ctx* ctx) {
   for (int d = 0; d < ctx->dim; ++d) {
     const int lo = ctx->ext_box ? ctx->box_min[d] : ctx->bb_min[d];
     const int hi = ctx->ext_box ? ctx->box_max[d] : ctx->bb_max[d];
+    // NaN/inf positions (a diverged simulation) show up as an absurd box: refuse before any index math
+    if (lo > hi || lo < -(1 << 28) || hi > (1 << 28) || (int64_t)hi - lo > ((int64_t)1 << 24)) {
+      ctx->layout_valid = false;
+      return fail(ctx, MPM_E_KEY_BITS, "particle bounding box is not finite/representable (diverged simulation?)");
+    }
     bmin[d] = (lo + half) >> ll;
     bmax[d] = (hi + half) >> ll;
     if (keep && !(bmin[d] >= ctx->L.ob[d] + 1 && bmax[d] <= ctx->L.ob[d] + ctx->L.eb[d] - 3)) keep = false;

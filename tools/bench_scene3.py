@@ -10,7 +10,7 @@ from oracle.seeding_oracle import icosphere
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--ellipsoids', type=int, default=482)
-ap.add_argument('--steps', type=int, default=100)
+ap.add_argument('--steps', type=int, default=50)   # the timed window covers free flight and the first floor contacts
 args = ap.parse_args()
 with contextlib.redirect_stdout(io.StringIO()):
     s = MPMSolver(res=(256, 256, 256), unbounded=True)
