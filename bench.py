@@ -206,7 +206,8 @@ def main():
                 else:
                     cuts = [int((math.floor((x0 + side * k) * res) + 2048) // 4) for k in range(1, world)]
                 s = DistributedMPMSolver(res=w['res'], cuts=cuts, size=1, unbounded=False, device=local,
-                                         mig_capacity=1 << 14, halo_capacity=1 << 11, substep_batch=20,
+                                         mig_capacity=1 << 14 if not args.strong else 1 << 16,
+                                         halo_capacity=1 << 11 if not args.strong else 1 << 13, substep_batch=20,
                                          comm=os.environ.get('MPM_COMM', 'auto'))
                 s.reserve_blocks(1 << 16)
         s.set_gravity(w['gravity'])

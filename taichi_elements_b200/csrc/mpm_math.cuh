@@ -138,6 +138,8 @@ MPM_HD void svd3(const float* F, float* U, float* sig, float* V) {
   V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1;
 #pragma unroll 1
   for (int sweep = 0; sweep < 4; ++sweep) {
+    // F^T F of an MPM particle is close to diagonal: most lanes are done after two sweeps
+    if (a01 * a01 + a02 * a02 + a12 * a12 <= 1e-15f * (a00 * a00 + a11 * a11 + a22 * a22)) break;
     jacobi_rot(a00, a11, a01, a02, a12, V, 0, 1);
     jacobi_rot(a00, a22, a02, a01, a12, V, 0, 2);
     jacobi_rot(a11, a22, a12, a01, a02, V, 1, 2);
