@@ -232,6 +232,8 @@ def main():
         for x, m in parts:
             mpm.add_particles(x, m)
     n_local = mpm.n_particles[None]
+    if world > 1:
+        mpm.reserve_blocks(max(1 << 16, n_local // 128))   # block capacity cannot grow inside a distributed batch
     dt = w['frame_dt'] / (int(w['frame_dt'] / mpm.default_dt) + 1)
     if w['res'][0] != 256:
         dt = mpm.default_dt
