@@ -284,8 +284,8 @@ def main():
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of k_p2g_cell<3> on this workload, one ncu --set full
-        # capture (profiles/r01_ncu_p2g_g2p_v3.md): 466.1 MB + 153.1 MB per launch
-        'traffic': 619.2e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
+        # capture (profiles/r01_ncu_final.md): 479.4 MB + 155.5 MB per launch
+        'traffic': 634.9e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
         'peak_source': peak_src,
         'algorithmic_bytes_per_launch': b_alg_p2g,
         'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
