@@ -44,7 +44,7 @@ extern "C" {
 #define MPM_E_CUDA (-2)
 #define MPM_E_UNBOUND (-3)
 
-#define MPM_ABI_VERSION 1
+#define MPM_ABI_VERSION 2
 
 typedef struct mpm_ctx mpm_ctx;
 
@@ -59,12 +59,13 @@ typedef struct mpm_params {
   int32_t padding;         /* :52 */
   int32_t support_plasticity;
   int32_t device;          /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t flags;           /* bit 0: use_g2p2g (:57), bit 1: quant (F clamp in g2p2g, :99, 415-416) */
   double dx, inv_dx;       /* :82-83 */
   double p_vol, p_mass;    /* :85-87 */
   double mu_0, lambda_0;   /* :203-205 */
   double alpha;            /* :208-210 */
   double water_density;    /* :61 */
+  double g2p2g_cfl;        /* g2p2g_allowed_cfl if v_clamp_g2p2g else 0: grid-velocity clamp (:589, 596-598) */
 } mpm_params;
 
 /* One entry of MPMSolver.grid_postprocess, applied in order after
@@ -91,7 +92,7 @@ typedef struct mpm_stats {
   float max_velocity;        /* compute_max_velocity (:726-735): max over the substeps of the last call */
   int32_t launches;          /* kernels launched by the last mpm_substep(s) call */
   int32_t substeps_done;     /* substeps completed by the last mpm_substep(s) call */
-  int32_t reserved;
+  float max_grid_velocity;   /* compute_max_grid_velocity (:737-746) of the last substep's grid */
   float ms_sort, ms_p2g, ms_grid, ms_g2p; /* filled when profiling is enabled */
 } mpm_stats;
 
@@ -137,7 +138,10 @@ int mpm_seed_ellipsoid(mpm_ctx* ctx, int64_t n, const double* center, const doub
 int mpm_seed_restart(mpm_ctx* ctx, const float* x_dev, const float* v_dev, const int32_t* material_dev,
                      const int32_t* color_dev, int64_t n, void* stream);
 
-/* One substep of step() (:789-799): deactivate_all, build_pid, p2g,
+/* With flags bit 0 (use_g2p2g) a substep is the fused order of :773-787 -- gather from the
+ * previous substep's grid, advect, then bin/scatter/grid-op at the new positions -- with the
+ * semantic differences of the g2p2g kernel (:363-485).
+ * One substep of step() (:789-799): deactivate_all, build_pid, p2g,
  * grid_normalization_and_gravity, grid_postprocess[*], g2p, compute_max_velocity.
  * On MPM_OK the live set has flipped; on a recoverable code nothing changed. */
 int mpm_substep(mpm_ctx* ctx, double dt, double t, void* stream);

@@ -139,7 +139,15 @@ class OracleMPM:
     (engine/mpm_solver.py:44-310, 344-361, 487-616, 618-735, 748-805)."""
 
     def __init__(self, res, size=1, padding=3, unbounded=False, dt_scale=1,
-                 E_scale=1, water_density=1.0, support_plasticity=True):
+                 E_scale=1, water_density=1.0, support_plasticity=True,
+                 use_g2p2g=False, v_clamp_g2p2g=True, g2p2g_allowed_cfl=0.9, quant=False):
+        self.use_g2p2g = use_g2p2g                                # :57, 69
+        self.v_clamp_g2p2g = v_clamp_g2p2g
+        self.g2p2g_allowed_cfl = g2p2g_allowed_cfl
+        self.quant = quant
+        self.F_bound = 4.0                                        # :99
+        self.last_time_final_particles = 0                        # :124
+        self._prev_grid = None                                    # (sorted linear cell keys, velocities)
         self.dim = len(res)
         assert self.dim in (2, 3)
         self.res = tuple(res)
@@ -285,7 +293,9 @@ class OracleMPM:
                 f32(0.5) * (fx - f32(0.5)) ** 2]
 
     # ---- P2G (:487-584) -----------------------------------------------------
-    def p2g(self, dt):
+    def p2g(self, dt, g2p2g=False):
+        """P2G of the split path (:487-584); g2p2g=True switches to the P2G half of the fused
+        kernel (:405-483), whose differences are marked [g2p2g]."""
         dt = f32(dt)
         d = self.dim
         n = self.n_particles
@@ -297,17 +307,19 @@ class OracleMPM:
         I = np.eye(d, dtype=f32)
         F = self.F.copy()                                         # :507
         water = mat == MATERIAL_WATER
-        if water.any():                                           # :508-511
+        if water.any() and not g2p2g:                             # :508-511 ([g2p2g] keeps the stored F, :414)
             Fw = np.tile(I, (int(water.sum()), 1, 1))
             if self.support_plasticity:
                 Fw[:, 0, 0] = self.Jp[water]
             F[water] = Fw
         F = _mm((I[None] + dt * C).astype(f32), F)                # :513
+        if g2p2g and self.quant:                                  # [g2p2g] :415-416
+            F = np.maximum(f32(-self.F_bound), np.minimum(f32(self.F_bound), F)).astype(f32)
         h = np.ones(n, f32)                                       # :515-521
         if self.support_plasticity:
             with np.errstate(over='ignore'):
                 hh = np.exp(f32(10) * (f32(1.0) - self.Jp)).astype(f32)
-            h = np.where(~water, hh, h).astype(f32)
+            h = hh if g2p2g else np.where(~water, hh, h).astype(f32)   # [g2p2g] hardens water too (:419-421)
         h = np.where(mat == MATERIAL_ELASTIC, f32(0.3), h).astype(f32)
         mu = (f32(self.mu_0) * h).astype(f32)
         la = (f32(self.lambda_0) * h).astype(f32)
@@ -334,7 +346,7 @@ class OracleMPM:
             Fw = np.tile(I, (int(water.sum()), 1, 1))
             Fw[:, 0, 0] = J[water]
             F[water] = Fw
-            if self.support_plasticity:
+            if self.support_plasticity and not g2p2g:             # [g2p2g] does not reset Jp (:440-444)
                 Jp[water] = J[water]
         if snow.any():                                            # :543-545
             F[snow] = _mm(_mm(U[snow], _diag(sig[snow])), _T(V[snow]))
@@ -366,7 +378,8 @@ class OracleMPM:
                     f32(self.inv_dx ** 2))                        # :569
         stress = (scale * stress).astype(f32)
         mass = np.full(n, f32(self.p_mass), f32)                  # :571-573
-        mass = np.where(water, mass * f32(self.water_density), mass).astype(f32)
+        if not g2p2g:                                             # [g2p2g] has no water_density (:472, 570)
+            mass = np.where(water, mass * f32(self.water_density), mass).astype(f32)
         affine = (stress + mass[:, None, None] * C).astype(f32)   # :574
         self._affine, self._mass = affine, mass
 
@@ -418,6 +431,9 @@ class OracleMPM:
             vn = ((f32(1) / m)[:, None] * v).astype(f32)
         vn = (vn + dt * self.gravity[None]).astype(f32)
         v = np.where(pos[:, None], vn, v).astype(f32)
+        if self.g2p2g_allowed_cfl > 0 and self.use_g2p2g and self.v_clamp_g2p2g:   # :589, 596-598
+            v_allowed = f32(f32(self.dx * self.g2p2g_allowed_cfl) / dt)
+            v = np.minimum(np.maximum(v, -v_allowed), v_allowed).astype(f32)
         for c in self.colliders:
             if c.kind == 'bbox':
                 v = self._bbox(v, I, c.unbounded)
@@ -506,6 +522,58 @@ class OracleMPM:
         self.C = np.where(mov[:, None, None], new_C, self.C).astype(f32)
         self.x = np.where(mov[:, None], self.x + dt * self.v, self.x).astype(f32)
 
+    # ---- fused mode (:363-485, host :773-787) ------------------------------------
+    def _lin(self, cells):
+        shift = cells - np.array(self.offset, np.int64)
+        lin = np.zeros(cells.shape[0], np.int64)
+        for a in range(self.dim):
+            lin = lin * self.grid_size + shift[:, a]
+        return lin
+
+    def substep_g2p2g(self, dt):
+        """One use_g2p2g substep: gather from the previous output grid with the OLD positions,
+        advect, then scatter with the NEW positions into the other grid; normalise, clamp,
+        post-process."""
+        dtf = f32(dt)
+        d, n = self.dim, self.n_particles
+        inv_dx = f32(self.inv_dx)
+        base = self.base_index()
+        fx = (self.x * inv_dx - base.astype(f32)).astype(f32)
+        w = self._weights(fx)
+        new_v = np.zeros((n, d), f32)
+        C = np.zeros((n, d, d), f32)
+        old = np.arange(n) < self.last_time_final_particles         # :396-399
+        four_inv = f32(4 * self.inv_dx)
+        if self._prev_grid is not None and old.any():
+            keys, gv = self._prev_grid
+            for o in self._stencil():
+                lin = self._lin(base[old] + o[None])
+                pos = np.searchsorted(keys, lin)
+                assert np.array_equal(keys[pos], lin)
+                g_v = gv[pos]
+                dpos = (o.astype(f32)[None] - fx[old]).astype(f32)
+                weight = np.ones(int(old.sum()), f32)
+                for a in range(d):
+                    weight = (weight * w[o[a]][old, a]).astype(f32)
+                new_v[old] = (new_v[old] + weight[:, None] * g_v).astype(f32)
+                C[old] = (C[old] + (four_inv * weight)[:, None, None] * (g_v[:, :, None] * dpos[:, None, :])).astype(f32)
+        new_v[~old] = self.v[~old]
+        mov = self.material != MATERIAL_STATIONARY                # :401-403
+        self.v = np.where(mov[:, None], new_v, self.v).astype(f32)
+        self.x = np.where(mov[:, None], self.x + dtf * self.v, self.x).astype(f32)
+        self.C = C                                                # a register value in the reference (:385)
+        self.p2g(dt, g2p2g=True)
+        self.last_time_final_particles = n                        # :485
+        self.grid_op(dt, self.t)
+        self.t += float(dt)
+        order = np.argsort(self._lin(self.grid_cells))
+        self._prev_grid = (self._lin(self.grid_cells)[order], self.grid_v[order])
+
+    def compute_max_grid_velocity(self):                          # :737-746
+        if self.grid_v is None or len(self.grid_v) == 0:
+            return 0.0
+        return float(np.abs(self.grid_v).max())
+
     def compute_max_velocity(self):                               # :726-735
         if self.n_particles == 0:
             return 0.0
@@ -513,6 +581,8 @@ class OracleMPM:
 
     # ---- host loop (:748-805) ---------------------------------------------------
     def substep(self, dt):
+        if self.use_g2p2g:
+            return self.substep_g2p2g(dt)
         self.p2g(dt)
         self.grid_op(dt, self.t)
         self.t += float(dt)
@@ -529,6 +599,23 @@ class OracleMPM:
             count += 1
             left -= dt
         return dt, count
+
+    def step_adaptive(self, frame_dt, allowed_cfl=0.9):
+        """step() with use_adaptive_dt=True (:752-771): dt only ever shrinks inside a frame."""
+        substeps = int(frame_dt / self.default_dt) + 1
+        dt = frame_dt / substeps
+        left = frame_dt
+        dts = []
+        while left > 0:
+            self.total_substeps += 1
+            max_grid_v = self.compute_max_grid_velocity()
+            cfl_dt = allowed_cfl * self.dx / (max_grid_v + 1e-6)
+            dt = min(dt, cfl_dt, left)
+            left -= dt
+            self.substep(dt)
+            dts.append(dt)
+            self.all_time_max_velocity = max(self.all_time_max_velocity, self.compute_max_velocity())
+        return dts
 
     def step(self, frame_dt):
         dt, count = self.substep_schedule(frame_dt, self.default_dt)

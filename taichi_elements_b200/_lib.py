@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 MPM_OK = 0
 MPM_E_BLOCK_CAPACITY = 1
 MPM_E_KEY_BITS = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
@@ -29,11 +29,12 @@ class MPMParams(ctypes.Structure):
         ('dim', ctypes.c_int32), ('res', ctypes.c_int32 * 3),
         ('grid_size', ctypes.c_int32), ('leaf', ctypes.c_int32),
         ('padding', ctypes.c_int32), ('support_plasticity', ctypes.c_int32),
-        ('device', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('device', ctypes.c_int32), ('flags', ctypes.c_int32),
         ('dx', ctypes.c_double), ('inv_dx', ctypes.c_double),
         ('p_vol', ctypes.c_double), ('p_mass', ctypes.c_double),
         ('mu_0', ctypes.c_double), ('lambda_0', ctypes.c_double),
         ('alpha', ctypes.c_double), ('water_density', ctypes.c_double),
+        ('g2p2g_cfl', ctypes.c_double),
     ]
 
 
@@ -52,7 +53,7 @@ class MPMStats(ctypes.Structure):
         ('max_blocks', ctypes.c_int32), ('key_bits', ctypes.c_int32),
         ('bbox_min', ctypes.c_int32 * 3), ('bbox_max', ctypes.c_int32 * 3),
         ('max_velocity', ctypes.c_float), ('launches', ctypes.c_int32),
-        ('substeps_done', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('substeps_done', ctypes.c_int32), ('max_grid_velocity', ctypes.c_float),
         ('ms_sort', ctypes.c_float), ('ms_p2g', ctypes.c_float),
         ('ms_grid', ctypes.c_float), ('ms_g2p', ctypes.c_float),
     ]

@@ -50,6 +50,10 @@ struct mpm_ctx {
   bool ext_box = false;          // layout box supplied by the host (global box of all ranks)
   int box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
   // state of the batch being enqueued (phase API)
+  // g2p2g mode: a scatter half (bin + P2G + grid op) awaits its gather half
+  bool have_pending = false, pending_rebuild = false, skip_gather = false;
+  float pending_dt = 0.f;
+  int pending_n = 0, pending_npb = 0, pending_ngb = 0;
   bool in_batch = false;
   int batch_cur0 = 0, batch_enq = 0;
   const uint32_t* cur_keys = nullptr;
@@ -193,6 +197,9 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   K.inv_dx2 = (float)(p->inv_dx * p->inv_dx);
   K.four_inv_dx = (float)(4 * p->inv_dx);
   K.support_plasticity = p->support_plasticity;
+  K.g2p2g = (p->flags & 1) ? 1 : 0;
+  K.clamp_F = (p->flags & 2) ? 1 : 0;
+  K.v_allowed_cfl = (float)(p->dx * p->g2p2g_cfl);
   for (int d = 0; d < 3; ++d) ctx->gcfg.res[d] = p->res[d];
   ctx->gcfg.padding = p->padding;
   ctx->gcfg.grid_size = p->grid_size;
@@ -276,6 +283,7 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->table_cap = c.table_cap;
   ctx->ct_dirty = true;
   ctx->last_valid = false;
+  if (ctx->have_pending) ctx->pending_rebuild = true;   // the pending g2p2g half lived in the old workspace
   return MPM_OK;
 }
 
@@ -287,6 +295,10 @@ extern "C" int mpm_get_state(mpm_ctx* ctx, int32_t* cur, int64_t* n) {
 }
 extern "C" int mpm_set_state(mpm_ctx* ctx, int32_t cur, int64_t n) {
   if (!ctx || (cur != 0 && cur != 1) || n < 0 || (size_t)n > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_set_state: bad argument");
+  if (ctx->have_pending && n < ctx->pending_n) {
+    ctx->have_pending = false;   // particles were replaced or cleared: start over (all rows count as new)
+    ctx->skip_gather = false;
+  }
   ctx->cur = cur;
   ctx->n = n;
   ctx->bbox_valid = false;
@@ -512,6 +524,7 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.pb_key = ctx->pb_key; a.cellstart = ctx->cur_cellstart;
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
   a.slab = ctx->slab; a.cb = ctx->comm;
+  a.n_rows = (int)ctx->n;
   return a;
 }
 
@@ -594,21 +607,137 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
 }
 
 template <int D>
-static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
+static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s) {
   using G = Geo<D>;
+  k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, ctx->sm_count), 256, 0, s>>>(
+      ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt,
+      (ctx->K.g2p2g && ctx->K.v_allowed_cfl > 0.f) ? ctx->K.v_allowed_cfl / dt : 0.f, ctx->d_status);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return MPM_OK;
+}
+
+template <int D>
+static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
   const bool prof = ev != nullptr;
-  const int sm = ctx->sm_count;
   Status* st = ctx->d_status;
   SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
-  k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(
-      ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt, st);
+  int rc = enqueue_grid_op<D>(ctx, dt, s);
+  if (rc) return rc;
   if (prof) cudaEventRecord(ev[3], s);
   launch_g2p<D>(ctx, a, s);
   if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, st); ctx->launches += 1; }
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
-  ctx->launches += 2;   // grid op, g2p
+  ctx->launches += 1;   // g2p
   return MPM_OK;
+}
+
+// ---- g2p2g order (engine/mpm_solver.py:773-787): a substep is the GATHER half of the split
+// substep whose scatter half ran last (same particle sets, same binning), then a new scatter
+// half at the advected positions.  `cur` = live set before the call.
+template <int D>
+static int enqueue_gather_half(mpm_ctx* ctx, float dt, int cur, cudaStream_t s) {
+  const int n = (int)ctx->n;
+  const int r0 = ctx->have_pending ? ctx->pending_n : 0;
+  if (ctx->have_pending) {
+    SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
+    launch_g2p<D>(ctx, a, s);
+    ctx->launches += 1;
+  }
+  if (r0 < n) {
+    k_copy_advect<D><<<gs_blocks(n - r0, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[cur], ctx->state[cur ^ 1], ctx->cap, r0, n, dt,
+                                                                       ctx->K.inv_dx, ctx->d_status);
+    ctx->launches += 1;
+  }
+  k_half_commit<<<1, 1, 0, s>>>(ctx->d_status);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+template <int D>
+static int enqueue_scatter_half(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s) {
+  int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, nullptr);
+  if (rc) return rc;
+  return enqueue_grid_op<D>(ctx, dt, s);
+}
+
+static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
+  const bool d3 = ctx->dim == 3;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    int rc = refresh_bbox(ctx, s);
+    if (rc) return rc;
+    rc = update_layout(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+    if (ctx->have_pending && ctx->pending_rebuild) {
+      // the workspace was re-bound: redo the pending scatter half (same rows, same dt) so that its
+      // block structure and grid exist again; it is a pure function of the live set
+      k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n);
+      const int64_t n_keep = ctx->n;
+      ctx->n = ctx->pending_n;
+      rc = d3 ? enqueue_scatter_half<3>(ctx, ctx->pending_dt, ctx->cur, 0, s) : enqueue_scatter_half<2>(ctx, ctx->pending_dt, ctx->cur, 0, s);
+      ctx->n = n_keep;
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (ctx->h_status->err) {
+        ctx->bbox_valid = false; ctx->layout_valid = false;
+        if (ctx->h_status->err & ERR_BLOCK_CAPACITY) {
+          ctx->last.need_blocks = ctx->h_status->need_blocks;
+          ctx->err = "active leaf blocks exceed the bound capacity (rebuilding the pending g2p2g half)";
+          return MPM_E_BLOCK_CAPACITY;
+        }
+        continue;
+      }
+      ctx->pending_npb = ctx->h_status->npb; ctx->pending_ngb = ctx->h_status->ngb;
+      ctx->pending_rebuild = false;
+      CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+    }
+    k_batch_begin_keep<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, ctx->pending_npb, ctx->pending_ngb);
+    const int cur0 = ctx->cur;
+    int cur = cur0;
+    const bool skipped_first = ctx->skip_gather;
+    for (int i = 0; i < count; ++i) {
+      if (!(i == 0 && ctx->skip_gather)) {
+        rc = d3 ? enqueue_gather_half<3>(ctx, dt, cur, s) : enqueue_gather_half<2>(ctx, dt, cur, s);
+        if (rc) return rc;
+        cur ^= 1;
+      }
+      // from here on every row is binned: the pending description covers all n rows
+      ctx->have_pending = true; ctx->pending_n = (int)ctx->n; ctx->pending_dt = dt;
+      rc = d3 ? enqueue_scatter_half<3>(ctx, dt, cur, i > 0, s) : enqueue_scatter_half<2>(ctx, dt, cur, i > 0, s);
+      if (rc) return rc;
+    }
+    k_end<<<1, 1, 0, s>>>(ctx->d_status);
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const Status& h = *ctx->h_status;
+    ctx->cur = cur0 ^ (h.half & 1);
+    count -= h.done;
+    ctx->done_last += h.done;
+    ctx->skip_gather = false;
+    ctx->bbox_valid = false;            // the box of the advected positions is re-measured next batch
+    if (h.done > 0 || !h.err) { ctx->last = h; ctx->lastL = ctx->L; ctx->last_valid = (h.err == 0); }
+    if (!h.err) {
+      ctx->pending_npb = h.npb; ctx->pending_ngb = h.ngb;
+      return MPM_OK;
+    }
+    // a scatter half refused to run; its gather half (if it ran) is done and must not be repeated
+    const int halves = h.half + (skipped_first ? 1 : 0);
+    ctx->skip_gather = halves > h.done;
+    ctx->have_pending = false;
+    ctx->layout_valid = false;
+    if (h.err & ERR_BLOCK_CAPACITY) {
+      ctx->last.need_blocks = h.need_blocks;
+      char buf[160];
+      snprintf(buf, sizeof buf, "active leaf blocks (%d) exceed the bound capacity (%d)", h.need_blocks, ctx->max_blocks);
+      ctx->err = buf;
+      return MPM_E_BLOCK_CAPACITY;
+    }
+  }
+  return fail(ctx, MPM_E_INVALID, "g2p2g substep could not establish a key layout");
 }
 
 template <int D>
@@ -629,6 +758,10 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
   cudaStream_t s = (cudaStream_t)stream;
   int rc = upload_colliders(ctx, s);
   if (rc) return rc;
+  if (ctx->K.g2p2g) {
+    if (ctx->slab.enabled) return fail(ctx, MPM_E_INVALID, "g2p2g mode is single-GPU");
+    return substeps_g2p2g(ctx, (float)dt, count, s);
+  }
   for (int attempt = 0; attempt < 3; ++attempt) {
     rc = refresh_bbox(ctx, s);
     if (rc) return rc;
@@ -996,6 +1129,8 @@ extern "C" int mpm_get_stats(mpm_ctx* ctx, mpm_stats* o) {
   memcpy(&o->max_velocity, &bits, 4);
   o->launches = ctx->launches;
   o->substeps_done = ctx->done_last;
+  bits = ctx->last.maxgv_bits;
+  memcpy(&o->max_grid_velocity, &bits, 4);
   o->ms_sort = ctx->ms[0]; o->ms_p2g = ctx->ms[1]; o->ms_grid = ctx->ms[2]; o->ms_g2p = ctx->ms[3];
   return MPM_OK;
 }

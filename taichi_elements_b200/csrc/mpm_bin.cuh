@@ -185,6 +185,7 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
     st->halo_cnt[0] = st->halo_cnt[1] = 0;
     st->work_p2g = 0; st->work_g2p = 0;
     st->maxv_bits = 0;
+    st->maxgv_bits = 0;
     for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npb * G::NO; i += gridDim.x * blockDim.x) {

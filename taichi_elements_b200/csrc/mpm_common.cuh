@@ -59,7 +59,8 @@ struct Status {
   int n_live;       // particles binned this substep (= rows of the other set after G2P)
   int mig_cnt[2];   // particles leaving to the -x / +x neighbour rank (filled by G2P)
   int halo_cnt[2];  // packed boundary-column grid blocks (-x / +x side)
-  int pad[2];
+  unsigned maxgv_bits;  // max |grid v|_inf after the grid op (compute_max_grid_velocity)
+  int half;         // g2p2g: gather halves completed in this batch
 };
 
 // Slab decomposition along x (multi-GPU): this rank owns leaf-block columns

@@ -56,6 +56,7 @@ __global__ void k_reset(Status* st) {
   st->npb = 0; st->ngb_raw = 0; st->ngb = 0;
   st->work_p2g = 0; st->work_g2p = 0;
   st->maxv_bits = 0;
+  st->maxgv_bits = 0;
   for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
 }
 __global__ void k_batch_begin(Status* st, int n) { st->n_cur = n; st->n_live = n; }
@@ -275,6 +276,7 @@ template <int D> struct SubstepArgs {
   KeyLayout L;
   Consts K;
   float dt;
+  int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
   CommBufs cb;    // multi-GPU: migration / halo send buffers
 };
@@ -395,9 +397,10 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
 template <int D>
 __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict__ gb_key, KeyLayout L,
                           const ColliderTable* __restrict__ ct, Grav grav, GridCfg cfg, float dx, float dt,
-                          const Status* st) {
+                          float v_allowed, Status* st) {
   using G = Geo<D>;
   if (st->err) return;
+  float gvmax = 0.0f;
   const size_t total = (size_t)st->ngb * G::CELLS;
   const int ncol = ct->n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -417,6 +420,10 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
       float inv = __fdiv_rn(1.0f, m);
 #pragma unroll
       for (int d = 0; d < D; ++d) v[d] = __fadd_rn(__fmul_rn(inv, v[d]), __fmul_rn(dt, grav.g[d]));
+    }
+    if (v_allowed > 0.0f) {                                    // g2p2g grid-velocity clamp (:596-598)
+#pragma unroll
+      for (int d = 0; d < D; ++d) v[d] = fminf(fmaxf(v[d], -v_allowed), v_allowed);
     }
     for (int c = 0; c < ncol; ++c) {
       const ColliderDev& col = ct->c[c];
@@ -479,7 +486,13 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
     }
     if (D == 3) grid[i] = make_float4(v[0], v[1], v[2], m);
     else grid[i] = make_float4(v[0], v[1], m, 0.0f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) gvmax = fmaxf(gvmax, fabsf(v[d]));
   }
+  // compute_max_grid_velocity (engine/mpm_solver.py:737-746), folded into the pass
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gvmax = fmaxf(gvmax, __shfl_xor_sync(0xffffffffu, gvmax, o));
+  if ((threadIdx.x & 31) == 0 && gvmax > 0.0f) atomicMax(&st->maxgv_bits, __float_as_uint(gvmax));
 }
 
 // ------------------------------------------------------------------ G2P
@@ -655,8 +668,10 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       if (mat == (uint32_t)STATIONARY) {                       // :722
 #pragma unroll
         for (int d = 0; d < D; ++d) nv[d] = ldf(a.src, cap, FL::V + d, p);
+        if (!a.K.g2p2g) {      // [g2p2g] C is a register value there: the gathered C is used (:385, 414)
 #pragma unroll
-        for (int i = 0; i < D * D; ++i) nC[i] = ldf(a.src, cap, FL::C + i, p);
+          for (int i = 0; i < D * D; ++i) nC[i] = ldf(a.src, cap, FL::C + i, p);
+        }
       } else {
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, nv[d]));   // :724
@@ -725,6 +740,55 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     for (int d = 0; d < D; ++d)
       if (lo[d] <= hi[d]) { atomicMin(&a.st->bb_min[d], lo[d]); atomicMax(&a.st->bb_max[d], hi[d]); }
   }
+}
+
+
+// g2p2g: particles that are not in the pending binning (added since, or all of them on the
+// first substep) skip the gather (engine/mpm_solver.py:396-399): v kept, C = 0, advected
+// unless STATIONARY; the row is copied to the same row of the other set.
+template <int D>
+__global__ void k_copy_advect(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t cap, int r0, int n,
+                              float dt, float inv_dx, Status* st) {
+  using FL = Fld<D>;
+  if (st->err) return;
+  float vmax = 0.0f;
+  for (int p = r0 + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const uint32_t mat = ldu(src, cap, FL::MAT, p);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float v = ldf(src, cap, FL::V + d, p);
+      float x = ldf(src, cap, FL::X + d, p);
+      if (mat != (uint32_t)STATIONARY) x = __fadd_rn(x, __fmul_rn(dt, v));
+      stf(dst, cap, FL::X + d, p, x);
+      stf(dst, cap, FL::V + d, p, v);
+      vmax = fmaxf(vmax, fabsf(v));
+    }
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      stu(dst, cap, FL::F + i, p, ldu(src, cap, FL::F + i, p));
+      stf(dst, cap, FL::C + i, p, 0.0f);
+    }
+    stu(dst, cap, FL::JP, p, ldu(src, cap, FL::JP, p));
+    stu(dst, cap, FL::MAT, p, mat);
+    stu(dst, cap, FL::COLOR, p, ldu(src, cap, FL::COLOR, p));
+    stu(dst, cap, FL::ID, p, ldu(src, cap, FL::ID, p));
+    stu(dst, cap, FL::EMIT, p, ldu(src, cap, FL::EMIT, p));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&st->maxv_bits, __float_as_uint(vmax));
+}
+// end of the gather half of a g2p2g substep
+__global__ void k_half_commit(Status* st) {
+  if (st->err) return;
+  st->half += 1;
+  if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
+}
+// batch start in g2p2g mode: the pending scatter half's block structure stays valid
+__global__ void k_batch_begin_keep(Status* st, int n, int npb, int ngb) {
+  st->n_cur = n; st->n_live = n;
+  st->npb = npb; st->ngb = ngb;
+  st->work_g2p = 0; st->maxv_bits = 0;
 }
 
 // ------------------------------------------------------------------ seeding

@@ -29,6 +29,9 @@ struct Consts {
   float inv_dx2;          // inv_dx**2 as one f32 constant (:569)
   float four_inv_dx;      // 4*inv_dx as one f32 constant (:721)
   int support_plasticity;
+  int g2p2g;              // P2G half of the fused kernel (:405-483): see particle_update
+  int clamp_F;            // quant: F clamped to +-F_bound in g2p2g (:99, 415-416)
+  float v_allowed_cfl;    // dx * g2p2g_allowed_cfl, 0 = no grid-velocity clamp (:589, 596-598)
 };
 
 // Approximate (MUFU-based, ~1-2 ulp) division / reciprocal square root on the
@@ -325,8 +328,9 @@ template <int D>
 MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, const float* C,
                             float& Jp, float* affine, float& mass) {
   constexpr int DD = D * D;
+  const bool fused = K.g2p2g != 0;   // [g2p2g] differences, SURVEY Appendix D-1
   float Fin[DD];
-  if (material == WATER) {                                   // :508-511
+  if (material == WATER && !fused) {                         // :508-511 ([g2p2g] keeps the stored F, :414)
 #pragma unroll
     for (int i = 0; i < DD; ++i) Fin[i] = 0.0f;
 #pragma unroll
@@ -343,9 +347,13 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
   for (int i = 0; i < D; ++i) A[i * D + i] += 1.0f;
   float Fn[DD];
   matmul<D>(A, Fin, Fn);
+  if (fused && K.clamp_F) {                                  // [g2p2g] :415-416
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Fn[i] = fmaxf(-4.0f, fminf(4.0f, Fn[i]));
+  }
 
-  float h = 1.0f;                                            // :515-521
-  if (K.support_plasticity && material != WATER) h = expf(10.0f * (1.0f - Jp));
+  float h = 1.0f;                                            // :515-521 ([g2p2g] hardens water too, :419-421)
+  if (K.support_plasticity && (material != WATER || fused)) h = expf(10.0f * (1.0f - Jp));
   if (material == ELASTIC) h = 0.3f;
   float mu = K.mu_0 * h, la = K.lambda_0 * h;
   if (material == WATER) mu = 0.0f;
@@ -360,13 +368,13 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
 #pragma unroll
     for (int i = 0; i < D; ++i) Fn[i * D + i] = 1.0f;
     Fn[0] = J;                                               // :537-542
-    if (K.support_plasticity) Jp = J;
+    if (K.support_plasticity && !fused) Jp = J;              // [g2p2g] does not reset Jp (:440-444)
     float p = la * J * (J - 1.0f);
 #pragma unroll
     for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
 #pragma unroll
     for (int i = 0; i < D; ++i) stress[i * D + i] = p;
-    mass *= K.water_density;                                 // :571-573
+    if (!fused) mass *= K.water_density;                     // :571-573 ([g2p2g]: p_mass, :472)
   } else {
     float Rp[DD], Jpol = 1.0f;
     bool fast = false;

@@ -104,6 +104,8 @@ def _make_distributed_solver():
 
         def __init__(self, res, cuts, group=None, mig_capacity=1 << 16, halo_capacity=1 << 12, substep_batch=8,
                      world=None, rank=None, comm='auto', **kw):
+            if kw.get('use_g2p2g'):
+                raise NotImplementedError('use_g2p2g is single-GPU in this build')
             super().__init__(res, **kw)
             self.group = group
             # 'peer': kernels write into the neighbour's buffers over NVLink (CUDA IPC), no NCCL per

@@ -13,11 +13,13 @@ void host_svd2(const float* F, int n, float* U, float* sig, float* V) {
 void host_particle_update(int dim, const float* consts12, int support_plasticity, float dt, int n,
                           const int* material, float* F, const float* C, float* Jp,
                           float* affine, float* mass) {
-  mpm::Consts K;
+  mpm::Consts K{};
   K.dx = consts12[0]; K.inv_dx = consts12[1]; K.p_vol = consts12[2]; K.p_mass = consts12[3];
   K.mu_0 = consts12[4]; K.lambda_0 = consts12[5]; K.alpha = consts12[6]; K.sand_coef = consts12[7];
   K.water_density = consts12[8]; K.inv_dx2 = consts12[9]; K.four_inv_dx = consts12[10];
   K.support_plasticity = support_plasticity;
+  K.g2p2g = (int)consts12[11] & 1;      // fused-mode variant
+  K.clamp_F = ((int)consts12[11] >> 1) & 1;
   for (int i = 0; i < n; ++i) {
     if (dim == 2)
       mpm::particle_update<2>(K, dt, material[i], F + 4 * i, C + 4 * i, Jp[i], affine + 4 * i, mass[i]);

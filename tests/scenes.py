@@ -21,6 +21,7 @@ def build_pair(dim, scene, res=32, colliders=(), gravity=None, unbounded=False, 
     from taichi_elements_b200.engine.mpm_solver import MPMSolver
     o = OracleMPM((res, ) * dim, size=size, unbounded=unbounded, **kw)
     s = MPMSolver((res, ) * dim, size=size, unbounded=unbounded, **kw)
+    s.substep_batch = 1
     for kind, args in colliders:
         getattr(o, kind)(*args)
         getattr(s, kind)(*args)

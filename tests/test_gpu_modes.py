@@ -1,0 +1,109 @@
+"""The optional modes of the hot path: the fused g2p2g order and its semantic
+differences, adaptive dt, and the 2D shape seeders -- against the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from scenes import build_pair, mixed_scene, state_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('quant', [False, True])
+def test_g2p2g_matches_oracle(dim, quant):
+    import warnings
+    warnings.simplefilter('ignore')
+    cols = [('add_surface_collider', ((0.5, 0.22, 0.5)[:dim], (0.0, 1.0, 0.0)[:dim], 1, 0.3))]
+    o, s = build_pair(dim, mixed_scene(dim, seed=21), colliders=cols, use_g2p2g=True, quant=quant)
+    dt = o.default_dt
+    for it in range(4):                      # single substeps: every half is checked
+        o.substep(dt)
+        st = s._run_substeps(dt, 1)
+        assert st.substeps_done == 1
+        err = state_errors(s, o)
+        assert max(err[k] for k in ('x', 'v', 'F', 'Jp')) <= (1e-4 if it == 0 else 2e-3), (it, err)
+        assert abs(s.compute_max_velocity() - o.compute_max_velocity()) <= 1e-3 * max(1.0, o.compute_max_velocity())
+    # particles added between substeps skip the first gather (reference :396-399)
+    extra = (np.random.default_rng(3).random((200, dim)) * 0.1 + 0.45).astype(np.float32)
+    o.add_particles(extra, 1, velocity=[0.0, 2.0, 0.0][:dim])
+    s.add_particles(extra, 1, velocity=[0.0, 2.0, 0.0][:dim])
+    for _ in range(6):
+        o.substep(dt)
+    st = s._run_substeps(dt, 6)              # one batch
+    assert st.substeps_done == 6
+    err = state_errors(s, o)
+    assert max(err[k] for k in ('x', 'v', 'F', 'Jp')) <= 5e-3, err
+    # water keeps F = diag(J, 1, 1) and does not reset Jp in this mode (:440-444)
+    w = s.material.to_numpy() == 0
+    assert np.all(s.Jp.to_numpy()[w] == 1.0) and np.all(s.F.to_numpy()[w][:, 1, 1] == 1.0)
+
+
+def test_g2p2g_survives_capacity_growth():
+    """Growing the particle/block buffers between substeps re-creates the pending scatter half."""
+    from oracle.mpm_oracle import OracleMPM
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    rng = np.random.default_rng(7)
+    o, s = OracleMPM((64, ) * 3, use_g2p2g=True), MPMSolver((64, ) * 3, use_g2p2g=True)
+    a = (rng.random((9000, 3)) * 0.2 + 0.3).astype(np.float32)
+    b = (rng.random((30000, 3)) * 0.3 + 0.55).astype(np.float32)     # > initial 16384 rows: forces a re-bind
+    dt = o.default_dt
+    for m in (o, s):
+        m.add_particles(a, 1, velocity=[0.5, 0, 0])
+    for _ in range(3):
+        o.substep(dt)
+    s._run_substeps(dt, 3)
+    for m in (o, s):
+        m.add_particles(b, 0)
+    for _ in range(3):
+        o.substep(dt)
+    s._run_substeps(dt, 3)
+    err = state_errors(s, o)
+    assert max(err[k] for k in ('x', 'v', 'F')) <= 5e-3, err
+
+
+def test_adaptive_dt_follows_reference_loop():
+    from oracle.mpm_oracle import OracleMPM
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    scene = mixed_scene(3, seed=22)
+    o = OracleMPM((32, ) * 3)
+    s = MPMSolver((32, ) * 3, use_adaptive_dt=True, g2p2g_allowed_cfl=0.05)   # tight CFL so the limiter acts
+    for p, m, vel in scene:
+        o.add_particles(p, m, velocity=[5 * c for c in vel])
+        s.add_particles(p, m, velocity=[5 * c for c in vel])
+    dts = o.step_adaptive(4e-3, allowed_cfl=0.05)
+    s.step(4e-3)
+    assert s.total_substeps == len(dts) == o.total_substeps
+    assert min(dts) < dts[0]                                             # the limiter really shortened dt
+    assert abs(s.t - sum(dts)) < 1e-9 + 1e-5 * sum(dts)
+    err = state_errors(s, o)
+    assert max(err[k] for k in ('x', 'v')) <= 5e-3, err
+    assert abs(s.compute_max_grid_velocity() - o.compute_max_grid_velocity()) <= 1e-3 * o.compute_max_grid_velocity()
+
+
+def test_add_ngon_and_texture_2d():
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    s = MPMSolver((64, 64))
+    s.add_ngon(sides=6, center=[0.5, 0.5], radius=0.2, angle=0.3, material=s.material_elastic, velocity=[1, 0])
+    n = s.n_particles[None]
+    want = int(math.ceil(0.5 * (0.2 * 64)**2 * math.sin(2 * math.pi / 6) * 6 * 4))   # reference :903-906
+    assert n == want
+    x = s.particle_info()['position'] - 0.5
+    r, th = np.hypot(x[:, 0], x[:, 1]) / 0.2, np.arctan2(x[:, 1], x[:, 0])
+    central = 2 * math.pi / 6
+    inside = r < np.cos(central / 2) / np.cos(central / 2 - np.mod(th - 0.3, central)) + 1e-5
+    assert inside.all() and r.max() > 0.9
+    with pytest.raises(ValueError):
+        MPMSolver((32, 32, 32)).add_ngon(3, [0.5, 0.5, 0.5], 0.1, 0, 1)
+    tex = np.zeros((10, 8), np.float32)
+    tex[2:5, 3:7] = 1.0
+    s.add_texture_2d(0.1, 0.2, tex, s.material_water, 0x123456)
+    p = s.particle_info()
+    assert s.n_particles[None] == n + 12
+    got = p['position'][n:]
+    want_pts = np.array([[0.1 + i / 64, 0.2 + j / 64] for i in range(2, 5) for j in range(3, 7)], np.float32)
+    assert np.allclose(got, want_pts, atol=1e-6) and np.all(p['color'][n:] == 0x123456)
+    assert np.allclose(p['velocity'][n:], [1, 0])      # the last source velocity, as in the reference kernel
+    s.step(2e-3)
+    assert np.isfinite(s.particle_info()['position']).all()

@@ -42,9 +42,9 @@ def test_device_svd2_is_the_closed_form(host_math):
 
 
 @pytest.mark.parametrize('dim', [2, 3])
-@pytest.mark.parametrize('plastic', [True, False])
-def test_particle_update_matches_oracle(host_math, dim, plastic):
-    o = OracleMPM((32, ) * dim, support_plasticity=plastic)
+@pytest.mark.parametrize('plastic,fused', [(True, 0), (False, 0), (True, 1), (True, 3)])
+def test_particle_update_matches_oracle(host_math, dim, plastic, fused):
+    o = OracleMPM((32, ) * dim, support_plasticity=plastic, use_g2p2g=bool(fused), quant=bool(fused & 2))
     for p, m, vel in mixed_scene(dim, seed=5):
         o.add_particles(p, m, velocity=vel)
     rng = np.random.default_rng(6)
@@ -54,10 +54,10 @@ def test_particle_update_matches_oracle(host_math, dim, plastic):
     o.Jp = (o.Jp + 0.02 * rng.normal(size=n)).astype(np.float32)
     F, C, Jp, mat = o.F.copy(), o.C.copy(), o.Jp.copy(), o.material.copy()
     dt = o.default_dt
-    o.p2g(dt)
+    o.p2g(dt, g2p2g=bool(fused))
     consts = np.array([o.dx, o.inv_dx, o.p_vol, o.p_mass, o.mu_0, o.lambda_0, o.alpha,
                        (dim * o.lambda_0 + 2 * o.mu_0) / (2 * o.mu_0), o.water_density, o.inv_dx**2,
-                       4 * o.inv_dx, 0], np.float32)
+                       4 * o.inv_dx, fused], np.float32)
     aff, mass = np.empty_like(F), np.empty(n, np.float32)
     host_math.host_particle_update(dim, P(consts), int(plastic), ctypes.c_float(dt), n, P(mat), P(F), P(C), P(Jp),
                                    P(aff), P(mass))
