@@ -662,6 +662,37 @@ static int enqueue_scatter_half(mpm_ctx* ctx, float dt, int cur, int commit_prev
   return enqueue_grid_op<D>(ctx, dt, s);
 }
 
+// The workspace was re-bound while a scatter half was pending: redo it (same rows, same dt) so that
+// its block structure, grid and advanced F/Jp exist again; it is a pure function of the live set.
+// Expects a valid key layout.  Returns MPM_OK, MPM_E_BLOCK_CAPACITY, or MPM_E_INVALID (retry layout).
+static int rebuild_pending(mpm_ctx* ctx, cudaStream_t s) {
+  const bool d3 = ctx->dim == 3;
+  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
+  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n);
+  const int64_t n_keep = ctx->n;
+  ctx->n = ctx->pending_n;
+  int rc = d3 ? enqueue_scatter_half<3>(ctx, ctx->pending_dt, ctx->cur, 0, s)
+              : enqueue_scatter_half<2>(ctx, ctx->pending_dt, ctx->cur, 0, s);
+  ctx->n = n_keep;
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (ctx->h_status->err) {
+    ctx->bbox_valid = false;
+    ctx->layout_valid = false;
+    if (ctx->h_status->err & ERR_BLOCK_CAPACITY) {
+      ctx->last.need_blocks = ctx->h_status->need_blocks;
+      ctx->err = "active leaf blocks exceed the bound capacity (rebuilding the pending g2p2g half)";
+      return MPM_E_BLOCK_CAPACITY;
+    }
+    return MPM_E_INVALID;
+  }
+  ctx->pending_npb = ctx->h_status->npb;
+  ctx->pending_ngb = ctx->h_status->ngb;
+  ctx->pending_rebuild = false;
+  return MPM_OK;
+}
+
 static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
   const bool d3 = ctx->dim == 3;
   for (int attempt = 0; attempt < 4; ++attempt) {
@@ -671,27 +702,9 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     if (ctx->have_pending && ctx->pending_rebuild) {
-      // the workspace was re-bound: redo the pending scatter half (same rows, same dt) so that its
-      // block structure and grid exist again; it is a pure function of the live set
-      k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n);
-      const int64_t n_keep = ctx->n;
-      ctx->n = ctx->pending_n;
-      rc = d3 ? enqueue_scatter_half<3>(ctx, ctx->pending_dt, ctx->cur, 0, s) : enqueue_scatter_half<2>(ctx, ctx->pending_dt, ctx->cur, 0, s);
-      ctx->n = n_keep;
-      if (rc) return rc;
-      CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      if (ctx->h_status->err) {
-        ctx->bbox_valid = false; ctx->layout_valid = false;
-        if (ctx->h_status->err & ERR_BLOCK_CAPACITY) {
-          ctx->last.need_blocks = ctx->h_status->need_blocks;
-          ctx->err = "active leaf blocks exceed the bound capacity (rebuilding the pending g2p2g half)";
-          return MPM_E_BLOCK_CAPACITY;
-        }
-        continue;
-      }
-      ctx->pending_npb = ctx->h_status->npb; ctx->pending_ngb = ctx->h_status->ngb;
-      ctx->pending_rebuild = false;
+      rc = rebuild_pending(ctx, s);
+      if (rc == MPM_E_BLOCK_CAPACITY) return rc;
+      if (rc) continue;
       CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     }
     k_batch_begin_keep<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, ctx->pending_npb, ctx->pending_ngb);
@@ -1141,18 +1154,10 @@ extern "C" int mpm_set_profiling(mpm_ctx* ctx, int32_t enabled) {
 }
 
 // ------------------------------------------------------------------ read-back
+extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t begin, int64_t end,
+                               void* dst_dev, void* stream);
 extern "C" int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream) {
-  if (!ctx || field < 0 || field >= ctx->nf || begin < 0 || end < begin || end > ctx->n) return fail(ctx, MPM_E_INVALID, "mpm_gather: bad range/field");
-  if (end == begin) return MPM_OK;
-  if (!dst_dev) return MPM_E_INVALID;
-  CK(cudaSetDevice(ctx->P.device));
-  cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t* st = ctx->state[ctx->cur];
-  const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
-  k_gather_field<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(st + (size_t)field * ctx->cap, st + (size_t)idf * ctx->cap,
-                                                                  (int)ctx->n, begin, end, (uint32_t*)dst_dev);
-  CK(cudaGetLastError());
-  return MPM_OK;
+  return mpm_gather_rows(ctx, field, 1, begin, end, dst_dev, stream);
 }
 
 extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t begin, int64_t end,
@@ -1163,6 +1168,33 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
   if (!dst_dev) return MPM_E_INVALID;
   CK(cudaSetDevice(ctx->P.device));
   const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
+  if (ctx->K.g2p2g && ctx->have_pending) {
+    // F and Jp were already advanced by the pending scatter half (see k_gather_rows_pending)
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->pending_rebuild) {
+      int rc = upload_colliders(ctx, s);
+      for (int attempt = 0; !rc && attempt < 3; ++attempt) {
+        rc = refresh_bbox(ctx, s);
+        if (!rc) rc = update_layout(ctx);
+        if (rc) break;
+        rc = rebuild_pending(ctx, s);
+        if (rc != MPM_E_INVALID) break;
+        rc = MPM_OK;
+      }
+      if (rc) return rc;
+    }
+    const int f_lo = ctx->dim == 3 ? Fld<3>::F : Fld<2>::F, dd = ctx->dim * ctx->dim;
+    const int jp = ctx->dim == 3 ? Fld<3>::JP : Fld<2>::JP;
+    // F occupies [f_lo, f_lo + dd), C the next dd words, then Jp: two advanced ranges
+    const int lo = first_field >= jp ? jp : f_lo, hi = first_field >= jp ? jp + 1 : f_lo + dd;
+    if (first_field < jp && first_field + nwords > f_lo + dd && first_field + nwords > jp)
+      return fail(ctx, MPM_E_INVALID, "mpm_gather_rows: a range may not span F and Jp in g2p2g mode");
+    k_gather_rows_pending<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
+        ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->cap, first_field, nwords, idf, lo, hi,
+        ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+    CK(cudaGetLastError());
+    return MPM_OK;
+  }
   k_gather_rows<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
       ctx->state[ctx->cur], ctx->cap, first_field, nwords, idf, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
   CK(cudaGetLastError());

@@ -1009,6 +1009,26 @@ __global__ void k_gather_rows(const uint32_t* __restrict__ state, size_t cap, in
   }
 }
 
+// g2p2g with a pending scatter half: F and Jp of the binned particles have already been
+// advanced by that half and live in the other set at their sorted slots (row s <- perm[s]);
+// everything else, and particles added since, is read from the live set.
+__global__ void k_gather_rows_pending(const uint32_t* __restrict__ live, const uint32_t* __restrict__ other,
+                                      const uint32_t* __restrict__ perm, size_t cap, int first, int nwords, int idf,
+                                      int f_lo, int f_hi, int n_binned, int n, int64_t begin, int64_t end,
+                                      uint32_t* __restrict__ out) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    const bool binned = s < (uint32_t)n_binned;
+    const uint32_t p = binned ? perm[s] : s;
+    const int64_t id = live[(size_t)idf * cap + p];
+    if (id < begin || id >= end) continue;
+    for (int w = 0; w < nwords; ++w) {
+      const int f = first + w;
+      const bool adv = binned && f >= f_lo && f < f_hi;     // F words and Jp are contiguous
+      out[(size_t)(id - begin) * nwords + w] = adv ? other[(size_t)f * cap + s] : live[(size_t)f * cap + p];
+    }
+  }
+}
+
 template <int D>
 __global__ void k_debug_binning(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, int half,
                                 int* __restrict__ out) {
