@@ -170,6 +170,7 @@ def main():
     ap.add_argument('--workload', default='cube_drop_4m')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--g2p2g', action='store_true', help='time the use_g2p2g=True mode (N = 1)')
     ap.add_argument('--strong', action='store_true', help='N > 1: split the N=1 scene over the ranks (strong scaling)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -196,7 +197,7 @@ def main():
     def make_solver():
         with quiet:
             if world == 1:
-                s = MPMSolver(res=w['res'], size=1, unbounded=False, device=local)
+                s = MPMSolver(res=w['res'], size=1, unbounded=False, device=local, use_g2p2g=args.g2p2g)
             else:
                 from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
                 res = w['res'][0]
@@ -356,6 +357,7 @@ def main():
             'config': {'workload': f"configs[1] 3D cube drop, res 256^3 bounded, {n_total} particles "
                                    f"(ELASTIC cube over WATER cube, 8 per cell), g=(0,-20,0), dt=3e-3/39"
                                    if args.workload == 'cube_drop_4m' else args.workload,
+                       'mode': 'use_g2p2g=True (fused order, SURVEY 8(f)1)' if args.g2p2g else 'default (split p2g / g2p)',
                        'particles_per_gpu': n_local, 'l2': 'inputs (2 x 116 B x N particle state) exceed L2',
                        'active_blocks': int(st.n_grid_blocks), 'particle_blocks': int(st.n_particle_blocks)},
             'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches,
