@@ -104,6 +104,27 @@ def test_multi_substep_tracking(dim):
     assert np.isfinite(s.x.to_numpy()).all()
 
 
+@pytest.mark.parametrize('dim', [2, 3])
+def test_dense_blocks_take_the_multi_chunk_path(dim):
+    """Leaf blocks holding more particles than one shared-memory pass stages (640 in 3D, 1280 in
+    2D) are processed in several chunks; 40+ particles per cell also stresses the per-cell loops."""
+    n_per = 5000 if dim == 3 else 9000
+    o, s = build_pair(dim, mixed_scene(dim, n_per=n_per, seed=6, spread=0.12), res=16 if dim == 3 else 32)
+    dt = o.default_dt
+    o.substep(dt)
+    s._run_substeps(dt, 1)
+    _, cnt, _ = s.debug_blocks()
+    assert cnt.max() > (1400 if dim == 3 else 2700)          # several chunks in at least one block
+    assert _check_grid(s, o) <= TOL_ONE
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    for _ in range(5):
+        o.substep(dt)
+    s._run_substeps(dt, 5)
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_MANY, err
+
+
 def _run_variant(env_extra, tag):
     import os
     import subprocess
