@@ -54,6 +54,8 @@ struct mpm_ctx {
   bool have_pending = false, pending_rebuild = false, skip_gather = false;
   float pending_dt = 0.f;
   int pending_n = 0, pending_npb = 0, pending_ngb = 0;
+  bool keys_ready = false;     // the previous G2P of this batch already produced keys + flags
+  int fuse_keys = 1;
   bool in_batch = false;
   int batch_cur0 = 0, batch_enq = 0;
   const uint32_t* cur_keys = nullptr;
@@ -225,6 +227,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
     ctx->grid_p2g = ctx->sm_count * std::max(occ, 1);
 
   }
+  if (const char* v = getenv("MPM_FUSE_KEYS")) ctx->fuse_keys = atoi(v);
   if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
@@ -546,10 +549,16 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     int nlin = 1;
     for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
     const int ncell = ctx->max_blocks * G::CELLS + 1;
-    CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
     CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
-    k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
-                                                       nlin, commit_prev, st);
+    if (ctx->keys_ready) {
+      // keys and flags were written by the previous substep's G2P (mpm_kernels.cuh, next_keys)
+      k_substep_begin<<<1, 1, 0, s>>>(st);
+    } else {
+      CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+      k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
+                                                         nlin, commit_prev, st);
+    }
+    ctx->keys_ready = false;
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
     k_bin_rank<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
@@ -618,13 +627,21 @@ static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s) {
 }
 
 template <int D>
-static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev) {
+static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cudaEvent_t* ev, bool fuse_next = false) {
   const bool prof = ev != nullptr;
   Status* st = ctx->d_status;
   SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
   int rc = enqueue_grid_op<D>(ctx, dt, s);
   if (rc) return rc;
   if (prof) cudaEventRecord(ev[3], s);
+  if (fuse_next) {
+    // another substep of this batch follows with the same key layout: let G2P emit its keys/flags
+    int nlin = 1;
+    for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+    CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+    a.next_keys = ctx->keys_a; a.next_flags = ctx->flags; a.next_nlin = nlin;
+    ctx->keys_ready = true;
+  }
   launch_g2p<D>(ctx, a, s);
   if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, st); ctx->launches += 1; }
   if (prof) cudaEventRecord(ev[4], s);
@@ -754,10 +771,12 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
 }
 
 template <int D>
-static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
+static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev,
+                           bool more_follow = false) {
   int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, ev);
   if (rc) return rc;
-  return enqueue_grid_g2p<D>(ctx, dt, cur, s, ev);
+  const bool fuse = more_follow && ctx->fuse_keys && ctx->dense && !ctx->slab.enabled && !ctx->K.g2p2g;
+  return enqueue_grid_g2p<D>(ctx, dt, cur, s, ev, fuse);
 }
 
 extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, void* stream) {
@@ -783,6 +802,7 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
     const int cur0 = ctx->cur;
+    ctx->keys_ready = false;
     const bool prof = ctx->profiling && count <= 4096;
     if (prof)
       while ((int)ctx->ev.size() < 5 * count) {
@@ -793,8 +813,8 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     const int enq = count;
     for (int i = 0; i < count; ++i) {
       cudaEvent_t* ev = prof ? ctx->ev.data() + 5 * i : nullptr;
-      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev)
-                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev);
+      rc = ctx->dim == 3 ? enqueue_substep<3>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev, i + 1 < count)
+                         : enqueue_substep<2>(ctx, (float)dt, cur0 ^ (i & 1), i > 0, s, ev, i + 1 < count);
       if (rc) return rc;
     }
     k_end<<<1, 1, 0, s>>>(ctx->d_status);   // commit of the last substep

@@ -61,6 +61,7 @@ struct Status {
   int halo_cnt[2];  // packed boundary-column grid blocks (-x / +x side)
   unsigned maxgv_bits;  // max |grid v|_inf after the grid op (compute_max_grid_velocity)
   int half;         // g2p2g: gather halves completed in this batch
+  int next_err;     // error bits raised for the NEXT substep by G2P's fused key pass
 };
 
 // Slab decomposition along x (multi-GPU): this rank owns leaf-block columns

@@ -36,6 +36,11 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
                : "memory");
 }
 
+template <int D> __device__ __forceinline__ int oct_delta_l(const KeyLayout& L, int o) {
+  if constexpr (D == 3) return ((o & 1) ? L.eb[1] * L.eb[2] : 0) + ((o & 2) ? L.eb[2] : 0) + ((o & 4) ? 1 : 0);
+  else return ((o & 1) ? L.eb[1] : 0) + ((o & 2) ? 1 : 0);
+}
+
 // linear block key (relative to the layout box) <-> relative block coords
 template <int D> __device__ __forceinline__ void key_to_rel(const KeyLayout& L, uint32_t lin, int* rel) {
 #pragma unroll
@@ -60,6 +65,16 @@ __global__ void k_reset(Status* st) {
   for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
 }
 __global__ void k_batch_begin(Status* st, int n) { st->n_cur = n; st->n_live = n; }
+// first kernel of a substep whose keys came from the previous G2P: commit that substep, then
+// let the errors its key pass raised take effect
+__global__ void k_substep_begin(Status* st) {
+  if (!st->err) {
+    st->done += 1;
+    if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
+  }
+  st->err |= st->next_err;
+  st->next_err = 0;
+}
 __global__ void k_end(Status* st) {
   if (!st->err) {
     st->done += 1;
@@ -276,6 +291,9 @@ template <int D> struct SubstepArgs {
   KeyLayout L;
   Consts K;
   float dt;
+  uint32_t* next_keys;  // non-null: G2P also emits the next substep's sort keys and block flags
+  int* next_flags;      //   (same key layout, see mpm_bin.cuh); saves the k_bin_keys pass
+  int next_nlin;
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
   CommBufs cb;    // multi-GPU: migration / halo send buffers
@@ -676,6 +694,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, nv[d]));   // :724
       }
+      uint32_t nlin_key = 0, ncell = 0, nsp = 0;
+      bool nbad = false;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         stf(a.dst, cap, FL::X + d, s, x[d]);
@@ -683,6 +703,33 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         vmax = fmaxf(vmax, fabsf(nv[d]));
         int nb = base_index(x[d], a.K.inv_dx);
         lo[d] = min(lo[d], nb); hi[d] = max(hi[d], nb);
+        // next substep's bin of this particle (same arithmetic as k_bin_keys)
+        const int g = nb + a.L.half;
+        int rel = (g >> G::LOG_LEAF) - a.L.ob[d];
+        if (rel < 0 || rel > a.L.eb[d] - 2) { nbad = true; rel = min(max(rel, 0), a.L.eb[d] - 2); }
+        nlin_key = nlin_key * (uint32_t)a.L.eb[d] + (uint32_t)rel;
+        const uint32_t lc = (uint32_t)(g & (G::LEAF - 1));
+        ncell = (ncell << G::LOG_LEAF) | lc;
+        nsp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
+      }
+      if (a.next_keys) {
+        a.next_keys[s] = (nlin_key << G::CB) | ncell;
+        if (nbad) {
+          atomicOr(&a.st->next_err, ERR_BBOX);
+        } else {
+          uint32_t om = 0;
+#pragma unroll
+          for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
+            if ((o & ~nsp) == 0) om |= 1u << o;
+          if (a.next_flags[nlin_key] == 0) a.next_flags[nlin_key] = 1;
+          int* gf = a.next_flags + a.next_nlin;
+#pragma unroll
+          for (int o = 0; o < G::NO; ++o)
+            if ((om >> o) & 1u) {
+              const int tt = (int)nlin_key + oct_delta_l<D>(a.L, o);
+              if (gf[tt] == 0) gf[tt] = 1;
+            }
+        }
       }
 #pragma unroll
       for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::C + i, s, nC[i]);
