@@ -508,9 +508,14 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
     for (int d = 0; d < D; ++d) gvmax = fmaxf(gvmax, fabsf(v[d]));
   }
   // compute_max_grid_velocity (engine/mpm_solver.py:737-746), folded into the pass
+  __shared__ unsigned s_gv;
+  if (threadIdx.x == 0) s_gv = 0u;
+  __syncthreads();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) gvmax = fmaxf(gvmax, __shfl_xor_sync(0xffffffffu, gvmax, o));
-  if ((threadIdx.x & 31) == 0 && gvmax > 0.0f) atomicMax(&st->maxgv_bits, __float_as_uint(gvmax));
+  if ((threadIdx.x & 31) == 0 && gvmax > 0.0f) atomicMax(&s_gv, __float_as_uint(gvmax));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_gv) atomicMax(&st->maxgv_bits, s_gv);
 }
 
 // ------------------------------------------------------------------ G2P
@@ -721,14 +726,20 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
           for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
             if ((o & ~nsp) == 0) om |= 1u << o;
-          if (a.next_flags[nlin_key] == 0) a.next_flags[nlin_key] = 1;
-          int* gf = a.next_flags + a.next_nlin;
+          // neighbouring lanes mostly hit the same leaf block: one lane per distinct block of the
+          // (currently converged) warp marks the union of its group's octants
+          const unsigned grp = __match_any_sync(__activemask(), nlin_key);
+          om = __reduce_or_sync(grp, om);
+          if ((int)(tid & 31) == __ffs(grp) - 1) {
+            if (a.next_flags[nlin_key] == 0) a.next_flags[nlin_key] = 1;
+            int* gf = a.next_flags + a.next_nlin;
 #pragma unroll
-          for (int o = 0; o < G::NO; ++o)
-            if ((om >> o) & 1u) {
-              const int tt = (int)nlin_key + oct_delta_l<D>(a.L, o);
-              if (gf[tt] == 0) gf[tt] = 1;
-            }
+            for (int o = 0; o < G::NO; ++o)
+              if ((om >> o) & 1u) {
+                const int tt = (int)nlin_key + oct_delta_l<D>(a.L, o);
+                if (gf[tt] == 0) gf[tt] = 1;
+              }
+          }
         }
       }
 #pragma unroll
