@@ -731,14 +731,13 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
           const unsigned grp = __match_any_sync(__activemask(), nlin_key);
           om = __reduce_or_sync(grp, om);
           if ((int)(tid & 31) == __ffs(grp) - 1) {
-            if (a.next_flags[nlin_key] == 0) a.next_flags[nlin_key] = 1;
+            // plain stores, no read-check: a load here would put an L2 round trip on the loop's
+            // critical path at this kernel's occupancy
+            a.next_flags[nlin_key] = 1;
             int* gf = a.next_flags + a.next_nlin;
 #pragma unroll
             for (int o = 0; o < G::NO; ++o)
-              if ((om >> o) & 1u) {
-                const int tt = (int)nlin_key + oct_delta_l<D>(a.L, o);
-                if (gf[tt] == 0) gf[tt] = 1;
-              }
+              if ((om >> o) & 1u) gf[(int)nlin_key + oct_delta_l<D>(a.L, o)] = 1;
           }
         }
       }
