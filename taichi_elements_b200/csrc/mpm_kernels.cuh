@@ -538,17 +538,22 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
   for (int d = 0; d < D; ++d) { lo[d] = INT_MAX; hi[d] = INT_MIN; }
   __shared__ int s_next;
-  if (tid == 0) s_b = atomicAdd(&a.st->work_g2p, 1);
+  // fused key pass: which spill patterns (bit = 1 << nsp) the particles that STAY in this CTA's
+  // current block show; expanded to block flags once per block instead of once per particle
+  __shared__ unsigned s_seen;
+  if (tid == 0) { s_b = atomicAdd(&a.st->work_g2p, 1); s_seen = 0u; }
   __syncthreads();
   int b = s_b;
   while (b < npb) {
     if (tid == 0) s_next = atomicAdd(&a.st->work_g2p, 1);   // one block ahead, for the prefetch below
     const int start = a.pb_start[b], end = a.pb_start[b + 1];
     if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
+    const uint32_t cur_lin = a.pb_key[b];
+    unsigned seen = 0u;
     int org[D];
     {
       int rel[D];
-      key_to_rel<D>(a.L, a.pb_key[b], rel);
+      key_to_rel<D>(a.L, cur_lin, rel);
 #pragma unroll
       for (int d = 0; d < D; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
     }
@@ -721,24 +726,16 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         a.next_keys[s] = (nlin_key << G::CB) | ncell;
         if (nbad) {
           atomicOr(&a.st->next_err, ERR_BBOX);
+        } else if (nlin_key == cur_lin) {
+          seen |= 1u << nsp;         // the common case: flags are written once per block, below
         } else {
-          uint32_t om = 0;
+          // the particle changed leaf block (rare under the CFL bound): mark directly.  Plain
+          // stores, no read-check: a load would put an L2 round trip on the loop's critical path
+          a.next_flags[nlin_key] = 1;
+          int* gf = a.next_flags + a.next_nlin;
 #pragma unroll
           for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
-            if ((o & ~nsp) == 0) om |= 1u << o;
-          // neighbouring lanes mostly hit the same leaf block: one lane per distinct block of the
-          // (currently converged) warp marks the union of its group's octants
-          const unsigned grp = __match_any_sync(__activemask(), nlin_key);
-          om = __reduce_or_sync(grp, om);
-          if ((int)(tid & 31) == __ffs(grp) - 1) {
-            // plain stores, no read-check: a load here would put an L2 round trip on the loop's
-            // critical path at this kernel's occupancy
-            a.next_flags[nlin_key] = 1;
-            int* gf = a.next_flags + a.next_nlin;
-#pragma unroll
-            for (int o = 0; o < G::NO; ++o)
-              if ((om >> o) & 1u) gf[(int)nlin_key + oct_delta_l<D>(a.L, o)] = 1;
-          }
+            if ((o & ~nsp) == 0) gf[(int)nlin_key + oct_delta_l<D>(a.L, (int)o)] = 1;
         }
       }
 #pragma unroll
@@ -776,8 +773,23 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       stu(a.dst, cap, FL::ID, s, pid);
       stu(a.dst, cap, FL::EMIT, s, emit);
     }
+    if (a.next_keys) {
+      seen = __reduce_or_sync(0xffffffffu, seen);
+      if ((tid & 31) == 0 && seen) atomicOr(&s_seen, seen);
+    }
     b = s_next;
     __syncthreads();
+    if (a.next_keys && tid < G::NO) {
+      // octant o of the stencil union is touched iff some staying particle spills along every axis of o
+      const unsigned sn = s_seen;
+      unsigned sup = 0u;
+#pragma unroll
+      for (unsigned q = 0; q < (unsigned)G::NO; ++q)
+        if (((unsigned)tid & ~q) == 0u) sup |= 1u << q;
+      if (sn & sup) a.next_flags[a.next_nlin + (int)cur_lin + oct_delta_l<D>(a.L, tid)] = 1;
+      __syncwarp((1u << G::NO) - 1u);
+      if (tid == 0 && sn) { a.next_flags[cur_lin] = 1; s_seen = 0u; }   // next atomicOr is two barriers away
+    }
   }
   // CTA-wide reductions, once per CTA lifetime
 #pragma unroll
