@@ -15,6 +15,7 @@
 #include "mpm_bin.cuh"
 #include "mpm_comm.cuh"
 #include "mpm_p2g.cuh"
+#include "mpm_p2g3.cuh"
 
 using namespace mpm;
 
@@ -83,6 +84,7 @@ struct mpm_ctx {
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
   int g2p_cfg = 2;
   int p2g_cfg = 0;
+  int p2g_ver = 3;              // 3: mpm_p2g3.cuh (3D, dense binning); 2: mpm_p2g.cuh
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;
   int done_last = 0;
@@ -230,6 +232,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_FUSE_KEYS")) ctx->fuse_keys = atoi(v);
   if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
+  if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
@@ -480,9 +483,32 @@ static void launch_p2g_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s
   }
   k_p2g_cell<D, CH, MB><<<grid, P2GCfg<D>::THREADS, smem, s>>>(a);
 }
+// third revision (mpm_p2g3.cuh): 3D, needs the counting sort's per-cell bucket starts
+template <int CH, int MB>
+static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t s) {
+  static int grid = 0;
+  constexpr size_t smem = p2g3_smem_bytes<CH>();
+  if (!grid) {
+    int occ = 1;
+    cudaFuncSetAttribute(k_p2g3<CH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g3<CH, MB>, P2G3::T, smem);
+    grid = ctx->sm_count * std::max(occ, 1);
+  }
+  k_p2g3<CH, MB><<<grid, P2G3::T, smem, s>>>(a);
+}
 template <int D>
 static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   if constexpr (D == 3) {
+    if (ctx->p2g_ver == 3 && a.cellstart) {
+      switch (ctx->p2g_cfg) {
+        case 1: launch_p2g3_cfg<512, 5>(ctx, a, s); break;
+        case 2: launch_p2g3_cfg<640, 3>(ctx, a, s); break;
+        case 3: launch_p2g3_cfg<384, 6>(ctx, a, s); break;
+        case 4: launch_p2g3_cfg<768, 3>(ctx, a, s); break;
+        default: launch_p2g3_cfg<640, 4>(ctx, a, s); break;
+      }
+      return;
+    }
     switch (ctx->p2g_cfg) {
       case 1: launch_p2g_cfg<3, 512, 5>(ctx, a, s); break;
       case 2: launch_p2g_cfg<3, 576, 4>(ctx, a, s); break;

@@ -1,0 +1,274 @@
+// P2G, cell-owner formulation, third revision (3D, sm_100a).
+//
+// Same algorithm as mpm_p2g.cuh (engine/mpm_solver.py:487-584: one thread per
+// particle for the constitutive update, one thread per (cell, x-slice) for the
+// scatter, accumulated in registers), re-organised around what ncu showed on the
+// second revision: 14 CTA barriers per block (3.4 of ~6 resident warps per
+// scheduler parked at a barrier), a 64-step rank loop on two warps, and an
+// FFMA-per-scalar inner loop.
+//   * payload is AoS, five float4 per particle (m*v|m, three columns of dx*A
+//     with a zero fourth lane, fx): 5 LDS.128 instead of 16 LDS.32, and the
+//     scatter arithmetic runs on packed pairs (fma.rn.f32x2 -> FFMA2), the
+//     mass riding in the fourth lane
+//   * the accumulators of a thread are flushed ONCE per block into nine private
+//     4x4x6 copies (one per (x, y) stencil offset) that alias the dead payload:
+//     three conflict-free rounds over the z offset, no tile to clear; a node then
+//     sums the <= 9 copies that touch it and issues one REDG.E.ADD.F32x4
+//   * the next block's cell ranges and the descending-count cell order (counting
+//     sort on a 32-bin shared histogram) are prepared by the first warp that runs
+//     out of scatter work, off the critical path (double-buffered)
+// Barriers per block: 6, of which only two can see unbalanced arrivals.
+#pragma once
+#include "mpm_kernels.cuh"
+
+namespace mpm {
+
+struct P2G3 {
+  static constexpr int T = 192, SL = 3, NPT = 9, PS = 5;   // threads, x-slices, nodes per thread, float4 per particle
+  static constexpr int CP = 16 * 6;                        // one flush copy: [cx][cy][z] float4
+  static constexpr int COPIES = 9 * CP;                    // float4
+};
+
+template <int CHUNK> constexpr size_t p2g3_smem_bytes() {
+  static_assert(CHUNK * P2G3::PS >= P2G3::COPIES, "flush copies alias the payload");
+  return (size_t)CHUNK * P2G3::PS * sizeof(float4);
+}
+
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+
+// One warp: cell ranges of block nb (relative to its first particle) and the cells in
+// descending particle-count order (a warp's trip count in the scatter loop is the largest
+// count among its lanes): counting sort over min(count, 31), order inside a bin arbitrary.
+__device__ __forceinline__ void p2g3_prepare(const SubstepArgs<3>& a, int nb, int npb, int lane, int* cs, int* order,
+                                             int* hist) {
+  if (nb >= npb) return;
+  const int ns = a.pb_start[nb];
+  for (int c = lane; c <= 64; c += 32) cs[c] = a.cellstart[(size_t)nb * 64 + c] - ns;
+  hist[lane] = 0;
+  __syncwarp();
+  const int m0 = min(cs[lane + 1] - cs[lane], 31), m1 = min(cs[lane + 33] - cs[lane + 32], 31);
+  const int r0 = atomicAdd(&hist[m0], 1), r1 = atomicAdd(&hist[m1], 1);
+  __syncwarp();
+  const int h = hist[lane];
+  int incl = h;                                   // cells whose bin is >= lane
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  __syncwarp();
+  hist[lane] = incl - h;                          // cells in a higher bin come first
+  __syncwarp();
+  order[hist[m0] + r0] = lane;
+  order[hist[m1] + r1] = lane + 32;
+}
+
+template <int CHUNK, int MINB>
+__global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
+  constexpr int D = 3;
+  using G = Geo<3>;
+  using FL = Fld<3>;
+  constexpr int T = P2G3::T, CH = CHUNK, PS = P2G3::PS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* pay = reinterpret_cast<float4*>(smem_raw);      // [CH][PS]; the flush copies [27][64] alias it
+  __shared__ int s_cs[2][G::CELLS + 1];
+  __shared__ int s_order[2][G::CELLS];
+  __shared__ int s_nbr[G::NO];
+  __shared__ int s_b, s_next, s_ticket;
+  __shared__ int s_hist[32];
+  if (a.st->err) return;
+  const int npb = a.st->npb;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t cap = a.cap;
+  const int sl = tid % P2G3::SL;
+  const float slf = (float)sl;
+  // quadratic B-spline weight of this thread's x-slice as a polynomial in fx (:505)
+  const float k2 = sl == 1 ? -1.0f : 0.5f, k1 = sl == 0 ? -1.5f : (sl == 1 ? 2.0f : -0.5f),
+              k0 = sl == 0 ? 1.125f : (sl == 1 ? -0.25f : 0.125f);
+
+  if (tid == 0) { s_b = atomicAdd(&a.st->work_p2g, 1); s_ticket = 0; }
+  __syncthreads();
+  int b = s_b;
+  if (tid < 32) p2g3_prepare(a, b, npb, lane, s_cs[0], s_order[0], s_hist);
+  int u = 0;
+  __syncthreads();
+  while (b < npb) {
+    if (tid == 0) s_next = atomicAdd(&a.st->work_p2g, 1);   // claimed one block ahead
+    const int start = a.pb_start[b], end = a.pb_start[b + 1];
+    const int cnt = end - start;
+    if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
+    const int* cs = s_cs[u];
+    const int cell = s_order[u][tid / P2G3::SL];
+    const int c_lo = cs[cell], c_hi = cs[cell + 1];
+
+    // a block with more than CH particles (rare) takes several passes, each complete down to
+    // the global reductions, so the accumulators never live across a constitutive update
+    for (int c0 = 0; c0 < cnt; c0 += CH) {
+      const int cn = min(CH, cnt - c0);
+      const bool last = c0 + CH >= cnt;
+      // ---- phase 1: constitutive update (engine/mpm_solver.py:506-574), payload to shared memory
+      constexpr int NIT = (CH + T - 1) / T;
+      uint32_t pq[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
+#pragma unroll 1
+      for (int q = tid; q < cn; q += T) {
+        const int s = start + c0 + q;
+        const uint32_t p = pq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
+        float x[D], v[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          x[d] = ldf(a.src, cap, FL::X + d, p);
+          v[d] = ldf(a.src, cap, FL::V + d, p);
+        }
+        float F[D * D], C[D * D], aff[D * D], mass;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) {
+          F[i] = ldf(a.src, cap, FL::F + i, p);
+          C[i] = ldf(a.src, cap, FL::C + i, p);
+        }
+        float Jp = ldf(a.src, cap, FL::JP, p);
+        const int mat = (int)ldu(a.src, cap, FL::MAT, p);
+        particle_update<D>(a.K, a.dt, mat, F, C, Jp, aff, mass);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, F[i]);
+        stf(a.dst, cap, FL::JP, s, Jp);
+        float fx[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
+        const float dx = a.K.dx;                                       // dpos = (o - fx) * dx
+        float4* pp = pay + q * PS;
+        pp[0] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+        pp[1] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, 0.0f);
+        pp[2] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, 0.0f);
+        pp[3] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, 0.0f);
+        pp[4] = make_float4(fx[0], fx[1], fx[2], 0.0f);
+      }
+      __syncthreads();                                                  // payload ready
+      // next block's particle rows towards L2 while this one computes (storage order is last
+      // substep's sorted order, so rows [start, end) are almost where `perm` will point)
+      if (c0 == 0) {
+        const int nb = s_next;
+        if (nb < npb) {
+          const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
+          const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
+          for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
+            const int f = i / lines, l = i % lines;
+            const uint32_t* ptr = (f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + l * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      }
+      // ---- phase 2: (cell, slice) register accumulation (:577-584), packed pairs
+      float2 acc01[P2G3::NPT], acc23[P2G3::NPT];
+#pragma unroll
+      for (int r = 0; r < P2G3::NPT; ++r) { acc01[r] = make_float2(0.f, 0.f); acc23[r] = make_float2(0.f, 0.f); }
+      {
+        const int lo = max(c_lo, c0) - c0, hi = min(c_hi, c0 + cn) - c0;
+        for (int q = lo; q < hi; ++q) {
+          const float4* pp = pay + q * PS;
+          const float4 M = pp[0], Ax = pp[1], Ay = pp[2], Az = pp[3], fxv = pp[4];
+          const float wi = fmaf(fmaf(k2, fxv.x, k1), fxv.x, k0);
+          const float2 d0 = f2(slf - fxv.x);
+          const float2 a01 = __ffma2_rn(make_float2(Ax.x, Ax.y), d0, make_float2(M.x, M.y));
+          const float2 a23 = __ffma2_rn(make_float2(Ax.z, Ax.w), d0, make_float2(M.z, M.w));
+          float wy[3], wz[3];
+          wy[0] = 0.5f * (1.5f - fxv.y) * (1.5f - fxv.y);
+          wy[1] = 0.75f - (fxv.y - 1.0f) * (fxv.y - 1.0f);
+          wy[2] = 0.5f * (fxv.y - 0.5f) * (fxv.y - 0.5f);
+          wz[0] = 0.5f * (1.5f - fxv.z) * (1.5f - fxv.z);
+          wz[1] = 0.75f - (fxv.z - 1.0f) * (fxv.z - 1.0f);
+          wz[2] = 0.5f * (fxv.z - 0.5f) * (fxv.z - 0.5f);
+          float2 d2[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) d2[k] = f2((float)k - fxv.z);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float2 d1 = f2((float)j - fxv.y);
+            const float wij = wi * wy[j];
+            const float2 b01 = __ffma2_rn(make_float2(Ay.x, Ay.y), d1, a01);
+            const float2 b23 = __ffma2_rn(make_float2(Ay.z, Ay.w), d1, a23);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float2 wt = f2(wij * wz[k]);
+              const float2 t01 = __ffma2_rn(make_float2(Az.x, Az.y), d2[k], b01);
+              const float2 t23 = __ffma2_rn(make_float2(Az.z, Az.w), d2[k], b23);   // .y = mass
+              acc01[j * 3 + k] = __ffma2_rn(wt, t01, acc01[j * 3 + k]);
+              acc23[j * 3 + k] = __ffma2_rn(wt, t23, acc23[j * 3 + k]);
+            }
+          }
+        }
+      }
+      // the first warp out of scatter work prepares the next block
+      if (last) {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(&s_ticket, 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk == 0) p2g3_prepare(a, s_next, npb, lane, s_cs[u ^ 1], s_order[u ^ 1], s_hist);
+      }
+      __syncthreads();                                                  // payload dead
+      // ---- phase 3: accumulators -> the nine (x-slice, y-offset) copies, z offset by rounds.
+      // For a fixed z offset k the map cell -> (cx, cy, cz + k) is injective, so a round is a
+      // plain store (first touch) or a private read-add-write.
+      {
+        const int cx = cell >> 4, cy = (cell >> 2) & 3, cz = cell & 3;
+        float4* my = pay + ((sl * 3) * 16 + cx * 4 + cy) * 6 + cz;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                                   // z = cz (k = 0); z = 4, 5 (k = 2)
+          my[j * P2G3::CP] = make_float4(acc01[j * 3].x, acc01[j * 3].y, acc23[j * 3].x, acc23[j * 3].y);
+          if (cz >= 2)
+            my[j * P2G3::CP + 2] = make_float4(acc01[j * 3 + 2].x, acc01[j * 3 + 2].y, acc23[j * 3 + 2].x,
+                                               acc23[j * 3 + 2].y);
+        }
+        if (tid == 0) s_ticket = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                                   // z = cz + 1
+          float4 t = my[j * P2G3::CP + 1];
+          t.x += acc01[j * 3 + 1].x; t.y += acc01[j * 3 + 1].y; t.z += acc23[j * 3 + 1].x; t.w += acc23[j * 3 + 1].y;
+          my[j * P2G3::CP + 1] = t;
+        }
+        __syncthreads();
+        if (cz < 2) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {                                 // z = cz + 2 in {2, 3}
+            float4 t = my[j * P2G3::CP + 2];
+            t.x += acc01[j * 3 + 2].x; t.y += acc01[j * 3 + 2].y; t.z += acc23[j * 3 + 2].x; t.w += acc23[j * 3 + 2].y;
+            my[j * P2G3::CP + 2] = t;
+          }
+        }
+      }
+      __syncthreads();                                                  // copies ready
+      // ---- phase 4: node = sum of the copies (i, j) with 0 <= nx - i, ny - j < 4 -> global grid
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int n = tid + pass * T;
+        if (n < G::TN) {
+          const int nz = n % 6, ny = (n / 6) % 6, nx = n / 36;
+          const float4* row = pay + (nx * 4 + ny) * 6 + nz;
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if ((unsigned)(nx - i) < 4u && (unsigned)(ny - j) < 4u) {
+                const float4 o = row[(i * 3 + j) * P2G3::CP - i * 24 - j * 6];
+                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+              }
+          if (val.w != 0.0f) {
+            int oct, cellg;
+            tile_node<D>(n, oct, cellg);
+            const int slot = s_nbr[oct];
+            if (slot >= 0) red_add_v4(a.grid + (size_t)slot * G::CELLS + cellg, val);
+          }
+        }
+      }
+      if (last) { b = s_next; u ^= 1; }
+      __syncthreads();                                                  // copies dead, s_next consumed
+    }
+  }
+}
+
+}  // namespace mpm

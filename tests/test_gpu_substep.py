@@ -145,10 +145,12 @@ def _run_variant(env_extra, tag):
 
 
 def test_kernel_variants_agree():
-    """Default build (counting-sort binning, cell-owner P2G) against the radix-sort
-    fallback and the first shared-atomic P2G: same block structure, same physics."""
+    """Default build (counting-sort binning, cell-owner P2G rev. 3) against the radix-sort
+    fallback, the second-revision cell-owner P2G and the first shared-atomic P2G: same
+    block structure, same physics."""
     base = _run_variant({}, 'default')
-    for tag, env in (('radix', {'MPM_SORT': 'radix'}), ('atomic', {'MPM_P2G': 'atomic'})):
+    for tag, env in (('radix', {'MPM_SORT': 'radix'}), ('p2g2', {'MPM_P2G_VER': '2'}),
+                     ('atomic', {'MPM_P2G': 'atomic'})):
         alt = _run_variant(env, tag)
         assert np.array_equal(base['pb'], alt['pb']) and np.array_equal(base['gb'], alt['gb'])
         assert np.array_equal(base['cnt'], alt['cnt'])
