@@ -84,6 +84,7 @@ struct mpm_ctx {
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
   int g2p_cfg = 2;
   int p2g_cfg = 0;
+  int pf_mode = 2;              // next-block L2 prefetch: cp.async.bulk.prefetch ranges (MPM_PREFETCH)
   int p2g_ver = 3;              // 3: mpm_p2g3.cuh (3D, dense binning); 2: mpm_p2g.cuh
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
   int launches = 0;
@@ -233,6 +234,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
+  if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
@@ -554,6 +556,7 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
   a.slab = ctx->slab; a.cb = ctx->comm;
   a.n_rows = (int)ctx->n;
+  a.pf_mode = ctx->pf_mode;
   return a;
 }
 

@@ -36,6 +36,15 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
                : "memory");
 }
 
+// L2 prefetch of [p, p + bytes): one cp.async.bulk.prefetch (sm_90+) per range
+__device__ __forceinline__ void prefetch_l2_range(const void* p, uint32_t bytes) {
+  const unsigned long long a = (unsigned long long)__cvta_generic_to_global(p);
+  const unsigned long long a0 = a & ~15ull;
+  const uint32_t sz = (bytes + (uint32_t)(a - a0) + 15u) & ~15u;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int D> __device__ __forceinline__ int oct_delta_l(const KeyLayout& L, int o) {
   if constexpr (D == 3) return ((o & 1) ? L.eb[1] * L.eb[2] : 0) + ((o & 2) ? L.eb[2] : 0) + ((o & 4) ? 1 : 0);
   else return ((o & 1) ? L.eb[1] : 0) + ((o & 2) ? 1 : 0);
@@ -294,6 +303,7 @@ template <int D> struct SubstepArgs {
   uint32_t* next_keys;  // non-null: G2P also emits the next substep's sort keys and block flags
   int* next_flags;      //   (same key layout, see mpm_bin.cuh); saves the k_bin_keys pass
   int next_nlin;
+  int pf_mode;    // next-block L2 prefetch: 0 off, 1 one prefetch per 128 B, 2 bulk range prefetch, 3 one per 32 B
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
   CommBufs cb;    // multi-GPU: migration / halo send buffers
@@ -583,19 +593,31 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     __syncthreads();
     {   // next block's particle rows and grid tiles towards L2 while this one computes
       const int nb = s_next;
-      if (nb < npb) {
+      if (nb < npb && a.pf_mode) {
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
-        const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
-        for (int i = tid; i < 8 * lines; i += G2P_THREADS) {
-          const int k = i / lines, l = i % lines;
-          const int f = k < D ? FL::X + k : (k == 3 ? FL::MAT : (k == 4 ? FL::COLOR : (k == 5 ? FL::ID : FL::EMIT)));
-          if (k == 7 || (D == 2 && k == 2)) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.perm + ns + l * 32)); continue; }
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.src + (size_t)f * cap + ns + l * 32));
-        }
-        for (int i = tid; i < G::NO * (G::CELLS * 16 / 128); i += G2P_THREADS) {
-          const int o = i / (G::CELLS * 16 / 128), l = i % (G::CELLS * 16 / 128);
-          const int slot = a.pb_nbr[nb * G::NO + o];
-          if (slot >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.grid + (size_t)slot * G::CELLS + l * 8));
+        if (a.pf_mode == 2) {
+          if (tid < 8 && !(D == 2 && tid == 2)) {
+            const int f = tid < D ? FL::X + tid : (tid == 3 ? FL::MAT : (tid == 4 ? FL::COLOR : (tid == 5 ? FL::ID : FL::EMIT)));
+            prefetch_l2_range((tid == 7 ? a.perm : a.src + (size_t)f * cap) + ns, (uint32_t)(ne - ns) * 4u);
+          } else if (tid >= 32 && tid < 32 + G::NO) {
+            const int slot = a.pb_nbr[nb * G::NO + tid - 32];
+            if (slot >= 0) prefetch_l2_range(a.grid + (size_t)slot * G::CELLS, G::CELLS * 16);
+          }
+        } else {
+          const int sh = a.pf_mode == 3 ? 3 : 5;           // words per prefetch: 8 (32 B) or 32 (128 B)
+          const int lines = (((ne - ns) + (1 << sh) - 1) >> sh) + 1;
+          for (int i = tid; i < 8 * lines; i += G2P_THREADS) {
+            const int k = i / lines, l = i % lines;
+            const int f = k < D ? FL::X + k : (k == 3 ? FL::MAT : (k == 4 ? FL::COLOR : (k == 5 ? FL::ID : FL::EMIT)));
+            if (D == 2 && k == 2) continue;
+            prefetch_l2((k == 7 ? a.perm : a.src + (size_t)f * cap) + ns + (l << sh));
+          }
+          const int per = G::CELLS * 16 / (4 << sh);
+          for (int i = tid; i < G::NO * per; i += G2P_THREADS) {
+            const int o = i / per, l = i % per;
+            const int slot = a.pb_nbr[nb * G::NO + o];
+            if (slot >= 0) prefetch_l2(reinterpret_cast<const uint32_t*>(a.grid + (size_t)slot * G::CELLS) + (l << sh));
+          }
         }
       }
     }

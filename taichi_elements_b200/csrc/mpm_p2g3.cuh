@@ -149,15 +149,20 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
       __syncthreads();                                                  // payload ready
       // next block's particle rows towards L2 while this one computes (storage order is last
       // substep's sorted order, so rows [start, end) are almost where `perm` will point)
-      if (c0 == 0) {
+      if (c0 == 0 && a.pf_mode) {
         const int nb = s_next;
         if (nb < npb) {
           const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
-          const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
-          for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
-            const int f = i / lines, l = i % lines;
-            const uint32_t* ptr = (f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + l * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          if (a.pf_mode == 2) {
+            if (tid < FL::MAT + 2)
+              prefetch_l2_range((tid <= FL::MAT ? a.src + (size_t)tid * cap : a.perm) + ns, (uint32_t)(ne - ns) * 4u);
+          } else {
+            const int sh = a.pf_mode == 3 ? 3 : 5;         // words per prefetch: 8 (32 B) or 32 (128 B)
+            const int lines = (((ne - ns) + (1 << sh) - 1) >> sh) + 1;
+            for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
+              const int f = i / lines, l = i % lines;
+              prefetch_l2((f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + (l << sh));
+            }
           }
         }
       }
