@@ -82,7 +82,7 @@ struct mpm_ctx {
   GridCfg gcfg{};
   int sm_count = 148;
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
-  int g2p_cfg = 2;
+  int g2p_cfg = 6;
   int p2g_cfg = 0;
   int pf_mode = 2;              // next-block L2 prefetch: cp.async.bulk.prefetch ranges (MPM_PREFETCH)
   int p2g_ver = 3;              // 3: mpm_p2g3.cuh (3D, dense binning); 2: mpm_p2g.cuh
@@ -542,6 +542,8 @@ static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
     case 3: launch_g2p_cfg<D, 128, 8>(ctx, a, s); break;
     case 4: launch_g2p_cfg<D, 128, 10>(ctx, a, s); break;
     case 5: launch_g2p_cfg<D, 64, 16>(ctx, a, s); break;
+    case 6: launch_g2p_cfg<D, 128, 5>(ctx, a, s); break;
+    case 7: launch_g2p_cfg<D, 128, 4>(ctx, a, s); break;
     default: launch_g2p_cfg<D, 256, 3>(ctx, a, s); break;
   }
 }

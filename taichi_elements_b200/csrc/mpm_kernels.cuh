@@ -588,7 +588,9 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       int oct, cell;
       tile_node<D>(n, oct, cell);
       int slot = s_nbr[oct];
-      tile[n] = slot >= 0 ? a.grid[(size_t)slot * G::CELLS + cell] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g = slot >= 0 ? a.grid[(size_t)slot * G::CELLS + cell] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (D == 3) g.w = g.z;   // (vx, vy | vz, vz): the gather below works on packed pairs
+      tile[n] = g;
     }
     __syncthreads();
     {   // next block's particle rows and grid tiles towards L2 while this one computes
@@ -648,48 +650,59 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       }
       // Tensor-product evaluation of sum_ijk w_i w_j w_k g_ijk and of its first
       // moments (C = 4 inv_dx sum w g (x) (o - fx), :715-721): partial sums along
-      // z, then y, then x -- 279 FMAs instead of 27 x 23.
+      // z, then y, then x -- 279 FMAs instead of 27 x 23, issued as 126 FFMA2 + 21 FFMA in 3D.
       float nv[D], nC[D * D], mw[3][D];
 #pragma unroll
       for (int d = 0; d < D; ++d)
 #pragma unroll
         for (int i = 0; i < 3; ++i) mw[i][d] = w[i][d] * ((float)i - fx[d]);
       if constexpr (D == 3) {
-        float cx[3] = {0.f, 0.f, 0.f}, cy[3] = {0.f, 0.f, 0.f}, cz[3] = {0.f, 0.f, 0.f};
-        nv[0] = nv[1] = nv[2] = 0.0f;
+        // packed pairs (fma.rn.f32x2 -> FFMA2): .xy of every partial sum in one register pair, the
+        // z components of the plain and the z-moment sums in another
+        float2 wz2[3], mz2[3], wmz[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wz2[k] = make_float2(w[k][2], w[k][2]);
+          mz2[k] = make_float2(mw[k][2], mw[k][2]);
+          wmz[k] = make_float2(w[k][2], mw[k][2]);
+        }
+        float2 nvxy = make_float2(0.f, 0.f), cxxy = nvxy, cyxy = nvxy, czxy = nvxy, nvcz = nvxy;   // nvcz = (nv.z, cz.z)
+        float cxz = 0.f, cyz = 0.f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          float B00[3] = {0.f, 0.f, 0.f}, B10[3] = {0.f, 0.f, 0.f}, B01[3] = {0.f, 0.f, 0.f};
+          float2 B00 = make_float2(0.f, 0.f), B10 = B00, B01 = B00, Bz = B00;   // Bz = (B00.z, B01.z)
+          float B10z = 0.f;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            float A0[3] = {0.f, 0.f, 0.f}, A1[3] = {0.f, 0.f, 0.f};
+            float2 A0 = make_float2(0.f, 0.f), A1 = A0, Az = A0;              // Az = (A0.z, A1.z)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const float4 g = tile[((l[0] + i) * G::T + (l[1] + j)) * G::T + (l[2] + k)];
-              A0[0] += w[k][2] * g.x; A0[1] += w[k][2] * g.y; A0[2] += w[k][2] * g.z;
-              A1[0] += mw[k][2] * g.x; A1[1] += mw[k][2] * g.y; A1[2] += mw[k][2] * g.z;
+              A0 = __ffma2_rn(wz2[k], make_float2(g.x, g.y), A0);
+              A1 = __ffma2_rn(mz2[k], make_float2(g.x, g.y), A1);
+              Az = __ffma2_rn(wmz[k], make_float2(g.z, g.w), Az);
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              B00[r] += w[j][1] * A0[r];
-              B10[r] += mw[j][1] * A0[r];
-              B01[r] += w[j][1] * A1[r];
-            }
+            const float2 wj = make_float2(w[j][1], w[j][1]), mj = make_float2(mw[j][1], mw[j][1]);
+            B00 = __ffma2_rn(wj, A0, B00);
+            B10 = __ffma2_rn(mj, A0, B10);
+            B01 = __ffma2_rn(wj, A1, B01);
+            Bz = __ffma2_rn(wj, Az, Bz);
+            B10z = fmaf(mw[j][1], Az.x, B10z);
           }
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            nv[r] += w[i][0] * B00[r];
-            cx[r] += mw[i][0] * B00[r];
-            cy[r] += w[i][0] * B10[r];
-            cz[r] += w[i][0] * B01[r];
-          }
+          const float2 wi = make_float2(w[i][0], w[i][0]), mi = make_float2(mw[i][0], mw[i][0]);
+          nvxy = __ffma2_rn(wi, B00, nvxy);
+          cxxy = __ffma2_rn(mi, B00, cxxy);
+          cyxy = __ffma2_rn(wi, B10, cyxy);
+          czxy = __ffma2_rn(wi, B01, czxy);
+          nvcz = __ffma2_rn(wi, Bz, nvcz);
+          cxz = fmaf(mw[i][0], Bz.x, cxz);
+          cyz = fmaf(w[i][0], B10z, cyz);
         }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          nC[r * 3 + 0] = a.K.four_inv_dx * cx[r];
-          nC[r * 3 + 1] = a.K.four_inv_dx * cy[r];
-          nC[r * 3 + 2] = a.K.four_inv_dx * cz[r];
-        }
+        nv[0] = nvxy.x; nv[1] = nvxy.y; nv[2] = nvcz.x;
+        const float f4 = a.K.four_inv_dx;
+        nC[0] = f4 * cxxy.x; nC[1] = f4 * cyxy.x; nC[2] = f4 * czxy.x;
+        nC[3] = f4 * cxxy.y; nC[4] = f4 * cyxy.y; nC[5] = f4 * czxy.y;
+        nC[6] = f4 * cxz;    nC[7] = f4 * cyz;    nC[8] = f4 * nvcz.y;
       } else {
         float cx[2] = {0.f, 0.f}, cy[2] = {0.f, 0.f};
         nv[0] = nv[1] = 0.0f;

@@ -25,7 +25,8 @@ namespace mpm {
 
 struct P2G3 {
   static constexpr int T = 192, SL = 3, NPT = 9, PS = 5;   // threads, x-slices, nodes per thread, float4 per particle
-  static constexpr int CP = 16 * 6;                        // one flush copy: [cx][cy][z] float4
+  static constexpr int CP = 16 * 6 + 1;                    // one flush copy: [cx][cy][z] float4, +1: the three
+                                                           // x-slices of a cell must not share banks
   static constexpr int COPIES = 9 * CP;                    // float4
 };
 
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
       // plain store (first touch) or a private read-add-write.
       {
         const int cx = cell >> 4, cy = (cell >> 2) & 3, cz = cell & 3;
-        float4* my = pay + ((sl * 3) * 16 + cx * 4 + cy) * 6 + cz;
+        float4* my = pay + (sl * 3) * P2G3::CP + (cx * 4 + cy) * 6 + cz;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {                                   // z = cz (k = 0); z = 4, 5 (k = 2)
           my[j * P2G3::CP] = make_float4(acc01[j * 3].x, acc01[j * 3].y, acc23[j * 3].x, acc23[j * 3].y);
