@@ -503,10 +503,10 @@ static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   if constexpr (D == 3) {
     if (ctx->p2g_ver == 3 && a.cellstart) {
       switch (ctx->p2g_cfg) {
-        case 1: launch_p2g3_cfg<512, 5>(ctx, a, s); break;
-        case 2: launch_p2g3_cfg<640, 3>(ctx, a, s); break;
-        case 3: launch_p2g3_cfg<384, 6>(ctx, a, s); break;
-        case 4: launch_p2g3_cfg<768, 3>(ctx, a, s); break;
+        case 1: launch_p2g3_cfg<768, 4>(ctx, a, s); break;
+        case 2: launch_p2g3_cfg<576, 4>(ctx, a, s); break;
+        case 3: launch_p2g3_cfg<544, 4>(ctx, a, s); break;
+        case 4: launch_p2g3_cfg<1024, 3>(ctx, a, s); break;
         default: launch_p2g3_cfg<640, 4>(ctx, a, s); break;
       }
       return;

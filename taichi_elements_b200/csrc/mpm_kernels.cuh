@@ -536,9 +536,10 @@ template <int D, int G2P_THREADS, int G2P_MINB>
 __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
-  __shared__ float4 tile[G::TN];
+  // The velocity tile of the NEXT block is fetched with cp.async into the other buffer while this
+  // block's particles are gathered: one CTA barrier per block, no exposed grid-load latency.
+  __shared__ float4 tile_buf[2][G::TN];
   __shared__ int s_b;
-  __shared__ int s_nbr[G::NO];
   if (a.st->err) return;
   const int npb = a.st->npb;
   const int tid = threadIdx.x;
@@ -547,17 +548,47 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
   int lo[D], hi[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) { lo[d] = INT_MAX; hi[d] = INT_MIN; }
-  __shared__ int s_next;
+  __shared__ int s_next[2];
   // fused key pass: which spill patterns (bit = 1 << nsp) the particles that STAY in this CTA's
   // current block show; expanded to block flags once per block instead of once per particle
-  __shared__ unsigned s_seen;
-  if (tid == 0) { s_b = atomicAdd(&a.st->work_g2p, 1); s_seen = 0u; }
+  __shared__ unsigned s_seen[2];
+  if (tid == 0) { s_b = atomicAdd(&a.st->work_g2p, 1); s_seen[0] = 0u; s_seen[1] = 0u; }
   __syncthreads();
   int b = s_b;
+  // asynchronous copy of block blk's (LEAF+2)^D node tile (zero-filled where no grid block exists)
+  auto stage_tile = [&](int blk, float4* dstt) {
+    for (int n = tid; n < G::TN; n += G2P_THREADS) {
+      int oct, cell;
+      tile_node<D>(n, oct, cell);
+      const int slot = a.pb_nbr[blk * G::NO + oct];
+      const float4* src = a.grid + (slot >= 0 ? (size_t)slot * G::CELLS + cell : 0);
+      const unsigned daddr = (unsigned)__cvta_generic_to_shared(dstt + n);
+      const int nbytes = slot >= 0 ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(daddr), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (b < npb) stage_tile(b, tile_buf[0]);
+  int u = 0;
+  uint32_t prev_lin = 0u;
+  bool have_prev = false;
+  // flags of a finished block from the spill patterns its staying particles showed: octant o of
+  // the stencil union is touched iff some particle spills along every axis of o
+  auto write_flags = [&](uint32_t lin, unsigned* seen_slot) {
+    if (tid < G::NO) {
+      const unsigned sn = *seen_slot;
+      unsigned sup = 0u;
+#pragma unroll
+      for (unsigned q = 0; q < (unsigned)G::NO; ++q)
+        if (((unsigned)tid & ~q) == 0u) sup |= 1u << q;
+      if (sn & sup) a.next_flags[a.next_nlin + (int)lin + oct_delta_l<D>(a.L, tid)] = 1;
+      __syncwarp((1u << G::NO) - 1u);
+      if (tid == 0 && sn) { a.next_flags[lin] = 1; *seen_slot = 0u; }
+    }
+  };
   while (b < npb) {
-    if (tid == 0) s_next = atomicAdd(&a.st->work_g2p, 1);   // one block ahead, for the prefetch below
+    if (tid == 0) s_next[u] = atomicAdd(&a.st->work_g2p, 1);   // one block ahead
     const int start = a.pb_start[b], end = a.pb_start[b + 1];
-    if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
     const uint32_t cur_lin = a.pb_key[b];
     unsigned seen = 0u;
     int org[D];
@@ -570,7 +601,6 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     // software pipeline over this thread's particles: `perm` runs two iterations
     // ahead and the position/material loads one iteration ahead of the arithmetic, so
     // the dependent perm -> x latency chain overlaps the previous particle's math
-    // (and, for the first particle, the tile staging below)
     int s = start + tid;
     uint32_t p1 = s < end ? a.perm[s] : 0u;
     uint32_t p2 = s + G2P_THREADS < end ? a.perm[s + G2P_THREADS] : 0u;
@@ -583,27 +613,24 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       for (int d = 0; d < D; ++d) xn[d] = ldf(a.src, cap, FL::X + d, p1);
       matn = ldu(a.src, cap, FL::MAT, p1);
     }
-    __syncthreads();
-    for (int n = tid; n < G::TN; n += G2P_THREADS) {
-      int oct, cell;
-      tile_node<D>(n, oct, cell);
-      int slot = s_nbr[oct];
-      float4 g = slot >= 0 ? a.grid[(size_t)slot * G::CELLS + cell] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (D == 3) g.w = g.z;   // (vx, vy | vz, vz): the gather below works on packed pairs
-      tile[n] = g;
+    float4* tile = tile_buf[u];
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if constexpr (D == 3) {
+      // (vx, vy | vz, vz): the gather below works on packed pairs; every thread patches the nodes it copied
+      for (int n = tid; n < G::TN; n += G2P_THREADS) tile[n].w = tile[n].z;
     }
-    __syncthreads();
-    {   // next block's particle rows and grid tiles towards L2 while this one computes
-      const int nb = s_next;
+    __syncthreads();   // tile complete; s_next visible; every warp is done with the previous block
+    if (a.next_keys && have_prev) write_flags(prev_lin, &s_seen[u ^ 1]);
+    const int nb_claim = s_next[u];
+    if (nb_claim < npb) stage_tile(nb_claim, tile_buf[u ^ 1]);
+    {   // next block's particle rows towards L2 while this one computes
+      const int nb = nb_claim;
       if (nb < npb && a.pf_mode) {
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
         if (a.pf_mode == 2) {
           if (tid < 8 && !(D == 2 && tid == 2)) {
             const int f = tid < D ? FL::X + tid : (tid == 3 ? FL::MAT : (tid == 4 ? FL::COLOR : (tid == 5 ? FL::ID : FL::EMIT)));
             prefetch_l2_range((tid == 7 ? a.perm : a.src + (size_t)f * cap) + ns, (uint32_t)(ne - ns) * 4u);
-          } else if (tid >= 32 && tid < 32 + G::NO) {
-            const int slot = a.pb_nbr[nb * G::NO + tid - 32];
-            if (slot >= 0) prefetch_l2_range(a.grid + (size_t)slot * G::CELLS, G::CELLS * 16);
           }
         } else {
           const int sh = a.pf_mode == 3 ? 3 : 5;           // words per prefetch: 8 (32 B) or 32 (128 B)
@@ -613,12 +640,6 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
             const int f = k < D ? FL::X + k : (k == 3 ? FL::MAT : (k == 4 ? FL::COLOR : (k == 5 ? FL::ID : FL::EMIT)));
             if (D == 2 && k == 2) continue;
             prefetch_l2((k == 7 ? a.perm : a.src + (size_t)f * cap) + ns + (l << sh));
-          }
-          const int per = G::CELLS * 16 / (4 << sh);
-          for (int i = tid; i < G::NO * per; i += G2P_THREADS) {
-            const int o = i / per, l = i % per;
-            const int slot = a.pb_nbr[nb * G::NO + o];
-            if (slot >= 0) prefetch_l2(reinterpret_cast<const uint32_t*>(a.grid + (size_t)slot * G::CELLS) + (l << sh));
           }
         }
       }
@@ -729,11 +750,13 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         }
       }
       if (mat == (uint32_t)STATIONARY) {                       // :722
+        // The x + (-0) identity consumes each load INSIDE this rare branch: otherwise the stores after
+        // the join wait on a scoreboard shared with the next particle's prefetched loads.
 #pragma unroll
-        for (int d = 0; d < D; ++d) nv[d] = ldf(a.src, cap, FL::V + d, p);
+        for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(ldf(a.src, cap, FL::V + d, p), -0.0f);
         if (!a.K.g2p2g) {      // [g2p2g] C is a register value there: the gathered C is used (:385, 414)
 #pragma unroll
-          for (int i = 0; i < D * D; ++i) nC[i] = ldf(a.src, cap, FL::C + i, p);
+          for (int i = 0; i < D * D; ++i) nC[i] = __fadd_rn(ldf(a.src, cap, FL::C + i, p), -0.0f);
         }
       } else {
 #pragma unroll
@@ -810,21 +833,17 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     }
     if (a.next_keys) {
       seen = __reduce_or_sync(0xffffffffu, seen);
-      if ((tid & 31) == 0 && seen) atomicOr(&s_seen, seen);
+      if ((tid & 31) == 0 && seen) atomicOr(&s_seen[u], seen);
     }
-    b = s_next;
+    prev_lin = cur_lin;
+    have_prev = true;
+    b = nb_claim;
+    u ^= 1;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (a.next_keys && have_prev) {
     __syncthreads();
-    if (a.next_keys && tid < G::NO) {
-      // octant o of the stencil union is touched iff some staying particle spills along every axis of o
-      const unsigned sn = s_seen;
-      unsigned sup = 0u;
-#pragma unroll
-      for (unsigned q = 0; q < (unsigned)G::NO; ++q)
-        if (((unsigned)tid & ~q) == 0u) sup |= 1u << q;
-      if (sn & sup) a.next_flags[a.next_nlin + (int)cur_lin + oct_delta_l<D>(a.L, tid)] = 1;
-      __syncwarp((1u << G::NO) - 1u);
-      if (tid == 0 && sn) { a.next_flags[cur_lin] = 1; s_seen = 0u; }   // next atomicOr is two barriers away
-    }
+    write_flags(prev_lin, &s_seen[u ^ 1]);
   }
   // CTA-wide reductions, once per CTA lifetime
 #pragma unroll

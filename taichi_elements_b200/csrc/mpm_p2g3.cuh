@@ -6,10 +6,11 @@
 // second revision: 14 CTA barriers per block (3.4 of ~6 resident warps per
 // scheduler parked at a barrier), a 64-step rank loop on two warps, and an
 // FFMA-per-scalar inner loop.
-//   * payload is AoS, five float4 per particle (m*v|m, three columns of dx*A
-//     with a zero fourth lane, fx): 5 LDS.128 instead of 16 LDS.32, and the
-//     scatter arithmetic runs on packed pairs (fma.rn.f32x2 -> FFMA2), the
-//     mass riding in the fourth lane
+//   * payload is AoS, four float4 per particle (m*v|m and the three columns of
+//     dx*A, each with one component of fx in its fourth lane), 16-byte columns
+//     rotated by the particle index against bank conflicts: 4 LDS.128 instead of
+//     16 LDS.32, and the scatter arithmetic runs on packed pairs
+//     (fma.rn.f32x2 -> FFMA2)
 //   * the accumulators of a thread are flushed ONCE per block into nine private
 //     4x4x6 copies (one per (x, y) stencil offset) that alias the dead payload:
 //     three conflict-free rounds over the z offset, no tile to clear; a node then
@@ -24,7 +25,7 @@
 namespace mpm {
 
 struct P2G3 {
-  static constexpr int T = 192, SL = 3, NPT = 9, PS = 5;   // threads, x-slices, nodes per thread, float4 per particle
+  static constexpr int T = 192, SL = 3, NPT = 9, PS = 4;   // threads, x-slices, nodes per thread, float4 per particle
   static constexpr int CP = 16 * 6 + 1;                    // one flush copy: [cx][cy][z] float4, +1: the three
                                                            // x-slices of a cell must not share banks
   static constexpr int COPIES = 9 * CP;                    // float4
@@ -140,12 +141,11 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
 #pragma unroll
         for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
         const float dx = a.K.dx;                                       // dpos = (o - fx) * dx
-        float4* pp = pay + q * PS;
-        pp[0] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
-        pp[1] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, 0.0f);
-        pp[2] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, 0.0f);
-        pp[3] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, 0.0f);
-        pp[4] = make_float4(fx[0], fx[1], fx[2], 0.0f);
+        const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
+        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
+        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
+        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
       }
       __syncthreads();                                                  // payload ready
       // next block's particle rows towards L2 while this one computes (storage order is last
@@ -174,35 +174,39 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
       {
         const int lo = max(c_lo, c0) - c0, hi = min(c_hi, c0 + cn) - c0;
         for (int q = lo; q < hi; ++q) {
-          const float4* pp = pay + q * PS;
-          const float4 M = pp[0], Ax = pp[1], Ay = pp[2], Az = pp[3], fxv = pp[4];
-          const float wi = fmaf(fmaf(k2, fxv.x, k1), fxv.x, k0);
-          const float2 d0 = f2(slf - fxv.x);
+          const int sw = (q >> 1) & 3;
+          const float4 M = pay[q * PS + (0 ^ sw)], Ax = pay[q * PS + (1 ^ sw)], Ay = pay[q * PS + (2 ^ sw)],
+                       Az = pay[q * PS + (3 ^ sw)];
+          const float fx0 = Ax.w, fx1 = Ay.w, fx2 = Az.w;
+          const float wi = fmaf(fmaf(k2, fx0, k1), fx0, k0);
+          const float d0s = slf - fx0;
+          const float2 d0 = f2(d0s);
           const float2 a01 = __ffma2_rn(make_float2(Ax.x, Ax.y), d0, make_float2(M.x, M.y));
-          const float2 a23 = __ffma2_rn(make_float2(Ax.z, Ax.w), d0, make_float2(M.z, M.w));
+          const float a2 = fmaf(Ax.z, d0s, M.z);
           float wy[3], wz[3];
-          wy[0] = 0.5f * (1.5f - fxv.y) * (1.5f - fxv.y);
-          wy[1] = 0.75f - (fxv.y - 1.0f) * (fxv.y - 1.0f);
-          wy[2] = 0.5f * (fxv.y - 0.5f) * (fxv.y - 0.5f);
-          wz[0] = 0.5f * (1.5f - fxv.z) * (1.5f - fxv.z);
-          wz[1] = 0.75f - (fxv.z - 1.0f) * (fxv.z - 1.0f);
-          wz[2] = 0.5f * (fxv.z - 0.5f) * (fxv.z - 0.5f);
+          wy[0] = 0.5f * (1.5f - fx1) * (1.5f - fx1);
+          wy[1] = 0.75f - (fx1 - 1.0f) * (fx1 - 1.0f);
+          wy[2] = 0.5f * (fx1 - 0.5f) * (fx1 - 0.5f);
+          wz[0] = 0.5f * (1.5f - fx2) * (1.5f - fx2);
+          wz[1] = 0.75f - (fx2 - 1.0f) * (fx2 - 1.0f);
+          wz[2] = 0.5f * (fx2 - 0.5f) * (fx2 - 0.5f);
           float2 d2[3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) d2[k] = f2((float)k - fxv.z);
+          for (int k = 0; k < 3; ++k) d2[k] = f2((float)k - fx2);
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const float2 d1 = f2((float)j - fxv.y);
+            const float d1s = (float)j - fx1;
+            const float2 d1 = f2(d1s);
             const float wij = wi * wy[j];
             const float2 b01 = __ffma2_rn(make_float2(Ay.x, Ay.y), d1, a01);
-            const float2 b23 = __ffma2_rn(make_float2(Ay.z, Ay.w), d1, a23);
+            const float b2 = fmaf(Ay.z, d1s, a2);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const float2 wt = f2(wij * wz[k]);
               const float2 t01 = __ffma2_rn(make_float2(Az.x, Az.y), d2[k], b01);
-              const float2 t23 = __ffma2_rn(make_float2(Az.z, Az.w), d2[k], b23);   // .y = mass
+              const float2 t2m = make_float2(fmaf(Az.z, d2[k].x, b2), M.w);        // (momentum z, mass)
               acc01[j * 3 + k] = __ffma2_rn(wt, t01, acc01[j * 3 + k]);
-              acc23[j * 3 + k] = __ffma2_rn(wt, t23, acc23[j * 3 + k]);
+              acc23[j * 3 + k] = __ffma2_rn(wt, t2m, acc23[j * 3 + k]);
             }
           }
         }
