@@ -281,12 +281,12 @@ def main():
     if world > 1:   # phase API: no per-kernel events; report the whole substep per GPU
         achieved = b_alg_step / (ms_per_step * 1e-3) / 1e9
     roofline = {
-        'bound': 'hbm', 'kernel': 'k_p2g_cell<3>' if world == 1 else 'whole substep, per GPU (no per-kernel events in the multi-GPU phase path)',
+        'bound': 'hbm', 'kernel': 'k_p2g3<640,4>' if world == 1 else 'whole substep, per GPU (no per-kernel events in the multi-GPU phase path)',
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of k_p2g_cell<3> on this workload, one ncu --set full
-        # capture (profiles/r01_ncu_final.md): 479.4 MB + 155.5 MB per launch
-        'traffic': 634.9e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of k_p2g3<640,4> on this workload, one ncu --set full
+        # capture (profiles/r01_ncu_final_v5.md): 473.3 MB + 159.0 MB per launch
+        'traffic': 632.2e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
         'peak_source': peak_src,
         'algorithmic_bytes_per_launch': b_alg_p2g,
         'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--workload', default='cube_drop_4m')
 ap.add_argument('--warm', type=int, default=2)
 ap.add_argument('--substeps', type=int, default=3)
+ap.add_argument('--batch', type=int, default=1, help='substeps per mpm_substeps call (> 1: G2P also emits the next keys)')
 args = ap.parse_args()
 
 from taichi_elements_b200.engine.mpm_solver import MPMSolver  # noqa: E402
@@ -30,7 +31,7 @@ mpm._run_substeps(dt, 1)              # grows the block workspace (failed attemp
 for _ in range(args.warm):
     mpm._run_substeps(dt, 1)
 for _ in range(args.substeps):
-    mpm._run_substeps(dt, 1)
+    mpm._run_substeps(dt, args.batch)
 st = mpm.stats()
 print('particles', mpm.n_particles[None], 'particle blocks', st.n_particle_blocks, 'grid blocks', st.n_grid_blocks,
       'max_blocks', st.max_blocks, 'key bits', st.key_bits)
