@@ -159,6 +159,19 @@ int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t b
                     void* stream); /* rows dst[i][nwords] of consecutive words (copy_dynamic_nd, :1146-1150) */
 int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_dev, void* stream);
 
+/* ParticleIO.write_particles on the device (engine/particle_io.py:12-76): the slice-by-slice
+ * read-back of x, v and colour plus the NumPy quantisation become two calls.
+ * mpm_particle_ranges: min and max of every x and v component over all particles, as f32
+ *   ranges_dev[2][dim][2] = [x|v][axis][min|max] (device memory, 4*dim floats) (:42-45).
+ * mpm_pack_particles: x_and_v[id][axis] = (xq << 8) + vq with
+ *   q = uint32(((a - lo) * inv) * (2^bits - 1) + 0.499) in f32, bits = 24 / 8 (:50-56), and
+ *   color[id][0..2] = (c >> 16, c >> 8, c) & 255 (:71-72), both in insertion order.
+ *   lo_inv_host[2][dim][2] = [x|v][axis][lo | 1/(hi-lo)] is host memory (the caller applies the
+ *   reference's degenerate-range fix, :46-47, before inverting). */
+int mpm_particle_ranges(mpm_ctx* ctx, float* ranges_dev, void* stream);
+int mpm_pack_particles(mpm_ctx* ctx, const float* lo_inv_host, uint32_t* x_and_v_dev, uint8_t* color_dev,
+                       void* stream);
+
 
 
 /* ---- multi-GPU slab decomposition along x (no reference counterpart: the

@@ -85,6 +85,8 @@ SYMBOLS = [
     ('mpm_download', _i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     ('mpm_gather', _i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     ('mpm_gather_rows', _i32, [_vp, _i32, _i32, _i64, _i64, _vp, _vp]),
+    ('mpm_particle_ranges', _i32, [_vp, _vp, _vp]),
+    ('mpm_pack_particles', _i32, [_vp, _vp, _vp, _vp, _vp]),
     ('mpm_set_slab', _i32, [_vp, _i32, _i32, _i32]),
     ('mpm_comm_bytes', ctypes.c_size_t, [_i32, _i32, _i32]),
     ('mpm_bind_comm', _i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32]),

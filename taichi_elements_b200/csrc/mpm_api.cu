@@ -1252,6 +1252,44 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
   return MPM_OK;
 }
 
+// ParticleIO.write_particles on the device (engine/particle_io.py:42-76)
+extern "C" int mpm_particle_ranges(mpm_ctx* ctx, float* ranges_dev, void* stream) {
+  if (!ctx || !ranges_dev) return MPM_E_INVALID;
+  if (ctx->n <= 0) return fail(ctx, MPM_E_INVALID, "mpm_particle_ranges: no particles");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* r = reinterpret_cast<uint32_t*>(ranges_dev);
+  const int nw = 4 * ctx->dim;
+  k_ranges_init<<<1, 32, 0, s>>>(r, nw);
+  const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
+  if (ctx->dim == 3) k_ranges<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r);
+  else k_ranges<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r);
+  k_ranges_decode<<<1, 32, 0, s>>>(r, nw);
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+extern "C" int mpm_pack_particles(mpm_ctx* ctx, const float* lo_inv_host, uint32_t* x_and_v_dev, uint8_t* color_dev,
+                                  void* stream) {
+  if (!ctx || !lo_inv_host) return MPM_E_INVALID;
+  if (ctx->n <= 0) return MPM_OK;
+  if (!x_and_v_dev || !color_dev) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  PackArgs pa{};
+  for (int c = 0; c < 2; ++c)
+    for (int d = 0; d < ctx->dim; ++d) {
+      pa.lo[c][d] = lo_inv_host[(c * ctx->dim + d) * 2];
+      pa.inv[c][d] = lo_inv_host[(c * ctx->dim + d) * 2 + 1];
+    }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
+  if (ctx->dim == 3)
+    k_pack_particles<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, pa, x_and_v_dev, color_dev);
+  else
+    k_pack_particles<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, pa, x_and_v_dev, color_dev);
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
 extern "C" int mpm_download(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t end, void* dst_host, void* stream) {
   if (!ctx) return MPM_E_INVALID;
   int rc = mpm_gather(ctx, field, begin, end, ctx->stage, stream);

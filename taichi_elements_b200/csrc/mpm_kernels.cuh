@@ -1132,6 +1132,71 @@ __global__ void k_gather_rows(const uint32_t* __restrict__ state, size_t cap, in
   }
 }
 
+// ---- ParticleIO.write_particles on the device (engine/particle_io.py:42-76)
+// order-preserving map float -> uint32 so integer atomics give float min / max
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void k_ranges_init(uint32_t* r, int nwords) {
+  const int i = threadIdx.x;
+  if (i < nwords) r[i] = (i & 1) ? 0u : 0xffffffffu;     // [.. min, max ..]
+}
+// ranges[c][d][0|1] (c = 0: x, 1: v) as ordered uints; fields X and V are the first 2*D state words
+template <int D>
+__global__ void k_ranges(const uint32_t* __restrict__ state, size_t cap, int n, uint32_t* __restrict__ r) {
+  float lo[2 * D], hi[2 * D];
+#pragma unroll
+  for (int f = 0; f < 2 * D; ++f) { lo[f] = __int_as_float(0x7f800000); hi[f] = __int_as_float(0xff800000); }
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int f = 0; f < 2 * D; ++f) {
+      const float a = ldf(state, cap, f, s);
+      lo[f] = fminf(lo[f], a); hi[f] = fmaxf(hi[f], a);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 2 * D; ++f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[f] = fminf(lo[f], __shfl_xor_sync(0xffffffffu, lo[f], o));
+      hi[f] = fmaxf(hi[f], __shfl_xor_sync(0xffffffffu, hi[f], o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo[f] <= hi[f]) {
+      atomicMin(&r[2 * f], f2ord(lo[f]));
+      atomicMax(&r[2 * f + 1], f2ord(hi[f]));
+    }
+  }
+}
+__global__ void k_ranges_decode(uint32_t* r, int nwords) {
+  const int i = threadIdx.x;
+  if (i < nwords) r[i] = __float_as_uint(ord2f(r[i]));
+}
+struct PackArgs { float lo[2][3], inv[2][3]; };
+template <int D>
+__global__ void k_pack_particles(const uint32_t* __restrict__ state, size_t cap, int n, PackArgs pa,
+                                 uint32_t* __restrict__ xv, uint8_t* __restrict__ color) {
+  using FL = Fld<D>;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    const uint32_t id = ldu(state, cap, FL::ID, s);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      // ((a - lo) * (1 / (hi - lo)) * (2^bits - 1) + 0.499).astype(uint32), every step rounded to f32 (:50-55)
+      const float x = ldf(state, cap, FL::X + d, s), v = ldf(state, cap, FL::V + d, s);
+      const uint32_t xq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, pa.lo[0][d]), pa.inv[0][d]), 16777215.0f), 0.499f));
+      const uint32_t vq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v, pa.lo[1][d]), pa.inv[1][d]), 255.0f), 0.499f));
+      xv[(size_t)id * D + d] = (xq << 8) + vq;
+    }
+    const uint32_t c = ldu(state, cap, FL::COLOR, s);
+    color[(size_t)id * 3 + 0] = (uint8_t)((c >> 16) & 255u);
+    color[(size_t)id * 3 + 1] = (uint8_t)((c >> 8) & 255u);
+    color[(size_t)id * 3 + 2] = (uint8_t)(c & 255u);
+  }
+}
+
 // g2p2g with a pending scatter half: F and Jp of the binned particles have already been
 // advanced by that half and live in the other set at their sorted slots (row s <- perm[s]);
 // everything else, and particles added since, is read from the live set.

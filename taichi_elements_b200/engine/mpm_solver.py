@@ -588,6 +588,31 @@ class MPMSolver:
         from .particle_io import ParticleIO
         ParticleIO.write_particles(self, fn, slice_size)
 
+    def _pack_particles(self):
+        """(ranges, x_and_v, color) of ParticleIO.write_particles (ref engine/particle_io.py:12-76),
+        quantised and packed on the device: 4*dim + 3 bytes per particle cross PCIe instead of the
+        reference's slice-by-slice read-back of six f32 fields and the colour."""
+        n, dim = self._n, self.dim
+        if n == 0:
+            return None
+        with torch.cuda.device(self._device):
+            rdev = torch.empty((2, dim, 2), dtype=torch.float32, device=self._device)
+            self._check(self._lib.mpm_particle_ranges(self._ctx, rdev.data_ptr(), self._stream()),
+                        'mpm_particle_ranges')
+            ranges = rdev.cpu().numpy()
+            for c in range(2):          # avoid degenerate ranges (ref :46-47), in f32 like the reference
+                for d in range(dim):
+                    ranges[c, d, 1] = max(ranges[c, d, 0] + 1e-5, ranges[c, d, 1])
+            lo_inv = np.empty((2, dim, 2), np.float32)
+            lo_inv[:, :, 0] = ranges[:, :, 0]
+            lo_inv[:, :, 1] = 1 / (ranges[:, :, 1] - ranges[:, :, 0])
+            xv = torch.empty((n, dim), dtype=torch.int32, device=self._device)
+            col = torch.empty((n, 3), dtype=torch.uint8, device=self._device)
+            self._check(self._lib.mpm_pack_particles(self._ctx, lo_inv.ctypes.data_as(ctypes.c_void_p),
+                                                     xv.data_ptr(), col.data_ptr(), self._stream()),
+                        'mpm_pack_particles')
+        return ranges, xv.cpu().numpy().view(np.uint32), col.cpu().numpy()
+
     def write_particles_ply(self, fn):
         np_x = self.x.to_numpy()
         np_color = self.color.to_numpy().astype(np.uint32)

@@ -27,6 +27,12 @@ class ParticleIO:
         t = time.time()
         n = solver.n_particles[None]
         dim = solver.dim
+        packed = solver._pack_particles() if hasattr(solver, '_pack_particles') else None
+        if packed is not None:       # quantised and packed on the device, same bytes as the loop below
+            ranges, x_and_v, color = packed
+            np.savez(fn, ranges=ranges, x_and_v=x_and_v, color=color)
+            print(f'Writing to disk: {time.time() - t:.3f} s')
+            return
         x_and_v = np.ndarray((n, dim), dtype=np.uint32)
         ranges = np.ndarray((2, dim, 2), dtype=np.float32)
         num_slices = (n + slice_size - 1) // slice_size

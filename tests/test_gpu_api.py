@@ -147,6 +147,20 @@ def test_write_particles_round_trip(tmp_path):
     s.step(2e-3)
     fn = str(tmp_path / 'frame.npz')
     s.write_particles(fn, slice_size=1000)
+    # packed on the device (mpm_pack_particles) == the reference's NumPy loop over copy_ranged, byte for byte
+    class _HostPath:
+        def __init__(self, solver):
+            self._s = solver
+        def __getattr__(self, name):
+            if name == '_pack_particles':
+                raise AttributeError(name)
+            return getattr(self._s, name)
+    fn_host = str(tmp_path / 'frame_host.npz')
+    ParticleIO.write_particles(_HostPath(s), fn_host, slice_size=1000)
+    dev, host = np.load(fn), np.load(fn_host)
+    for key in ('ranges', 'x_and_v', 'color'):
+        assert dev[key].dtype == host[key].dtype and dev[key].shape == host[key].shape
+        assert np.array_equal(dev[key], host[key]), key
     x, v, color = ParticleIO.read_particles_3d(fn)
     info = s.particle_info()
     span = info['position'].max(0) - info['position'].min(0)
