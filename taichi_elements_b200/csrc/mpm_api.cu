@@ -84,6 +84,8 @@ struct mpm_ctx {
   int grid_p2g = 148, grid_g2p = 148, grid_p2g_cell = 148;
   int g2p_cfg = 6;
   int p2g_cfg = 0;
+  int pdl = 1;                  // programmatic dependent launch along the substep chain (MPM_PDL)
+  bool cell_zeroed = false, flags_zeroed = false;   // tables already cleared by k_clear_grid
   int pf_mode = 2;              // next-block L2 prefetch: cp.async.bulk.prefetch ranges (MPM_PREFETCH)
   int p2g_ver = 3;              // 3: mpm_p2g3.cuh (3D, dense binning); 2: mpm_p2g.cuh
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
@@ -112,6 +114,21 @@ static int fail(mpm_ctx* ctx, int code, const std::string& msg) {
 static inline int gs_blocks(int64_t n, int threads, int sm) {
   int64_t b = (n + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm * 16));
+}
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled
+// while the previous kernel of the stream drains; it parks in pdl_enter() until that one is complete.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 // ------------------------------------------------------------------ sizes
@@ -235,6 +252,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
+  if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
@@ -265,6 +283,7 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->state[0] = (uint32_t*)s0;
   ctx->state[1] = (uint32_t*)s1;
   ctx->cap = (size_t)capacity;
+  ctx->cell_zeroed = false; ctx->flags_zeroed = false;   // new workspace: nothing is cleared yet
   ctx->ws = ws;
   ctx->ws_bytes = ws_bytes;
   ctx->max_blocks = max_blocks;
@@ -496,7 +515,7 @@ static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g3<CH, MB>, P2G3::T, smem);
     grid = ctx->sm_count * std::max(occ, 1);
   }
-  k_p2g3<CH, MB><<<grid, P2G3::T, smem, s>>>(a);
+  launch_chain(ctx->pdl, k_p2g3<CH, MB>, grid, P2G3::T, smem, s, a);
 }
 template <int D>
 static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
@@ -532,7 +551,7 @@ static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<D, T, MB>, T, 0);
     grid = ctx->sm_count * std::max(occ, 1);
   }
-  k_g2p<D, T, MB><<<grid, T, 0, s>>>(a);
+  launch_chain(ctx->pdl, k_g2p<D, T, MB>, grid, T, 0, s, a);
 }
 template <int D>
 static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
@@ -563,7 +582,8 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
 }
 
 template <int D>
-static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev) {
+static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev,
+                           bool fuse_next = false) {
   const bool prof = ev != nullptr;
   using G = Geo<D>;
   const int n = (int)ctx->n;
@@ -580,10 +600,11 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     int nlin = 1;
     for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
     const int ncell = ctx->max_blocks * G::CELLS + 1;
-    CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
+    if (!ctx->cell_zeroed) CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
+    ctx->cell_zeroed = false;
     if (ctx->keys_ready) {
       // keys and flags were written by the previous substep's G2P (mpm_kernels.cuh, next_keys)
-      k_substep_begin<<<1, 1, 0, s>>>(st);
+      CK(launch_chain(ctx->pdl, k_substep_begin, 1, 1, 0, s, st));
     } else {
       CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
       k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
@@ -592,14 +613,15 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     ctx->keys_ready = false;
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
-    k_bin_rank<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
-                                                       ctx->max_blocks, st);
+    CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
+                    ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
     tb = ctx->cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->cellcount, ctx->cellstart, ncell, s));
-    k_bin_scatter<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(ctx->keys_a, ctx->vals_a, ctx->fscan, ctx->cellstart, ctx->vals_b, st);
-    k_bin_finish<D><<<gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s>>>(
-        ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr, ctx->gb_key,
-        ctx->max_blocks, st);
+    CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
+                    ctx->fscan, ctx->cellstart, ctx->vals_b, st));
+    CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
+                    ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr,
+                    ctx->gb_key, ctx->max_blocks, st));
     keys = ctx->keys_a;
     perm = ctx->vals_b;
     cellstart = ctx->cellstart;
@@ -632,7 +654,22 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
                                                                               ctx->L, ctx->pb_nbr, st);
     ctx->launches += 7 + (commit_prev ? 1 : 0);
   }
-  k_clear_grid<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s>>>(ctx->grid, st);
+  {
+    // the same pass clears what the next substep of the batch needs zeroed (no memset nodes in the chain)
+    int *z1 = nullptr, *z2 = nullptr, n1 = 0, n2 = 0;
+    if (ctx->dense) {
+      z1 = ctx->cellcount; n1 = ctx->max_blocks * G::CELLS + 1;
+      ctx->cell_zeroed = true;
+      if (fuse_next) {
+        int nlin = 1;
+        for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+        z2 = ctx->flags; n2 = 2 * nlin + 1;
+        ctx->flags_zeroed = true;
+      }
+    }
+    CK(launch_chain(ctx->pdl, k_clear_grid<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s,
+                    ctx->grid, (const Status*)st, z1, n1, z2, n2));
+  }
   if (prof) cudaEventRecord(ev[1], s);
   ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
   SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
@@ -649,9 +686,10 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
 template <int D>
 static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s) {
   using G = Geo<D>;
-  k_grid_op<D><<<gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, ctx->sm_count), 256, 0, s>>>(
-      ctx->grid, ctx->gb_key, ctx->L, ctx->d_ct, ctx->grav, ctx->gcfg, ctx->K.dx, dt,
-      (ctx->K.g2p2g && ctx->K.v_allowed_cfl > 0.f) ? ctx->K.v_allowed_cfl / dt : 0.f, ctx->d_status);
+  CK(launch_chain(ctx->pdl, k_grid_op<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, ctx->sm_count), 256, 0, s,
+                  ctx->grid, (const uint32_t*)ctx->gb_key, ctx->L, (const ColliderTable*)ctx->d_ct, ctx->grav, ctx->gcfg,
+                  ctx->K.dx, dt, (ctx->K.g2p2g && ctx->K.v_allowed_cfl > 0.f) ? ctx->K.v_allowed_cfl / dt : 0.f,
+                  ctx->d_status));
   CK(cudaGetLastError());
   ctx->launches += 1;
   return MPM_OK;
@@ -669,7 +707,8 @@ static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cud
     // another substep of this batch follows with the same key layout: let G2P emit its keys/flags
     int nlin = 1;
     for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
-    CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+    if (!ctx->flags_zeroed) CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+    ctx->flags_zeroed = false;
     a.next_keys = ctx->keys_a; a.next_flags = ctx->flags; a.next_nlin = nlin;
     ctx->keys_ready = true;
   }
@@ -804,9 +843,9 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
 template <int D>
 static int enqueue_substep(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev,
                            bool more_follow = false) {
-  int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, ev);
-  if (rc) return rc;
   const bool fuse = more_follow && ctx->fuse_keys && ctx->dense && !ctx->slab.enabled && !ctx->K.g2p2g;
+  int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, ev, fuse);
+  if (rc) return rc;
   return enqueue_grid_g2p<D>(ctx, dt, cur, s, ev, fuse);
 }
 
@@ -834,6 +873,7 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
     const int cur0 = ctx->cur;
     ctx->keys_ready = false;
+    ctx->cell_zeroed = false; ctx->flags_zeroed = false;
     const bool prof = ctx->profiling && count <= 4096;
     if (prof)
       while ((int)ctx->ev.size() < 5 * count) {

@@ -106,6 +106,7 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
                            int* __restrict__ cellcount, uint32_t* __restrict__ rank, uint32_t* __restrict__ pb_key,
                            int max_blocks, Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   const int n = st->n_cur;
   const int lane = threadIdx.x & 31;
@@ -145,6 +146,7 @@ __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t*
                               const int* __restrict__ fscan, const int* __restrict__ cellstart,
                               uint32_t* __restrict__ perm, const Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   const int n = st->n_cur;
   const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
@@ -167,6 +169,7 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
                              int* __restrict__ pb_start, int* __restrict__ pb_nbr, uint32_t* __restrict__ gb_key,
                              int max_blocks, Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   const int npb = fscan[nlin];
   const int ngb = fscan[2 * nlin] - npb;

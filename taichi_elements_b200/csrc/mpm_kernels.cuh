@@ -36,6 +36,15 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
                : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): every kernel of the substep chain starts with
+// pdl_enter(): wait until the grids it depends on have completed and flushed, then allow the
+// NEXT kernel of the stream to be scheduled into the SM resources this grid frees while its last
+// CTAs drain (that kernel parks in its own pdl_enter()).  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // L2 prefetch of [p, p + bytes): one cp.async.bulk.prefetch (sm_90+) per range
 __device__ __forceinline__ void prefetch_l2_range(const void* p, uint32_t bytes) {
   const unsigned long long a = (unsigned long long)__cvta_generic_to_global(p);
@@ -77,6 +86,7 @@ __global__ void k_batch_begin(Status* st, int n) { st->n_cur = n; st->n_live = n
 // first kernel of a substep whose keys came from the previous G2P: commit that substep, then
 // let the errors its key pass raised take effect
 __global__ void k_substep_begin(Status* st) {
+  pdl_enter();
   if (!st->err) {
     st->done += 1;
     if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
@@ -262,7 +272,14 @@ __global__ void k_nbr(const uint32_t* __restrict__ keys, const int* __restrict__
 }
 
 template <int D>
-__global__ void k_clear_grid(float4* __restrict__ grid, const Status* st) {
+__global__ void k_clear_grid(float4* __restrict__ grid, const Status* st, int* __restrict__ z1, int n1,
+                             int* __restrict__ z2, int n2) {
+  pdl_enter();
+  // tables the NEXT substep of the batch expects zeroed (per-cell counts; block flags when the
+  // coming G2P emits them), so that no memset node sits between the kernels of the chain
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (int i = gtid; i < n1; i += gsz) z1[i] = 0;
+  for (int i = gtid; i < n2; i += gsz) z2[i] = 0;
   if (st->err) return;
   const size_t total = (size_t)st->ngb * Geo<D>::CELLS;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -427,6 +444,7 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
                           const ColliderTable* __restrict__ ct, Grav grav, GridCfg cfg, float dx, float dt,
                           float v_allowed, Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   float gvmax = 0.0f;
   const size_t total = (size_t)st->ngb * G::CELLS;
@@ -540,6 +558,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
   // block's particles are gathered: one CTA barrier per block, no exposed grid-load latency.
   __shared__ float4 tile_buf[2][G::TN];
   __shared__ int s_b;
+  pdl_enter();
   if (a.st->err) return;
   const int npb = a.st->npb;
   const int tid = threadIdx.x;

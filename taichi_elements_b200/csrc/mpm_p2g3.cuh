@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
   __shared__ int s_nbr[G::NO];
   __shared__ int s_b, s_next, s_ticket;
   __shared__ int s_hist[32];
+  pdl_enter();
   if (a.st->err) return;
   const int npb = a.st->npb;
   const int tid = threadIdx.x, lane = tid & 31;
