@@ -294,6 +294,25 @@ template <int D> MPM_HD void usvt(const float* U, const float* s, const float* V
     }
 }
 
+// C = U diag(s) U^T (symmetric)
+template <int D> MPM_HD void udut(const float* U, const float* s, float* C) {
+  float Us[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int k = 0; k < D; ++k) Us[i * D + k] = U[i * D + k] * s[k];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) a += Us[i * D + k] * U[j * D + k];
+      C[i * D + j] = a;
+      C[j * D + i] = a;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // sand_projection (engine/mpm_solver.py:321-342).  sig in/out, Jp in/out.
 // ---------------------------------------------------------------------------
@@ -395,37 +414,36 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
     svd<D>(Fn, U, sig, V);                                   // :525
     if (material != SAND) {
       float J = 1.0f;                                        // :527-536
+      bool clamped = false;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         float ns = sig[d];
         if (material == SNOW) ns = fminf(fmaxf(sig[d], 1.0f - 2.5e-2f), 1.0f + 4.5e-3f);
         if (K.support_plasticity) Jp *= sig[d] / ns;
+        clamped = clamped || (ns != sig[d]);
         sig[d] = ns;
         J *= ns;
       }
-      if (material == SNOW) usvt<D>(U, sig, V, Fn);          // :543-545
-      float R[DD], T[DD];
-      matmul_nt<D>(U, V, R);                                 // U V^T
+      // :543-545 rebuilds F = U sig V^T for every snow particle; without a clamp that is F itself
+      if (material == SNOW && clamped) usvt<D>(U, sig, V, Fn);
+      // :547-551  2 mu (F - U V^T) F^T + la J (J - 1) I with F = U sig V^T:
+      //   (F - R) F^T = U (sig - 1) V^T V sig U^T = U diag(sig (sig - 1)) U^T -- no V, no F - R cancellation
+      const float p = la * J * (J - 1.0f);
+      float dg[D];
 #pragma unroll
-      for (int i = 0; i < DD; ++i) T[i] = 2.0f * mu * (Fn[i] - R[i]);
-      matmul_nt<D>(T, Fn, stress);                           // (..) F^T (:550)
-      float p = la * J * (J - 1.0f);
-#pragma unroll
-      for (int i = 0; i < D; ++i) stress[i * D + i] += p;
+      for (int d = 0; d < D; ++d) dg[d] = 2.0f * mu * sig[d] * (sig[d] - 1.0f) + p;
+      udut<D>(U, dg, stress);
     } else if (K.support_plasticity) {                       // :553-566
       sand_projection<D>(K, sig, Jp);
       usvt<D>(U, sig, V, Fn);
-      float ls[D], center[D], lsum = 0.0f;
+      // center_i = (2 mu_0 log sig_i + lambda_0 sum log sig) / sig_i; U center V^T F^T = U diag(center sig) U^T
+      float ls[D], lsum = 0.0f;
 #pragma unroll
       for (int i = 0; i < D; ++i) { ls[i] = logf(sig[i]); lsum += ls[i]; }
+      float dg[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        float inv = 1.0f / sig[i];
-        center[i] = 2.0f * K.mu_0 * ls[i] * inv + K.lambda_0 * lsum * inv;
-      }
-      float T[DD];
-      usvt<D>(U, center, V, T);
-      matmul_nt<D>(T, Fn, stress);
+      for (int i = 0; i < D; ++i) dg[i] = 2.0f * K.mu_0 * ls[i] + K.lambda_0 * lsum;
+      udut<D>(U, dg, stress);
     } else {
 #pragma unroll
       for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
