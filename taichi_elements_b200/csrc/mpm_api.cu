@@ -684,12 +684,12 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
 }
 
 template <int D>
-static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s) {
+static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s, int* zero = nullptr, int nzero = 0) {
   using G = Geo<D>;
   CK(launch_chain(ctx->pdl, k_grid_op<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, ctx->sm_count), 256, 0, s,
                   ctx->grid, (const uint32_t*)ctx->gb_key, ctx->L, (const ColliderTable*)ctx->d_ct, ctx->grav, ctx->gcfg,
                   ctx->K.dx, dt, (ctx->K.g2p2g && ctx->K.v_allowed_cfl > 0.f) ? ctx->K.v_allowed_cfl / dt : 0.f,
-                  ctx->d_status));
+                  ctx->d_status, zero, nzero));
   CK(cudaGetLastError());
   ctx->launches += 1;
   return MPM_OK;
@@ -700,20 +700,22 @@ static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cud
   const bool prof = ev != nullptr;
   Status* st = ctx->d_status;
   SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
-  int rc = enqueue_grid_op<D>(ctx, dt, s);
+  int nlin = 1;
+  for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+  // flag table for the fused key pass: cleared by k_clear_grid (single GPU) or, with slabs, by the grid op
+  // (k_halo_add still reads this substep's flags after P2G) -- no memset node between the kernels
+  const bool zero_here = fuse_next && !ctx->flags_zeroed;
+  int rc = enqueue_grid_op<D>(ctx, dt, s, zero_here ? ctx->flags : nullptr, zero_here ? 2 * nlin + 1 : 0);
   if (rc) return rc;
   if (prof) cudaEventRecord(ev[3], s);
   if (fuse_next) {
     // another substep of this batch follows with the same key layout: let G2P emit its keys/flags
-    int nlin = 1;
-    for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
-    if (!ctx->flags_zeroed) CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
     ctx->flags_zeroed = false;
     a.next_keys = ctx->keys_a; a.next_flags = ctx->flags; a.next_nlin = nlin;
     ctx->keys_ready = true;
   }
   launch_g2p<D>(ctx, a, s);
-  if (ctx->slab.enabled) { k_mig_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, st); ctx->launches += 1; }
+  if (ctx->slab.enabled) { CK(launch_chain(ctx->pdl, k_mig_headers, 1, 1, 0, s, ctx->comm, (uint32_t)(ctx->epoch + 1), st)); ctx->launches += 1; }
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
   ctx->launches += 1;   // g2p
@@ -1004,6 +1006,7 @@ extern "C" int mpm_batch_begin(mpm_ctx* ctx, void* stream) {
   ctx->in_batch = true;
   ctx->batch_cur0 = ctx->cur;
   ctx->batch_enq = 0;
+  ctx->keys_ready = false; ctx->cell_zeroed = false; ctx->flags_zeroed = false;
   return MPM_OK;
 }
 
@@ -1018,13 +1021,19 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
   if (!from_lo && !from_hi) return MPM_OK;
   const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
   const int blocks = gs_blocks((int64_t)ctx->comm.mig_cap * ctx->nf, 256, ctx->sm_count);
+  // the last G2P emitted the coming substep's keys and flags: the appended rows need theirs too
+  uint32_t* keys = ctx->keys_ready ? ctx->keys_a : nullptr;
+  int nlin = 1;
+  for (int d = 0; d < ctx->dim; ++d) nlin *= ctx->L.eb[d];
   if (ctx->dim == 3)
-    k_mig_unpack<3><<<blocks, 256, 0, s>>>(ctx->state[cur], ctx->cap, (const uint32_t*)from_lo, (const uint32_t*)from_hi,
-                                           ctx->comm.mig_cap, ctx->d_status);
+    CK(launch_chain(ctx->pdl, k_mig_unpack<3>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (const uint32_t*)from_lo,
+                    (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
+                    ctx->K.inv_dx));
   else
-    k_mig_unpack<2><<<blocks, 256, 0, s>>>(ctx->state[cur], ctx->cap, (const uint32_t*)from_lo, (const uint32_t*)from_hi,
-                                           ctx->comm.mig_cap, ctx->d_status);
-  k_mig_commit<<<1, 1, 0, s>>>((uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status);
+    CK(launch_chain(ctx->pdl, k_mig_unpack<2>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (const uint32_t*)from_lo,
+                    (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
+                    ctx->K.inv_dx));
+  CK(launch_chain(ctx->pdl, k_mig_commit, 1, 1, 0, s, (uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status));
   CK(cudaGetLastError());
   ctx->launches += 2;
   return MPM_OK;
@@ -1045,12 +1054,14 @@ extern "C" int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream) {
     if (!ctx->comm.halo[side]) continue;
     const int bx = side == 0 ? ctx->slab.lo : ctx->slab.hi;
     if (ctx->dim == 3)
-      k_halo_pack<3><<<blocks, 256, 0, s>>>(ctx->grid, ctx->gb_key, ctx->L, bx, ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status);
+      CK(launch_chain(ctx->pdl, k_halo_pack<3>, blocks, 256, 0, s, (const float4*)ctx->grid, (const uint32_t*)ctx->gb_key, ctx->L, bx,
+                      ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status));
     else
-      k_halo_pack<2><<<blocks, 256, 0, s>>>(ctx->grid, ctx->gb_key, ctx->L, bx, ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status);
+      CK(launch_chain(ctx->pdl, k_halo_pack<2>, blocks, 256, 0, s, (const float4*)ctx->grid, (const uint32_t*)ctx->gb_key, ctx->L, bx,
+                      ctx->comm.halo[side], ctx->comm.halo_cap, side, ctx->d_status));
     ctx->launches += 1;
   }
-  k_halo_headers<<<1, 1, 0, s>>>(ctx->comm, ctx->epoch + 1, ctx->d_status);
+  CK(launch_chain(ctx->pdl, k_halo_headers, 1, 1, 0, s, ctx->comm, (uint32_t)(ctx->epoch + 1), ctx->d_status));
   ctx->launches += 1;
   CK(cudaGetLastError());
   return MPM_OK;
@@ -1067,9 +1078,11 @@ extern "C" int mpm_phase_halo_add(mpm_ctx* ctx, const void* from_lo, const void*
     if (!from[side]) continue;
     const int bx = side == 0 ? ctx->slab.lo : ctx->slab.hi;
     if (ctx->dim == 3)
-      k_halo_add<3><<<blocks, 256, 0, s>>>(ctx->grid, ctx->flags, ctx->fscan, nlin, ctx->L, bx, (const uint32_t*)from[side], ctx->comm.halo_cap, ctx->d_status);
+      CK(launch_chain(ctx->pdl, k_halo_add<3>, blocks, 256, 0, s, ctx->grid, (const int*)ctx->flags, (const int*)ctx->fscan, nlin, ctx->L, bx,
+                      (const uint32_t*)from[side], ctx->comm.halo_cap, (const Status*)ctx->d_status));
     else
-      k_halo_add<2><<<blocks, 256, 0, s>>>(ctx->grid, ctx->flags, ctx->fscan, nlin, ctx->L, bx, (const uint32_t*)from[side], ctx->comm.halo_cap, ctx->d_status);
+      CK(launch_chain(ctx->pdl, k_halo_add<2>, blocks, 256, 0, s, ctx->grid, (const int*)ctx->flags, (const int*)ctx->fscan, nlin, ctx->L, bx,
+                      (const uint32_t*)from[side], ctx->comm.halo_cap, (const Status*)ctx->d_status));
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
@@ -1079,8 +1092,11 @@ extern "C" int mpm_phase_halo_add(mpm_ctx* ctx, const void* from_lo, const void*
 extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
   REQUIRE_BATCH();
   const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
-  int rc = ctx->dim == 3 ? enqueue_grid_g2p<3>(ctx, (float)dt, cur, s, nullptr)
-                         : enqueue_grid_g2p<2>(ctx, (float)dt, cur, s, nullptr);
+  // the key pass of the next substep of this batch rides on G2P (its layout box is fixed for the batch);
+  // if no substep follows the keys are simply not used
+  const bool fuse = ctx->fuse_keys && ctx->dense && !ctx->K.g2p2g;
+  int rc = ctx->dim == 3 ? enqueue_grid_g2p<3>(ctx, (float)dt, cur, s, nullptr, fuse)
+                         : enqueue_grid_g2p<2>(ctx, (float)dt, cur, s, nullptr, fuse);
   if (rc) return rc;
   ctx->batch_enq += 1;
   return MPM_OK;
@@ -1187,7 +1203,8 @@ extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t
   const int n_iter = deliver_only ? 1 : count;
   for (int i = 0; i < n_iter; ++i) {
     // leavers of the neighbours' last G2P (epoch = substeps completed so far)
-    k_wait_flags<<<1, 1, 0, s>>>(has[0] ? me + 0 : nullptr, has[1] ? me + 1 : nullptr, ctx->epoch, ctx->d_status);
+    CK(launch_chain(ctx->pdl, k_wait_flags, 1, 1, 0, s, (const uint32_t*)(has[0] ? me + 0 : nullptr),
+                    (const uint32_t*)(has[1] ? me + 1 : nullptr), (uint32_t)ctx->epoch, ctx->d_status));
     ctx->launches += 1;
     int rc = mpm_phase_unpack(ctx, mig_from[0], mig_from[1], stream);
     if (rc) return rc;
@@ -1196,7 +1213,8 @@ extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t
     if (rc) return rc;
     rc = mpm_phase_halo_pack(ctx, stream);          // records + epoch go straight to the neighbours
     if (rc) return rc;
-    k_wait_flags<<<1, 1, 0, s>>>(has[0] ? me + 2 : nullptr, has[1] ? me + 3 : nullptr, ctx->epoch + 1, ctx->d_status);
+    CK(launch_chain(ctx->pdl, k_wait_flags, 1, 1, 0, s, (const uint32_t*)(has[0] ? me + 2 : nullptr),
+                    (const uint32_t*)(has[1] ? me + 3 : nullptr), (uint32_t)(ctx->epoch + 1), ctx->d_status));
     ctx->launches += 1;
     rc = mpm_phase_halo_add(ctx, halo_from[0], halo_from[1], stream);
     if (rc) return rc;

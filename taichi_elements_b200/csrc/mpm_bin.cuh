@@ -119,7 +119,8 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
     uint32_t rr[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t key = kk[j];
+      // rows past n in the last quad hold stale keys when the keys came from G2P / the unpack pass
+      const uint32_t key = 4u * t + j < (uint32_t)n ? kk[j] : INVALID_KEY;
       uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
       if (key != INVALID_KEY) {
         lin = key >> G::CB;
@@ -156,7 +157,7 @@ __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t*
     const uint32_t kk[4] = {kq.x, kq.y, kq.z, kq.w}, rr[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (kk[j] == INVALID_KEY) continue;
+      if (kk[j] == INVALID_KEY || 4u * t + j >= (uint32_t)n) continue;
       const int b = fscan[kk[j] >> G::CB];
       perm[cellstart[(size_t)b * G::CELLS + (kk[j] & (G::CELLS - 1))] + rr[j]] = 4u * t + j;
     }

@@ -29,6 +29,7 @@ template <int D>
 __global__ void k_halo_pack(const float4* __restrict__ grid, const uint32_t* __restrict__ gb_key, KeyLayout L,
                             int bx_abs, uint32_t* __restrict__ buf, int halo_cap, int side, Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -55,6 +56,7 @@ __global__ void k_halo_add(float4* __restrict__ grid, const int* __restrict__ fl
                            int nlin, KeyLayout L, int bx_abs, const uint32_t* __restrict__ buf, int halo_cap,
                            const Status* st) {
   using G = Geo<D>;
+  pdl_enter();
   if (st->err) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -102,6 +104,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // one thread: wait until both neighbours have published `epoch` (null = no neighbour)
 __global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t epoch, Status* st) {
+  pdl_enter();
   const unsigned long long t0 = global_ns();
   const uint32_t* f[2] = {f0, f1};
   for (int s = 0; s < 2; ++s) {
@@ -116,6 +119,7 @@ __global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t ep
 // message headers (one thread): counts, overflow detection, and (peer path) the signal.
 // They run even after a device error so that a neighbour never waits for ever.
 __global__ void k_halo_headers(CommBufs cb, uint32_t epoch, Status* st) {
+  pdl_enter();
   for (int s = 0; s < 2; ++s) {
     if (!cb.halo[s]) continue;
     int c = st->err ? 0 : st->halo_cnt[s];
@@ -125,6 +129,7 @@ __global__ void k_halo_headers(CommBufs cb, uint32_t epoch, Status* st) {
   }
 }
 __global__ void k_mig_headers(CommBufs cb, uint32_t epoch, Status* st) {
+  pdl_enter();
   for (int s = 0; s < 2; ++s) {
     if (!cb.mig[s]) continue;
     int c = st->err ? 0 : st->mig_cnt[s];
@@ -135,11 +140,17 @@ __global__ void k_mig_headers(CommBufs cb, uint32_t epoch, Status* st) {
   if (!st->err) st->n_cur = st->n_live;    // rows of the set G2P just wrote
 }
 
-// append the particles received from the -x and +x neighbours to the live set
+// append the particles received from the -x and +x neighbours to the live set; when the last
+// G2P already emitted the coming substep's sort keys and block flags (fused key pass), do the
+// same for the appended rows (same arithmetic as k_bin_keys)
 template <int D>
 __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uint32_t* __restrict__ from_lo,
-                             const uint32_t* __restrict__ from_hi, int mig_cap, Status* st) {
+                             const uint32_t* __restrict__ from_hi, int mig_cap, Status* st,
+                             uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, KeyLayout L, Slab slab,
+                             float inv_dx) {
+  using G = Geo<D>;
   constexpr int NF = Fld<D>::N;
+  pdl_enter();
   if (st->err) return;
   const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
   const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
@@ -155,8 +166,35 @@ __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uin
                               : from_hi[COMM_HEADER + (size_t)f * mig_cap + (r - c0)];
     state[(size_t)f * cap + base + r] = v;
   }
+  if (!keys) return;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < c0 + c1; r += gridDim.x * blockDim.x) {
+    uint32_t lin = 0, cell = 0, sp = 0;
+    bool bad = false, mine = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const uint32_t w = r < c0 ? from_lo[COMM_HEADER + (size_t)(Fld<D>::X + d) * mig_cap + r]
+                                : from_hi[COMM_HEADER + (size_t)(Fld<D>::X + d) * mig_cap + (r - c0)];
+      const int g = base_index(__uint_as_float(w), inv_dx) + L.half;
+      if (d == 0 && slab.enabled) { const int bx = g >> G::LOG_LEAF; mine = bx >= slab.lo && bx < slab.hi; }
+      int rel = (g >> G::LOG_LEAF) - L.ob[d];
+      if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
+      lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
+      const uint32_t lc = (uint32_t)(g & (G::LEAF - 1));
+      cell = (cell << G::LOG_LEAF) | lc;
+      sp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
+    }
+    keys[base + r] = mine ? ((lin << G::CB) | cell) : INVALID_KEY;
+    if (mine && bad) { atomicOr(&st->next_err, ERR_BBOX); mine = false; }
+    if (!mine) continue;
+    flags[lin] = 1;
+    int* gf = flags + nlin;
+#pragma unroll
+    for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
+      if ((o & ~sp) == 0) gf[(int)lin + oct_delta_l<D>(L, (int)o)] = 1;
+  }
 }
 __global__ void k_mig_commit(uint32_t* from_lo, uint32_t* from_hi, int mig_cap, Status* st) {
+  pdl_enter();
   if (st->err) return;
   const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
   const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;

@@ -442,9 +442,11 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
 template <int D>
 __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict__ gb_key, KeyLayout L,
                           const ColliderTable* __restrict__ ct, Grav grav, GridCfg cfg, float dx, float dt,
-                          float v_allowed, Status* st) {
+                          float v_allowed, Status* st, int* __restrict__ zero, int nzero) {
   using G = Geo<D>;
   pdl_enter();
+  // (slab runs) the block-flag table the coming G2P fills for the next substep
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;
   if (st->err) return;
   float gvmax = 0.0f;
   const size_t total = (size_t)st->ngb * G::CELLS;
@@ -799,7 +801,16 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         ncell = (ncell << G::LOG_LEAF) | lc;
         nsp |= (lc >= (uint32_t)(G::LEAF - 2)) ? (1u << d) : 0u;
       }
-      if (a.next_keys) {
+      // slab decomposition: a particle whose new base block left this rank's columns is handed to the
+      // neighbour below and dropped from the local sort (same rule as k_bin_keys)
+      bool leaver = false;
+      if (a.slab.enabled) {
+        const int nbx = (base_index(x[0], a.K.inv_dx) + a.L.half) >> G::LOG_LEAF;
+        leaver = nbx < a.slab.lo || nbx >= a.slab.hi;
+      }
+      if (a.next_keys && leaver) {
+        a.next_keys[s] = INVALID_KEY;
+      } else if (a.next_keys) {
         a.next_keys[s] = (nlin_key << G::CB) | ncell;
         if (nbad) {
           atomicOr(&a.st->next_err, ERR_BBOX);
