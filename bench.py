@@ -366,7 +366,7 @@ def main():
                        'particles_per_gpu': n_local, 'l2': 'inputs (2 x 116 B x N particle state) exceed L2',
                        'active_blocks': int(st.n_grid_blocks), 'particle_blocks': int(st.n_particle_blocks)},
             'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches,
-            'gpu_launches_note': 'own kernels only (8 per substep + 1 per batch; more with slabs); CUB scan launches not counted',
+            'gpu_launches_note': 'own kernels: 9 per substep inside a batch (scan, rank, scan, scatter, finish, clear, p2g, grid op, g2p), 10 for its first substep, + 2 per batch; more with slabs',
             'roofline': roofline, 'cpu_baseline': cpu,
         }
         print(json.dumps(line))

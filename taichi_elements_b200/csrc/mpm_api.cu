@@ -33,6 +33,9 @@ struct mpm_ctx {
   ColliderTable* d_ct = nullptr;
   uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *stage = nullptr;
   void* cub_temp = nullptr;
+  unsigned long long* scan_desc = nullptr;   // tile descriptors of k_scan_excl
+  uint32_t scan_epoch = 0;
+  int own_scan = 1, scan_grid = 0;
   size_t cub_bytes = 0;
   int* pb_start = nullptr;
   uint32_t* pb_mask = nullptr;
@@ -134,8 +137,8 @@ static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, in
 // ------------------------------------------------------------------ sizes
 struct Carve {
   size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
-      off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, total,
-      cub_bytes;
+      off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, off_scan_desc, total,
+      cub_bytes, scan_tiles;
   int64_t table_cap;
 };
 
@@ -173,6 +176,8 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.table_cap = table_capacity(max_blocks);
   c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks, std::max<int64_t>(c.table_cap, (int64_t)max_blocks * cells + 1));
   c.off_cub = take(c.cub_bytes);
+  c.scan_tiles = (size_t)(std::max<int64_t>(c.table_cap, (int64_t)max_blocks * cells + 1) / SCAN_TILE + 2);
+  c.off_scan_desc = take(c.scan_tiles * 8);
   c.off_pb_start = take((size_t)(max_blocks + 2) * 4);
   c.off_pb_mask = take((size_t)max_blocks * 4);
   c.off_pb_nbr = take((size_t)max_blocks * no * 4);
@@ -253,6 +258,12 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
+  if (const char* v = getenv("MPM_SCAN")) ctx->own_scan = strcmp(v, "cub") != 0;
+  {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_excl<true>, SCAN_T, 0);
+    ctx->scan_grid = ctx->sm_count * std::max(1, std::min(occ, 4));
+  }
   if (const char* v = getenv("MPM_G2P_CFG")) ctx->g2p_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G")) ctx->p2g_variant = (strcmp(v, "atomic") == 0) ? 0 : 1;
   *out = ctx;
@@ -294,6 +305,9 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->keys_a = sc; ctx->keys_b = sc + capacity; ctx->vals_a = sc + 2 * capacity;
   ctx->vals_b = sc + 3 * capacity; ctx->stage = sc + 4 * capacity;
   ctx->cub_temp = b + c.off_cub;
+  ctx->scan_desc = (unsigned long long*)(b + c.off_scan_desc);
+  cudaMemsetAsync(ctx->scan_desc, 0, c.scan_tiles * 8, 0);   // epoch 0 = never valid
+  cudaStreamSynchronize(0);
   ctx->cub_bytes = c.cub_bytes;
   ctx->pb_start = (int*)(b + c.off_pb_start);
   ctx->pb_mask = (uint32_t*)(b + c.off_pb_mask);
@@ -581,6 +595,23 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   return a;
 }
 
+// exclusive scan of n ints: one k_scan_excl launch (optionally committing the previous substep), or CUB
+static int enqueue_scan(mpm_ctx* ctx, const int* in, int* out, int n, bool commit, cudaStream_t s) {
+  // above a few tiles per resident CTA the look-back chain costs more than CUB's second launch
+  if (ctx->own_scan && n <= ctx->scan_grid * 4 * SCAN_TILE) {
+    ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x3fffffffu;
+    if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
+    const int grid = std::max(1, std::min(ctx->scan_grid, (n + SCAN_TILE - 1) / SCAN_TILE));
+    if (commit) CK(launch_chain(ctx->pdl, k_scan_excl<true>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
+    else CK(launch_chain(ctx->pdl, k_scan_excl<false>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
+    return MPM_OK;
+  }
+  if (commit) CK(launch_chain(ctx->pdl, k_substep_begin, 1, 1, 0, s, ctx->d_status));
+  size_t tb = ctx->cub_bytes;
+  CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, in, out, n, s));
+  return MPM_OK;
+}
+
 template <int D>
 static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s, cudaEvent_t* ev,
                            bool fuse_next = false) {
@@ -602,21 +633,18 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     const int ncell = ctx->max_blocks * G::CELLS + 1;
     if (!ctx->cell_zeroed) CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
     ctx->cell_zeroed = false;
-    if (ctx->keys_ready) {
-      // keys and flags were written by the previous substep's G2P (mpm_kernels.cuh, next_keys)
-      CK(launch_chain(ctx->pdl, k_substep_begin, 1, 1, 0, s, st));
-    } else {
+    const bool fused_keys = ctx->keys_ready;   // keys and flags were written by the previous substep's G2P
+    if (!fused_keys) {
       CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
       k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
                                                          nlin, commit_prev, st);
     }
     ctx->keys_ready = false;
-    tb = ctx->cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->flags, ctx->fscan, 2 * nlin + 1, s));
+    // (a substep whose keys came from G2P is committed by the scan's first thread)
+    { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, fused_keys, s); if (rc) return rc; }
     CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
                     ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
-    tb = ctx->cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, ctx->cellcount, ctx->cellstart, ncell, s));
+    { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s); if (rc) return rc; }
     CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
                     ctx->fscan, ctx->cellstart, ctx->vals_b, st));
     CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
@@ -625,7 +653,8 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     keys = ctx->keys_a;
     perm = ctx->vals_b;
     cellstart = ctx->cellstart;
-    ctx->launches += 4;
+    // own kernels: [keys | commit] rank scatter finish, plus the two scans when they are ours (CUB's are not counted)
+    ctx->launches += ctx->own_scan ? (fused_keys ? 5 : 6) : 4;   // (large tables: a scan may still go to CUB)
   } else {
     // ---- fallback: multi-pass LSD radix sort + sorted-candidate block list
     if (commit_prev) k_end<<<1, 1, 0, s>>>(st);

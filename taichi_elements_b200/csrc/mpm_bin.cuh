@@ -101,6 +101,121 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
   }
 }
 
+// ---------------------------------------------------------------------------
+// Exclusive prefix sum of n ints in ONE launch (replaces cub::DeviceScan's init + scan pair, and
+// takes part in the programmatic-dependent-launch chain): decoupled look-back over 2048-item
+// tiles.  A tile descriptor is {epoch:30 | status:2 | value:32}; the epoch changes with every
+// launch, so descriptors of earlier launches read as "not ready" and are never cleared.  The grid
+// is persistent and no larger than what is co-resident; every CTA takes its tiles in increasing
+// order, so the predecessors a look-back waits for are always being worked on.
+// COMMIT: thread 0 first commits the previous substep (k_substep_begin folded in).
+// ---------------------------------------------------------------------------
+static constexpr int SCAN_T = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_T * SCAN_IPT;
+__device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <bool COMMIT>
+__global__ void __launch_bounds__(SCAN_T) k_scan_excl(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                     unsigned long long* __restrict__ desc, uint32_t epoch,
+                                                     Status* st) {
+  pdl_enter();
+  if (COMMIT && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!st->err) {
+      st->done += 1;
+      if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
+    }
+    st->err |= st->next_err;
+    st->next_err = 0;
+  }
+  __shared__ int s_warp[SCAN_T / 32];
+  __shared__ int s_excl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  const unsigned long long tag = (unsigned long long)(epoch & 0x3fffffffu) << 34;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * SCAN_TILE + tid * SCAN_IPT;
+    int v[SCAN_IPT];
+    if (base + SCAN_IPT <= n) {
+      const int4 a = __ldg(reinterpret_cast<const int4*>(in + base)), b = __ldg(reinterpret_cast<const int4*>(in + base) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < SCAN_IPT; ++i) v[i] = base + i < n ? in[base + i] : 0;
+    }
+    int tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) tsum += v[i];
+    int incl = tsum;                                        // inclusive scan of the thread sums in the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = lane < SCAN_T / 32 ? s_warp[lane] : 0;
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < SCAN_T / 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      const int agg = __shfl_sync(0xffffffffu, wi, SCAN_T / 32 - 1);
+      if (lane < SCAN_T / 32) s_warp[lane] = wi - w;        // exclusive prefix of each warp inside the tile
+      int excl = 0;
+      if (tile == 0) {
+        if (lane == 0) scan_st(desc, tag | (2ull << 32) | (unsigned)agg);
+      } else {
+        if (lane == 0) scan_st(desc + tile, tag | (1ull << 32) | (unsigned)agg);
+        int t = tile - 1;
+        unsigned spins = 0;
+        while (true) {
+          const int idx = t - lane;
+          unsigned long long d = tag | (2ull << 32);        // before tile 0: prefix 0
+          if (idx >= 0) d = scan_ld(desc + idx);
+          const bool ready = (d >> 34) == (tag >> 34) && ((d >> 32) & 3ull) != 0ull;
+          if (!__all_sync(0xffffffffu, ready)) {
+            if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&st->err, ERR_SCAN_TIMEOUT); break; }   // never hang
+            continue;
+          }
+          const unsigned pref = __ballot_sync(0xffffffffu, ((d >> 32) & 3ull) == 2ull);
+          const int last = pref ? __ffs(pref) - 1 : 31;     // nearest tile whose inclusive prefix is known
+          int val = lane <= last ? (int)(unsigned)(d & 0xffffffffull) : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+          excl += val;
+          if (pref) break;
+          t -= 32;
+        }
+        if (lane == 0) scan_st(desc + tile, tag | (2ull << 32) | (unsigned)(excl + agg));
+      }
+      if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    int run = s_excl + s_warp[wid] + (incl - tsum);
+    if (base + SCAN_IPT <= n) {
+      int o[SCAN_IPT];
+#pragma unroll
+      for (int i = 0; i < SCAN_IPT; ++i) { o[i] = run; run += v[i]; }
+      reinterpret_cast<int4*>(out + base)[0] = make_int4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<int4*>(out + base)[1] = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < SCAN_IPT; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int D>
 __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restrict__ fscan,
                            int* __restrict__ cellcount, uint32_t* __restrict__ rank, uint32_t* __restrict__ pb_key,

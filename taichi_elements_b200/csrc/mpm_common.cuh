@@ -41,7 +41,7 @@ struct KeyLayout {
   int key_bits;
 };
 
-enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2, ERR_COMM_CAPACITY = 4, ERR_PARTICLE_CAPACITY = 8, ERR_COMM_TIMEOUT = 16 };
+enum ErrBits { ERR_BLOCK_CAPACITY = 1, ERR_BBOX = 2, ERR_COMM_CAPACITY = 4, ERR_PARTICLE_CAPACITY = 8, ERR_COMM_TIMEOUT = 16, ERR_SCAN_TIMEOUT = 32 };
 
 // Device-resident status block, copied to pinned host memory after each batch.
 struct Status {
