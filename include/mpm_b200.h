@@ -240,6 +240,9 @@ int mpm_voxel_sample(int32_t device, const int32_t* voxels_dev, const int32_t* r
 /* build_pid result: per particle (insertion order) the leaf-block coordinate
  * (base - offset) // leaf, int32 [n][dim] to host. */
 int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream);
+/* the binning's single-launch exclusive prefix sum (k_scan_excl) on caller data, device pointers:
+ * out[i] = in[0] + ... + in[i-1]; n is bounded by the bound workspace (tests) */
+int mpm_debug_scan(mpm_ctx* ctx, const int32_t* in_dev, int32_t* out_dev, int64_t n, void* stream);
 /* Structure of the LAST substep: particle blocks (coords [npb][dim], counts[npb])
  * and grid (active) blocks (coords [ngb][dim]); arrays may be NULL to query sizes. */
 int mpm_debug_blocks(mpm_ctx* ctx, int32_t* pb_coords_host, int32_t* pb_counts_host, int32_t* npb,

@@ -107,6 +107,7 @@ SYMBOLS = [
     ('mpm_voxelize', _i32, [_i32, _vp, _i64, _vp, _dbl, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_voxel_sample', _i32, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dp, _i32, _i32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_debug_binning', _i32, [_vp, _vp, _vp]),
+    ('mpm_debug_scan', _i32, [_vp, _vp, _vp, _i64, _vp]),
     ('mpm_debug_blocks', _i32, [_vp, _vp, _vp, ctypes.POINTER(_i32), _vp, ctypes.POINTER(_i32)]),
     ('mpm_debug_grid', _i32, [_vp, _vp, _vp, _i64, ctypes.POINTER(_i64)]),
     ('mpm_debug_particle_update', _i32, [_vp, _dbl, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

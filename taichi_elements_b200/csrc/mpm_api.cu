@@ -34,6 +34,7 @@ struct mpm_ctx {
   uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *stage = nullptr;
   void* cub_temp = nullptr;
   unsigned long long* scan_desc = nullptr;   // tile descriptors of k_scan_excl
+  size_t scan_tiles = 0;
   uint32_t scan_epoch = 0;
   int own_scan = 1, scan_grid = 0;
   size_t cub_bytes = 0;
@@ -306,6 +307,7 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->vals_b = sc + 3 * capacity; ctx->stage = sc + 4 * capacity;
   ctx->cub_temp = b + c.off_cub;
   ctx->scan_desc = (unsigned long long*)(b + c.off_scan_desc);
+  ctx->scan_tiles = c.scan_tiles;
   cudaMemsetAsync(ctx->scan_desc, 0, c.scan_tiles * 8, 0);   // epoch 0 = never valid
   cudaStreamSynchronize(0);
   ctx->cub_bytes = c.cub_bytes;
@@ -1429,6 +1431,21 @@ extern "C" int mpm_voxel_sample(int32_t device, const int32_t* vox, const int32_
 }
 
 // ------------------------------------------------------------------ debug
+// the binning's single-launch exclusive scan on caller data (parity tests): out[i] = sum(in[0..i))
+extern "C" int mpm_debug_scan(mpm_ctx* ctx, const int32_t* in_dev, int32_t* out_dev, int64_t n, void* stream) {
+  if (!ctx || !in_dev || !out_dev || n < 1) return MPM_E_INVALID;
+  if (!ctx->scan_desc) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  if ((n + SCAN_TILE - 1) / SCAN_TILE + 1 > (int64_t)ctx->scan_tiles) return fail(ctx, MPM_E_INVALID, "mpm_debug_scan: n exceeds the bound workspace");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x3fffffffu;
+  if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->scan_grid, (n + SCAN_TILE - 1) / SCAN_TILE));
+  CK(launch_chain(ctx->pdl, k_scan_excl<false>, grid, SCAN_T, 0, s, (const int*)in_dev, (int*)out_dev, (int)n,
+                  ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
+  return MPM_OK;
+}
+
 extern "C" int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream) {
   if (!ctx || !block_host) return MPM_E_INVALID;
   if (ctx->n == 0) return MPM_OK;

@@ -64,6 +64,43 @@ def test_reference_scene_test_2d():
     assert p['position'].shape == (5 * 5, 2) and np.isfinite(p['position']).all()
 
 
+def test_config0_demo_2d_against_oracle():
+    """BASELINE configs[0] = demo/demo_2d.py:28-45 of the reference (res 128, three ELASTIC cubes, a SAND
+    jet every frame, a WATER sheet from frame 11), 30 frames x 53 substeps through MPMSolver.step against
+    the NumPy oracle fed the same seeded particles: cubes in free fall, jet and sheet landing on them."""
+    from oracle.mpm_oracle import OracleMPM
+    s = _solver(res=(128, 128))
+    o = OracleMPM((128, 128))
+    seen = [0]
+
+    def mirror(material, velocity=None):
+        pos = s.particle_info()['position']
+        o.add_particles(pos[seen[0]:], material, velocity=velocity)
+        seen[0] = len(pos)
+
+    for i in range(3):
+        s.add_cube(lower_corner=[0.2 + i * 0.1, 0.3 + i * 0.1], cube_size=[0.1, 0.1], material=s.material_elastic)
+        mirror(1)
+    assert seen[0] == 3 * 656                      # SURVEY 8(d) cfg 1
+    for frame in range(30):
+        s.step(8e-3)
+        o.step(8e-3)
+        s.add_cube(lower_corner=[0.1, 0.8], cube_size=[0.01, 0.05], velocity=[1, 0], material=s.material_sand)
+        mirror(3, [1, 0])
+        if 10 < frame < 100:
+            vel = [math.sin(frame * 0.1), 0]
+            s.add_cube(lower_corner=[0.6, 0.7], cube_size=[0.2, 0.01], material=s.material_water, velocity=vel)
+            mirror(0, vel)
+    assert s.total_substeps == o.total_substeps == 30 * 53      # App. C-1: int(8e-3 / dt) + 1
+    s.step(8e-3)
+    o.step(8e-3)
+    p = s.particle_info()
+    assert len(p['position']) == len(o.x) == 3 * 656 + 30 * 33 + 19 * 132
+    assert np.array_equal(p['material'], o.material)
+    assert np.abs(p['position'] - o.x).max() < 1e-4              # measured 2e-6 after 1643 substeps
+    assert np.abs(p['velocity'] - o.v).max() < 5e-3 * max(1.0, np.abs(o.v).max())   # measured 1e-4 of max |v|
+
+
 def test_reference_scene_test_3d_against_oracle():
     """tests/test_3d.py:9-22: snow ball + elastic bar, size=10, g=(0,-50,0); same particles
     injected into the oracle."""

@@ -157,3 +157,32 @@ def test_kernel_variants_agree():
         scale = max(1.0, float(np.abs(base['v']).max()))
         assert np.abs(base['v'] - alt['v']).max() <= 1e-3 * scale
         assert np.abs(base['x'] - alt['x']).max() <= 1e-5
+
+
+def test_single_launch_scan_matches_cumsum():
+    """k_scan_excl (decoupled look-back, one launch) against NumPy on sizes around the tile (2048)
+    and look-back window (32 tiles) boundaries, zeros, and repeated launches on the same
+    descriptors (the epoch tag must make stale descriptors invisible)."""
+    import torch
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    s = MPMSolver((32, 32, 32), device=0)
+    for p, m, vel in mixed_scene(3, n_per=200, seed=3):
+        s.add_particles(p, m, velocity=vel)
+    s._run_substeps(s.default_dt, 1)           # binds the workspace
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 2047, 2048, 2049, 4096, 65535, 65536, 65537, 200001):
+        for rep in range(2):
+            a = rng.integers(0, 9, n).astype(np.int32) if rep == 0 else np.zeros(n, np.int32)
+            if rep == 1 and n > 3:
+                a[n // 2] = 5
+            d_in = torch.from_numpy(a).cuda()
+            d_out = torch.full((n, ), -1, dtype=torch.int32, device='cuda')
+            rc = s._lib.mpm_debug_scan(s._ctx, d_in.data_ptr(), d_out.data_ptr(), n, s._stream())
+            if rc != 0:
+                assert n > 65536, s._lib.mpm_last_error(s._ctx)   # larger than this small workspace allows
+                continue
+            torch.cuda.synchronize()
+            want = np.concatenate([[0], np.cumsum(a[:-1], dtype=np.int64)]).astype(np.int32)
+            assert np.array_equal(d_out.cpu().numpy(), want), n
+    st = s._run_substeps(s.default_dt, 2)      # the solver still works on the same descriptors
+    assert st.substeps_done == 2
