@@ -599,8 +599,8 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
 
 // exclusive scan of n ints: one k_scan_excl launch (optionally committing the previous substep), or CUB
 static int enqueue_scan(mpm_ctx* ctx, const int* in, int* out, int n, bool commit, cudaStream_t s) {
-  // above a few tiles per resident CTA the look-back chain costs more than CUB's second launch
-  if (ctx->own_scan && n <= ctx->scan_grid * 4 * SCAN_TILE) {
+  // the prefix travels one 32-tile window per hop: beyond ~8 hops the chain costs more than CUB's second launch
+  if (ctx->own_scan && n <= 256 * SCAN_TILE) {
     ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x3fffffffu;
     if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
     const int grid = std::max(1, std::min(ctx->scan_grid, (n + SCAN_TILE - 1) / SCAN_TILE));

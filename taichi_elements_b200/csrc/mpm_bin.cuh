@@ -103,14 +103,14 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
 
 // ---------------------------------------------------------------------------
 // Exclusive prefix sum of n ints in ONE launch (replaces cub::DeviceScan's init + scan pair, and
-// takes part in the programmatic-dependent-launch chain): decoupled look-back over 2048-item
+// takes part in the programmatic-dependent-launch chain): decoupled look-back over 8192-item
 // tiles.  A tile descriptor is {epoch:30 | status:2 | value:32}; the epoch changes with every
 // launch, so descriptors of earlier launches read as "not ready" and are never cleared.  The grid
 // is persistent and no larger than what is co-resident; every CTA takes its tiles in increasing
 // order, so the predecessors a look-back waits for are always being worked on.
 // COMMIT: thread 0 first commits the previous substep (k_substep_begin folded in).
 // ---------------------------------------------------------------------------
-static constexpr int SCAN_T = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_T * SCAN_IPT;
+static constexpr int SCAN_T = 512, SCAN_IPT = 16, SCAN_TILE = SCAN_T * SCAN_IPT;   // 8192-item tiles: few look-back hops
 __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -141,8 +141,11 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_excl(const int* __restrict__ in
     const int base = tile * SCAN_TILE + tid * SCAN_IPT;
     int v[SCAN_IPT];
     if (base + SCAN_IPT <= n) {
-      const int4 a = __ldg(reinterpret_cast<const int4*>(in + base)), b = __ldg(reinterpret_cast<const int4*>(in + base) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+      for (int q = 0; q < SCAN_IPT / 4; ++q) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(in + base) + q);
+        v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < SCAN_IPT; ++i) v[i] = base + i < n ? in[base + i] : 0;
@@ -203,8 +206,9 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_excl(const int* __restrict__ in
       int o[SCAN_IPT];
 #pragma unroll
       for (int i = 0; i < SCAN_IPT; ++i) { o[i] = run; run += v[i]; }
-      reinterpret_cast<int4*>(out + base)[0] = make_int4(o[0], o[1], o[2], o[3]);
-      reinterpret_cast<int4*>(out + base)[1] = make_int4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+      for (int q = 0; q < SCAN_IPT / 4; ++q)
+        reinterpret_cast<int4*>(out + base)[q] = make_int4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     } else {
 #pragma unroll
       for (int i = 0; i < SCAN_IPT; ++i) {

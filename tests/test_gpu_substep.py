@@ -160,7 +160,7 @@ def test_kernel_variants_agree():
 
 
 def test_single_launch_scan_matches_cumsum():
-    """k_scan_excl (decoupled look-back, one launch) against NumPy on sizes around the tile (2048)
+    """k_scan_excl (decoupled look-back, one launch) against NumPy on sizes around the tile (8192)
     and look-back window (32 tiles) boundaries, zeros, and repeated launches on the same
     descriptors (the epoch tag must make stale descriptors invisible)."""
     import torch
@@ -170,7 +170,7 @@ def test_single_launch_scan_matches_cumsum():
         s.add_particles(p, m, velocity=vel)
     s._run_substeps(s.default_dt, 1)           # binds the workspace
     rng = np.random.default_rng(5)
-    for n in (1, 7, 2047, 2048, 2049, 4096, 65535, 65536, 65537, 200001):
+    for n in (1, 7, 2047, 8191, 8192, 8193, 16384, 262143, 262144, 262145, 300001):
         for rep in range(2):
             a = rng.integers(0, 9, n).astype(np.int32) if rep == 0 else np.zeros(n, np.int32)
             if rep == 1 and n > 3:
@@ -179,7 +179,7 @@ def test_single_launch_scan_matches_cumsum():
             d_out = torch.full((n, ), -1, dtype=torch.int32, device='cuda')
             rc = s._lib.mpm_debug_scan(s._ctx, d_in.data_ptr(), d_out.data_ptr(), n, s._stream())
             if rc != 0:
-                assert n > 65536, s._lib.mpm_last_error(s._ctx)   # larger than this small workspace allows
+                assert n > 262144, s._lib.mpm_last_error(s._ctx)   # larger than this small workspace allows
                 continue
             torch.cuda.synchronize()
             want = np.concatenate([[0], np.cumsum(a[:-1], dtype=np.int64)]).astype(np.int32)
