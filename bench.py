@@ -290,11 +290,13 @@ def main():
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of k_p2g3<640,4> on this workload, one ncu --set full
-        # capture (profiles/r01_ncu_final_v5.md): 473.3 MB + 159.0 MB per launch
-        'traffic': 632.2e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
+        # capture (profiles/r01_ncu_final_v6.md): 471.3 MB + 157.9 MB per launch
+        'traffic': 629.2e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
         'peak_source': peak_src,
         'algorithmic_bytes_per_launch': b_alg_p2g,
         'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
+        'kernel_ms_note': 'CUDA events on the kernels\' stream, second pass of the same K steps right after the timed one '
+                          '(five event records per substep serialise the PDL chain, so they are kept out of `value`)',
         'substep': {'algorithmic_bytes': b_alg_step,
                     'achieved': b_alg_step / (ms_per_step * 1e-3) / 1e9 if world == 1 else None,
                     'frac': b_alg_step / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None},
