@@ -613,6 +613,12 @@ class MPMSolver:
                         'mpm_pack_particles')
         return ranges, xv.cpu().numpy().view(np.uint32), col.cpu().numpy()
 
+    def write_blender_cache(self, folder, frame):
+        """One frame of the Blender add-on's particle cache (ref blender/particles_io.py:40-61 as driven by
+        blender/operators.py:228-247 from particle_info())."""
+        from .blender_cache import write_frame
+        return write_frame(folder, frame, self.particle_info())
+
     def write_particles_ply(self, fn):
         np_x = self.x.to_numpy()
         np_color = self.color.to_numpy().astype(np.uint32)
