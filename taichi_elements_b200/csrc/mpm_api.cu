@@ -45,9 +45,6 @@ struct mpm_ctx {
   int *flags = nullptr, *fscan = nullptr, *cellcount = nullptr, *cellstart = nullptr;
   int64_t table_cap = 0;
   bool dense = false;   // counting-sort path usable for the current layout
-  bool dense_cells = false;   // ... with per-cell tables indexed by dense leaf-block index (mpm_bin.cuh, DENSE)
-  int use_dense_cells = 1;
-  size_t cell_cap = 0;
   Slab slab{0, INT_MIN, INT_MAX};
   CommBufs comm{{nullptr, nullptr}, {nullptr, nullptr}, 0, 0, {nullptr, nullptr}, {nullptr, nullptr}};
   // peer path (NVLink writes into the neighbour's buffers)
@@ -142,7 +139,7 @@ static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, in
 struct Carve {
   size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
       off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, off_scan_desc, total,
-      cub_bytes, scan_tiles, cell_cap;
+      cub_bytes, scan_tiles;
   int64_t table_cap;
 };
 
@@ -178,9 +175,9 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_ct = take(sizeof(ColliderTable));
   c.off_scratch = take((size_t)5 * cap * 4);
   c.table_cap = table_capacity(max_blocks);
-  c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks, std::max<int64_t>(c.table_cap, (int64_t)4 * max_blocks * cells + 1));
+  c.cub_bytes = cub_temp_bytes(cap, (int64_t)no * max_blocks, std::max<int64_t>(c.table_cap, (int64_t)max_blocks * cells + 1));
   c.off_cub = take(c.cub_bytes);
-  c.scan_tiles = (size_t)(std::max<int64_t>(c.table_cap, (int64_t)4 * max_blocks * cells + 1) / SCAN_TILE + 2);
+  c.scan_tiles = (size_t)(std::max<int64_t>(c.table_cap, (int64_t)max_blocks * cells + 1) / SCAN_TILE + 2);
   c.off_scan_desc = take(c.scan_tiles * 8);
   c.off_pb_start = take((size_t)(max_blocks + 2) * 4);
   c.off_pb_mask = take((size_t)max_blocks * 4);
@@ -192,11 +189,8 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_pb_key = take((size_t)max_blocks * 4);
   c.off_flags = take((size_t)c.table_cap * 4);
   c.off_fscan = take((size_t)c.table_cap * 4);
-  // per-cell counters / bucket starts: 4x the block capacity so that a compact particle box can be indexed
-  // by dense leaf-block index (nlin * cells entries, "dense cells") instead of by block slot
-  c.cell_cap = (size_t)4 * max_blocks * cells + 1;
-  c.off_cellcount = take(c.cell_cap * 4);
-  c.off_cellstart = take(c.cell_cap * 4);
+  c.off_cellcount = take(((size_t)max_blocks * cells + 1) * 4);
+  c.off_cellstart = take(((size_t)max_blocks * cells + 1) * 4);
   c.total = o;
   return c;
 }
@@ -265,7 +259,6 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
-  if (const char* v = getenv("MPM_DENSE_CELLS")) ctx->use_dense_cells = atoi(v);
   if (const char* v = getenv("MPM_SCAN")) ctx->own_scan = strcmp(v, "cub") != 0;
   {
     int occ = 1;
@@ -330,7 +323,6 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   ctx->fscan = (int*)(b + c.off_fscan);
   ctx->cellcount = (int*)(b + c.off_cellcount);
   ctx->cellstart = (int*)(b + c.off_cellstart);
-  ctx->cell_cap = c.cell_cap;
   ctx->table_cap = c.table_cap;
   ctx->ct_dirty = true;
   ctx->last_valid = false;
@@ -512,7 +504,6 @@ static int update_layout(mpm_ctx* ctx) {
   double nlin = 1.0;
   for (int d = 0; d < ctx->dim; ++d) nlin *= (double)ctx->L.eb[d];
   ctx->dense = ctx->use_dense && (2.0 * nlin + 1.0 <= (double)ctx->table_cap);
-  ctx->dense_cells = ctx->dense && ctx->use_dense_cells && (nlin * (double)ctx->cells + 1.0 <= (double)ctx->cell_cap);
   return MPM_OK;
 }
 
@@ -603,7 +594,6 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.slab = ctx->slab; a.cb = ctx->comm;
   a.n_rows = (int)ctx->n;
   a.pf_mode = ctx->pf_mode;
-  a.cell_dense = ctx->dense_cells ? 1 : 0;
   return a;
 }
 
@@ -642,8 +632,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     // ---- counting sort on the (block, cell) key over a dense flag table (mpm_bin.cuh)
     int nlin = 1;
     for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
-    const bool dc = ctx->dense_cells;
-    const int ncell = (dc ? nlin : ctx->max_blocks) * G::CELLS + 1;
+    const int ncell = ctx->max_blocks * G::CELLS + 1;
     if (!ctx->cell_zeroed) CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
     ctx->cell_zeroed = false;
     const bool fused_keys = ctx->keys_ready;   // keys and flags were written by the previous substep's G2P
@@ -655,16 +644,13 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     ctx->keys_ready = false;
     // (a substep whose keys came from G2P is committed by the scan's first thread)
     { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, fused_keys, s); if (rc) return rc; }
-    CK(launch_chain(ctx->pdl, dc ? k_bin_rank<D, true> : k_bin_rank<D, false>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s,
-                    (const uint32_t*)ctx->keys_a, (const int*)ctx->fscan, ctx->cellcount, ctx->vals_a, ctx->pb_key,
-                    ctx->max_blocks, st));
+    CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
+                    ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
     { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s); if (rc) return rc; }
-    CK(launch_chain(ctx->pdl, dc ? k_bin_scatter<D, true> : k_bin_scatter<D, false>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s,
-                    (const uint32_t*)ctx->keys_a, (const uint32_t*)ctx->vals_a, (const int*)ctx->fscan,
-                    (const int*)ctx->cellstart, ctx->vals_b, (const Status*)st));
-    CK(launch_chain(ctx->pdl, dc ? k_bin_finish<D, true> : k_bin_finish<D, false>,
-                    gs_blocks((int64_t)(dc ? nlin : ctx->max_blocks) * G::NO, 256, sm), 256, 0, s, (const int*)ctx->flags,
-                    (const int*)ctx->fscan, nlin, ctx->L, ctx->pb_key, (const int*)ctx->cellstart, ctx->pb_start, ctx->pb_nbr,
+    CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
+                    ctx->fscan, ctx->cellstart, ctx->vals_b, st));
+    CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
+                    ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr,
                     ctx->gb_key, ctx->max_blocks, st));
     keys = ctx->keys_a;
     perm = ctx->vals_b;
@@ -703,9 +689,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     // the same pass clears what the next substep of the batch needs zeroed (no memset nodes in the chain)
     int *z1 = nullptr, *z2 = nullptr, n1 = 0, n2 = 0;
     if (ctx->dense) {
-      int nl = 1;
-      for (int d = 0; d < D; ++d) nl *= ctx->L.eb[d];
-      z1 = ctx->cellcount; n1 = (ctx->dense_cells ? nl : ctx->max_blocks) * G::CELLS + 1;
+      z1 = ctx->cellcount; n1 = ctx->max_blocks * G::CELLS + 1;
       ctx->cell_zeroed = true;
       if (fuse_next) {
         int nlin = 1;

@@ -220,10 +220,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_excl(const int* __restrict__ in
   }
 }
 
-// DENSE: the per-cell counters are indexed by the key itself (dense leaf-block index * cells + cell) instead
-// of by the compacted block slot: no dependent fscan look-up, and the same counters can be filled by the
-// previous G2P (fused rank, mpm_kernels.cuh) because they do not depend on the block scan.
-template <int D, bool DENSE>
+template <int D>
 __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restrict__ fscan,
                            int* __restrict__ cellcount, uint32_t* __restrict__ rank, uint32_t* __restrict__ pb_key,
                            int max_blocks, Status* st) {
@@ -246,13 +243,9 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
       uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
       if (key != INVALID_KEY) {
         lin = key >> G::CB;
-        if constexpr (DENSE) {
-          idx = key;
-        } else {
-          const int b = fscan[lin];
-          if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
-          else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
-        }
+        const int b = fscan[lin];
+        if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
+        else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
       }
       const bool live = idx < 0xFFFFFF00u;
       // one atomic per distinct bucket in the warp (neighbouring particles share cells)
@@ -262,13 +255,13 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
       if (live && lane == leader) base = atomicAdd(&cellcount[idx], __popc(grp));
       base = __shfl_sync(0xffffffffu, base, leader);
       rr[j] = (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-      if (!DENSE && live && rr[j] == 0) pb_key[idx / G::CELLS] = lin;   // (DENSE: k_bin_finish fills pb_key)
+      if (live && rr[j] == 0) pb_key[idx / G::CELLS] = lin;
     }
     if (t < nquad) reinterpret_cast<uint4*>(rank)[t] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
   }
 }
 
-template <int D, bool DENSE>
+template <int D>
 __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
                               const int* __restrict__ fscan, const int* __restrict__ cellstart,
                               uint32_t* __restrict__ perm, const Status* st) {
@@ -284,19 +277,15 @@ __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t*
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (kk[j] == INVALID_KEY || 4u * t + j >= (uint32_t)n) continue;
-      if constexpr (DENSE) {
-        perm[cellstart[kk[j]] + rr[j]] = 4u * t + j;
-      } else {
-        const int b = fscan[kk[j] >> G::CB];
-        perm[cellstart[(size_t)b * G::CELLS + (kk[j] & (G::CELLS - 1))] + rr[j]] = 4u * t + j;
-      }
+      const int b = fscan[kk[j] >> G::CB];
+      perm[cellstart[(size_t)b * G::CELLS + (kk[j] & (G::CELLS - 1))] + rr[j]] = 4u * t + j;
     }
   }
 }
 
-template <int D, bool DENSE>
+template <int D>
 __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restrict__ fscan, int nlin, KeyLayout L,
-                             uint32_t* __restrict__ pb_key, const int* __restrict__ cellstart,
+                             const uint32_t* __restrict__ pb_key, const int* __restrict__ cellstart,
                              int* __restrict__ pb_start, int* __restrict__ pb_nbr, uint32_t* __restrict__ gb_key,
                              int max_blocks, Status* st) {
   using G = Geo<D>;
@@ -312,7 +301,7 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
   }
   if (first) {
     st->npb = npb; st->ngb = ngb; st->ngb_raw = ngb;
-    const int n_live = cellstart[(size_t)(DENSE ? nlin : npb) * G::CELLS];   // particles that were ranked
+    const int n_live = cellstart[(size_t)npb * G::CELLS];   // particles that were ranked
     pb_start[npb] = n_live;
     st->n_live = n_live;
     st->mig_cnt[0] = st->mig_cnt[1] = 0;
@@ -322,22 +311,6 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
     st->maxgv_bits = 0;
     for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
   }
-  if constexpr (DENSE) {
-    // one thread per (leaf block of the box, octant): blocks that hold particles find their slot in fscan
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlin * G::NO; i += gridDim.x * blockDim.x) {
-      const int lin = i / G::NO, o = i % G::NO;
-      if (!flags[lin]) continue;
-      const int b = fscan[lin];
-      const int t = lin + oct_delta<D>(L, o);
-      int slot = -1;
-      if (flags[nlin + t]) {
-        slot = fscan[nlin + t] - npb;
-        gb_key[slot] = (uint32_t)t;
-      }
-      pb_nbr[b * G::NO + o] = slot;
-      if (o == 0) { pb_key[b] = (uint32_t)lin; pb_start[b] = cellstart[(size_t)lin * G::CELLS]; }
-    }
-  } else
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npb * G::NO; i += gridDim.x * blockDim.x) {
     const int b = i / G::NO, o = i % G::NO;
     const int t = (int)pb_key[b] + oct_delta<D>(L, o);

@@ -320,7 +320,6 @@ template <int D> struct SubstepArgs {
   uint32_t* next_keys;  // non-null: G2P also emits the next substep's sort keys and block flags
   int* next_flags;      //   (same key layout, see mpm_bin.cuh); saves the k_bin_keys pass
   int next_nlin;
-  int cell_dense; // cellstart is indexed by dense leaf-block index (pb_key[b]) instead of by block slot
   int pf_mode;    // next-block L2 prefetch: 0 off, 1 one prefetch per 128 B, 2 bulk range prefetch, 3 one per 32 B
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)

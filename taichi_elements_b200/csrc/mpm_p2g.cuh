@@ -72,8 +72,7 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, MINB) k_p2g_cell(SubstepAr
     // phase 0: first sorted position of every cell of the block: straight from the
     // counting sort's bucket starts, or (radix fallback) from the sorted keys
     if (a.cellstart) {
-      const size_t cb = (size_t)(a.cell_dense ? a.pb_key[b] : (uint32_t)b) * G::CELLS;
-      for (int c = tid; c <= G::CELLS; c += T) cs[c] = a.cellstart[cb + c] - start;
+      for (int c = tid; c <= G::CELLS; c += T) cs[c] = a.cellstart[(size_t)b * G::CELLS + c] - start;
     } else {
       for (int q = tid; q < cnt; q += T) {
         const int c = (int)(a.keys[start + q] & (G::CELLS - 1));

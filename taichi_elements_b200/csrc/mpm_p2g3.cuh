@@ -45,8 +45,7 @@ __device__ __forceinline__ void p2g3_prepare(const SubstepArgs<3>& a, int nb, in
                                              int* hist) {
   if (nb >= npb) return;
   const int ns = a.pb_start[nb];
-  const size_t cb = (size_t)(a.cell_dense ? a.pb_key[nb] : (uint32_t)nb) * 64;
-  for (int c = lane; c <= 64; c += 32) cs[c] = a.cellstart[cb + c] - ns;
+  for (int c = lane; c <= 64; c += 32) cs[c] = a.cellstart[(size_t)nb * 64 + c] - ns;
   hist[lane] = 0;
   __syncwarp();
   const int m0 = min(cs[lane + 1] - cs[lane], 31), m1 = min(cs[lane + 33] - cs[lane + 32], 31);
