@@ -306,7 +306,17 @@ def main():
     e2e = None
     if not args.no_e2e:
         frames = max(1, min(3, args.steps // 40))
-        host_parts = [(torch.from_numpy(x).pin_memory().numpy(), m) for parts in bricks for x, m in parts]
+        # N > 1: the inputs of a rank are the rows of its slab (own brick plus the few boundary rows of the
+        # neighbouring bricks whose base block falls on this side of the cut), selected once, outside the timed region
+        if world == 1:
+            host_parts = [(torch.from_numpy(x).pin_memory().numpy(), m) for parts in bricks for x, m in parts]
+        else:
+            host_parts = []
+            for parts in bricks:
+                for x, m in parts:
+                    rows = x[mpm.slab.mine(x[:, 0])]
+                    if len(rows):
+                        host_parts.append((torch.from_numpy(np.ascontiguousarray(rows)).pin_memory().numpy(), m))
         sub_per_frame = 0
         with quiet:
             mpm2 = mpm
@@ -319,9 +329,7 @@ def main():
                 mpm2.step(w['frame_dt'])
                 if world > 1:
                     mpm2.flush_migration()
-                    keep.append(mpm2.local_rows())
-                else:
-                    keep.append(mpm2.particle_info())
+                keep.append(mpm2.particle_info())
             del keep
         barrier()
         t0 = time.perf_counter()
@@ -336,9 +344,7 @@ def main():
                 sub_per_frame = mpm2.total_substeps - before
                 if world > 1:
                     mpm2.flush_migration()
-                    info = mpm2.local_rows()
-                else:
-                    info = mpm2.particle_info()
+                info = mpm2.particle_info()      # N > 1: this rank's particles (position, velocity, material, color, id)
                 d2h = sum(a.nbytes for a in info.values())
         barrier()
         el = time.perf_counter() - t0
@@ -346,11 +352,11 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         el, d2h = float(te[0].item()), float(te[1].item())
-        h2d = sum(x.nbytes for x, _ in host_parts) / world   # each rank uploads only its slab
+        h2d = sum(x.nbytes for x, _ in host_parts)                  # this rank's rows
         e2e = {'value': n_total * sub_per_frame * frames / el, 'unit': 'particle-substeps/s',
                'h2d_bytes_per_step': h2d / sub_per_frame, 'd2h_bytes_per_step': d2h / sub_per_frame,
                'what': f'{frames} x [clear_particles, add_particles(host arrays), step({w["frame_dt"]}) = '
-                       f'{sub_per_frame} substeps, particle_info()] through MPMSolver; wall clock incl. copies'}
+                       f'{sub_per_frame} substeps, particle_info()] through MPMSolver (N > 1: DistributedMPMSolver, each rank its slab); wall clock incl. copies'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -160,17 +160,34 @@ def _make_distributed_solver():
 
         # ---- seeding: same call on every rank, each keeps its slab -------------
         def add_particles(self, particles, material, color=0xFFFFFF, velocity=None):
+            """Same call on every rank; each keeps the rows whose base block lies in its slab.  The rows are
+            uploaded once and selected on the device (same f32 arithmetic as the binning kernel and as
+            SlabDecomposition.block_x), global ids = position in the call sequence."""
             particles = np.ascontiguousarray(np.asarray(particles, dtype=np.float32))
-            keep = self.slab.mine(particles[:, 0])
-            ids = (self._global_n + np.nonzero(keep)[0]).astype(np.int32)
-            self._global_n += len(particles)
-            n0 = self._n
-            super().add_particles(particles[keep], material, color, velocity)
-            if len(ids):
-                cur = ctypes.c_int32()
-                self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
-                id_row = self._nf - 2          # x v F C Jp material color id emitter
-                self._state[cur.value, id_row, n0:n0 + len(ids)] = torch.from_numpy(ids).to(self._device)
+            assert particles.ndim == 2 and particles.shape[1] == self.dim
+            n_all = len(particles)
+            if n_all == 0:
+                return
+            with torch.cuda.device(self._device):
+                dev = torch.from_numpy(particles).to(self._device)
+                base = torch.floor(dev[:, 0] * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
+                bx = torch.div(base + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor')
+                keep = (bx >= self.slab.lo) & (bx < self.slab.hi)
+                cnt = int(keep.sum().item())
+                if cnt == n_all:
+                    ids = torch.arange(self._global_n, self._global_n + n_all, dtype=torch.int32, device=self._device)
+                else:
+                    idx = torch.nonzero(keep).squeeze(1)
+                    dev = dev.index_select(0, idx).contiguous()
+                    ids = (idx + self._global_n).to(torch.int32)
+                self._global_n += n_all
+                n0 = self._n
+                self._seed_from_device(dev, material, color, velocity)
+                if cnt:
+                    cur = ctypes.c_int32()
+                    self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
+                    id_row = self._nf - 2          # x v F C Jp material color id emitter
+                    self._state[cur.value, id_row, n0:n0 + cnt] = ids
 
         def clear_particles(self):
             if self.comm == 'peer':
@@ -305,6 +322,38 @@ def _make_distributed_solver():
                 raise _lib.MPMError('flush_migration: ' + self._lib.mpm_last_error(self._ctx).decode())
 
         # ---- read-back ----------------------------------------------------------------
+        def particle_info(self):
+            """MPMSolver.particle_info() (ref engine/mpm_solver.py:1172-1180) for THIS rank's particles, in storage
+            order, plus their global ids ('id').  Call flush_migration() first: rows of particles that have been
+            handed to a neighbour are excluded here (same f32 arithmetic as the binning), arrivals must have been
+            appended.  One device-side selection, one copy into pinned host memory per field."""
+            n, d = self._n, self.dim
+            names = ('position', 'velocity', 'material', 'color', 'id')
+            if n == 0:
+                out = {'position': np.zeros((0, d), np.float32), 'velocity': np.zeros((0, d), np.float32)}
+                out.update({k: np.zeros(0, np.int32) for k in names[2:]})
+                return out
+            cur = ctypes.c_int32()
+            self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
+            with torch.cuda.device(self._device):
+                torch.cuda.current_stream(self._device).synchronize()
+                st = self._state[cur.value]
+                x0 = st[0, :n].view(torch.float32)
+                base = torch.floor(x0 * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
+                bx = torch.div(base + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor')
+                keep = (bx >= self.slab.lo) & (bx < self.slab.hi)
+                idx = torch.nonzero(keep).squeeze(1)
+                jp = 2 * d + 2 * d * d
+                rows = [st[0:d], st[d:2 * d], st[jp + 1:jp + 2], st[jp + 2:jp + 3], st[jp + 3:jp + 4]]
+                out = {}
+                for name, r in zip(names, rows):
+                    sel = r[:, :n].index_select(1, idx).t().contiguous()          # (count, words)
+                    host = torch.empty(sel.shape, dtype=torch.int32, pin_memory=True)
+                    host.copy_(sel)
+                    a = host.numpy()
+                    out[name] = a.view(np.float32) if name in ('position', 'velocity') else a[:, 0]
+            return out
+
         def local_rows(self):
             """This rank's live particles: dict of arrays in storage order, with global ids.
             Rows of particles that have left the slab since the last substep are excluded."""

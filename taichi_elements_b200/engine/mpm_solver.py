@@ -504,7 +504,15 @@ class MPMSolver:
         self.set_source_velocity(velocity)
         if n == 0:
             return
-        dev = torch.from_numpy(particles).to(self._device)
+        self._seed_from_device(torch.from_numpy(particles).to(self._device), material, color, velocity)
+
+    def _seed_from_device(self, dev, material, color, velocity):
+        """add_particles for positions that already live on the device: (n, dim) float32, contiguous."""
+        n = int(dev.shape[0])
+        self._reserve(n)
+        self.set_source_velocity(velocity)
+        if n == 0:
+            return
         self._check(
             self._lib.mpm_seed_positions(self._ctx, dev.data_ptr(), n, int(material), int(color),
                                          self._vec(velocity), 0, self._stream()), 'mpm_seed_positions')
