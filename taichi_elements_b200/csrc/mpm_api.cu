@@ -61,6 +61,7 @@ struct mpm_ctx {
   int pending_n = 0, pending_npb = 0, pending_ngb = 0;
   bool keys_ready = false;     // the previous G2P of this batch already produced keys + flags
   int fuse_keys = 1;
+  int sort_seed = 1;            // (MPM_SORT_SEED) block-sorted storage of large add_particles arrays
   bool in_batch = false;
   int batch_cur0 = 0, batch_enq = 0;
   const uint32_t* cur_keys = nullptr;
@@ -254,6 +255,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
 
   }
   if (const char* v = getenv("MPM_FUSE_KEYS")) ctx->fuse_keys = atoi(v);
+  if (const char* v = getenv("MPM_SORT_SEED")) ctx->sort_seed = atoi(v);
   if (const char* v = getenv("MPM_SORT")) ctx->use_dense = (strcmp(v, "radix") == 0) ? 0 : 1;
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
@@ -383,6 +385,20 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   a.cap = ctx->cap;
   a.n0 = ctx->n;
   int blocks = gs_blocks(a.n, 256, ctx->sm_count);
+  // A large array of external positions is stored sorted by leaf block (ids keep the insertion order): the
+  // first substep then reads block-local rows instead of gathering 26 words per particle at random.  The sort
+  // borrows the binning scratch, which is free between batches except for g2p2g's pending permutation; the
+  // distributed solver writes its global ids by row and keeps the input order.
+  if (a.mode == 0 && ctx->sort_seed && a.n >= (1 << 15) && !ctx->K.g2p2g && !ctx->slab.enabled && !ctx->in_batch &&
+      ctx->P.grid_size == 4096 && (size_t)a.n <= ctx->cap) {
+    const int half = ctx->P.grid_size / 2;
+    if (ctx->dim == 3) k_seed_keys<3><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a);
+    else k_seed_keys<2><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a);
+    cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
+    size_t tb = ctx->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, (int)a.n, 0, 10 * ctx->dim, s));
+    a.order = dv.Current();
+  }
   if (ctx->dim == 3) k_seed<3><<<blocks, 256, 0, s>>>(a); else k_seed<2><<<blocks, 256, 0, s>>>(a);
   CK(cudaGetLastError());
   ctx->n += a.n;

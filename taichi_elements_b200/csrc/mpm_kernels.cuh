@@ -970,7 +970,28 @@ struct SeedArgs {
   const int* mats;      // restart per-particle material / color
   const int* colors;
   int mode;             // 0 external, 1 cube, 2 ellipsoid, 3 restart
+  const uint32_t* order; // non-null (mode 0): row n0 + i takes input order[i] (inputs pre-sorted by leaf block)
 };
+
+// Sort key of an external position for block-sorted seeding: absolute leaf-block coordinates, 10 bits per
+// axis (the 4096^3 virtual grid of 4^3 leaves), x slowest like the substep's key.  Only the storage order
+// of the new rows depends on it (ids keep the insertion order); it spares the first substep after a large
+// add_particles the random gather through `perm` that an arbitrary input order causes.
+template <int D>
+__global__ void k_seed_keys(const float* __restrict__ x, int64_t n, float inv_dx, int half, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+  using G = Geo<D>;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t k = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int b = (base_index(x[i * D + d], inv_dx) + half) >> G::LOG_LEAF;
+      k = (k << 10) | (uint32_t)min(max(b, 0), 1023);
+    }
+    keys[i] = k;
+    vals[i] = (uint32_t)i;
+  }
+}
 
 // seed_particle (engine/mpm_solver.py:823-838) behind seed / seed_ellipsoid /
 // seed_from_external_array / recover_from_external_array.
@@ -979,14 +1000,15 @@ __global__ void k_seed(SeedArgs a) {
   using FL = Fld<D>;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t p = (uint32_t)(a.n0 + i);
-    const uint64_t id = (uint64_t)(a.n0 + i);
+    const int64_t src = a.order ? (int64_t)a.order[i] : i;     // input this row takes (block-sorted seeding)
+    const uint64_t id = (uint64_t)(a.n0 + src);
     float x[D], v[D];
     int material = a.material, color = a.color;
 #pragma unroll
     for (int d = 0; d < D; ++d) v[d] = a.vel[d];
     if (a.mode == 0 || a.mode == 3) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = a.x[i * D + d];
+      for (int d = 0; d < D; ++d) x[d] = a.x[src * D + d];
       if (a.mode == 3) {
 #pragma unroll
         for (int d = 0; d < D; ++d) v[d] = a.v[i * D + d];
@@ -1021,7 +1043,7 @@ __global__ void k_seed(SeedArgs a) {
     stf(a.state, a.cap, FL::JP, p, material == SAND ? 0.0f : 1.0f);   // :831-835
     stu(a.state, a.cap, FL::MAT, p, (uint32_t)material);
     stu(a.state, a.cap, FL::COLOR, p, (uint32_t)color);
-    stu(a.state, a.cap, FL::ID, p, p);
+    stu(a.state, a.cap, FL::ID, p, (uint32_t)id);   // insertion index (block-sorted seeding: != row)
     stu(a.state, a.cap, FL::EMIT, p, (uint32_t)a.emitter);
   }
 }

@@ -180,6 +180,17 @@ def _make_distributed_solver():
                     idx = torch.nonzero(keep).squeeze(1)
                     dev = dev.index_select(0, idx).contiguous()
                     ids = (idx + self._global_n).to(torch.int32)
+                if cnt >= (1 << 15) and self.grid_size == 4096:
+                    # store the rows sorted by leaf block (ids keep the call order), as the single-GPU solver does for
+                    # large arrays: the first substep then reads block-local rows instead of gathering at random
+                    b = torch.floor(dev * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
+                    b = torch.div(b + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor').clamp_(0, 1023)
+                    key = b[:, 0]
+                    for d in range(1, self.dim):
+                        key = key * 1024 + b[:, d]
+                    order = torch.argsort(key)
+                    dev = dev.index_select(0, order).contiguous()
+                    ids = ids.index_select(0, order)
                 self._global_n += n_all
                 n0 = self._n
                 self._seed_from_device(dev, material, color, velocity)

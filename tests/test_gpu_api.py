@@ -212,6 +212,33 @@ def test_write_particles_round_trip(tmp_path):
     assert os.path.getsize(str(tmp_path / 'frame.ply')) > 16 * s.n_particles[None]
 
 
+def test_large_add_particles_is_stored_block_sorted_but_reads_back_in_insertion_order():
+    """add_particles with >= 2^15 host positions stores the rows sorted by leaf block (so the first substep
+    does not gather at random); ids keep the insertion order, and the physics is the same as the oracle's."""
+    from oracle.mpm_oracle import OracleMPM
+    rng = np.random.default_rng(21)
+    pos = (0.25 + 0.5 * rng.random((50000, 3))).astype(np.float32)
+    s = _solver(res=(64, 64, 64))
+    s.add_particles(pos[:30000], s.material_elastic, velocity=(0.5, -1.0, 0.25))   # small enough: input order
+    s.add_particles(pos[30000:40000], s.material_water)
+    s.add_particles(pos[10000:], s.material_snow, color=0x123456)                # 40000 rows: block-sorted
+    want = np.concatenate([pos[:30000], pos[30000:40000], pos[10000:]])
+    assert np.array_equal(s.x.to_numpy(), want)
+    mat = s.material.to_numpy()
+    assert np.all(mat[:30000] == 1) and np.all(mat[30000:40000] == 0) and np.all(mat[40000:] == 2)
+    o = OracleMPM((64, 64, 64))
+    o.add_particles(pos[:30000], 1, velocity=(0.5, -1.0, 0.25))
+    o.add_particles(pos[30000:40000], 0)
+    o.add_particles(pos[10000:], 2, color=0x123456)
+    for _ in range(2):
+        o.substep(o.default_dt)
+    st = s._run_substeps(o.default_dt, 2)
+    assert st.substeps_done == 2
+    assert np.abs(s.x.to_numpy() - o.x).max() < 1e-5
+    assert np.abs(s.v.to_numpy() - o.v).max() < 2e-3 * max(1.0, np.abs(o.v).max())
+    assert np.array_equal(s.color.to_numpy()[40000:], np.full(40000, 0x123456))
+
+
 def test_capacity_growth_and_batched_step_equivalence():
     rng = np.random.default_rng(5)
     pts = (rng.random((60000, 3)) * 0.5 + 0.25).astype(np.float32)        # > initial 16384 rows, > 1024 blocks at res 128
