@@ -1,7 +1,11 @@
-// Device kernels of the MLS-MPM substep (sm_100a).  One substep =
+// Device kernels of the MLS-MPM substep (sm_100a).  One substep inside a batch =
+//   k_scan_excl<1> (flags; commits the previous substep) -> k_bin_rank -> k_scan_excl<0> (cells)
+//   -> k_bin_scatter -> k_bin_finish                                     (mpm_bin.cuh; keys + flags came from
+//   -> k_clear_grid -> k_p2g3 (mpm_p2g3.cuh) -> k_grid_op -> k_g2p        the previous k_g2p, else k_bin_keys)
+// chained with programmatic dependent launch (pdl_enter()).  Fallback for particle boxes too large for the
+// flag table:
 //   k_reset -> k_keys -> radix sort -> head select -> k_pb_finalize -> k_pb_masks
-//   -> sort/unique of candidate grid blocks -> k_gb_finalize -> k_nbr
-//   -> k_clear_grid -> k_p2g -> k_grid_op -> k_g2p -> k_end
+//   -> sort/unique of candidate grid blocks -> k_gb_finalize -> k_nbr -> k_clear_grid -> k_p2g_cell -> ...
 // replacing build_pid / p2g / grid_normalization_and_gravity / grid_bounding_box
 // / collide / g2p / compute_max_velocity of /root/reference/engine/mpm_solver.py
 // (:344-361, 487-616, 618-687, 694-735).

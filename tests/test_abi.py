@@ -65,3 +65,19 @@ def test_reference_import_path_and_constants():
                  'write_particles_ply', 'copy_ranged', 'read_restart', 'clear_particles'):
         assert callable(getattr(M, meth)), meth
     assert list(inspect.signature(M.add_mesh).parameters)[-1] == 'emmiter_id'   # the reference's spelling
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) needs no GPU and prints one
+    JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '1'], check=True, capture_output=True, text=True, cwd=root, timeout=600).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'particle-substeps/sec' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['unit'] == 'particle-substeps/s' and line['dtype'] == 'f32'
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
