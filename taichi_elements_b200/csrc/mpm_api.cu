@@ -614,14 +614,15 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
 }
 
 // exclusive scan of n ints: one k_scan_excl launch (optionally committing the previous substep), or CUB
-static int enqueue_scan(mpm_ctx* ctx, const int* in, int* out, int n, bool commit, cudaStream_t s) {
+static int enqueue_scan(mpm_ctx* ctx, const int* in, int* out, int n, bool commit, cudaStream_t s,
+                        const int* n_dev = nullptr, int n_mul = 0) {
   // the prefix travels one 32-tile window per hop: beyond ~8 hops the chain costs more than CUB's second launch
   if (ctx->own_scan && n <= 256 * SCAN_TILE) {
     ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x3fffffffu;
     if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
     const int grid = std::max(1, std::min(ctx->scan_grid, (n + SCAN_TILE - 1) / SCAN_TILE));
-    if (commit) CK(launch_chain(ctx->pdl, k_scan_excl<true>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
-    else CK(launch_chain(ctx->pdl, k_scan_excl<false>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
+    if (commit) CK(launch_chain(ctx->pdl, k_scan_excl<true>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status, n_dev, n_mul));
+    else CK(launch_chain(ctx->pdl, k_scan_excl<false>, grid, SCAN_T, 0, s, in, out, n, ctx->scan_desc, ctx->scan_epoch, ctx->d_status, n_dev, n_mul));
     return MPM_OK;
   }
   if (commit) CK(launch_chain(ctx->pdl, k_substep_begin, 1, 1, 0, s, ctx->d_status));
@@ -662,7 +663,8 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, fused_keys, s); if (rc) return rc; }
     CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
                     ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
-    { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s); if (rc) return rc; }
+    // (only the cells of the npb = fscan[nlin] existing blocks: the table is sized by capacity)
+    { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s, ctx->fscan + nlin, G::CELLS); if (rc) return rc; }
     CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
                     ctx->fscan, ctx->cellstart, ctx->vals_b, st));
     CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
@@ -715,7 +717,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
       }
     }
     CK(launch_chain(ctx->pdl, k_clear_grid<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s,
-                    ctx->grid, (const Status*)st, z1, n1, z2, n2));
+                    ctx->grid, (const Status*)st, z1, n1, z2, n2, (int)G::CELLS));
   }
   if (prof) cudaEventRecord(ev[1], s);
   ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
@@ -1458,7 +1460,7 @@ extern "C" int mpm_debug_scan(mpm_ctx* ctx, const int32_t* in_dev, int32_t* out_
   if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->scan_grid, (n + SCAN_TILE - 1) / SCAN_TILE));
   CK(launch_chain(ctx->pdl, k_scan_excl<false>, grid, SCAN_T, 0, s, (const int*)in_dev, (int*)out_dev, (int)n,
-                  ctx->scan_desc, ctx->scan_epoch, ctx->d_status));
+                  ctx->scan_desc, ctx->scan_epoch, ctx->d_status, (const int*)nullptr, 0));
   return MPM_OK;
 }
 

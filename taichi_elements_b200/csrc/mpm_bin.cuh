@@ -122,8 +122,11 @@ __device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long lon
 template <bool COMMIT>
 __global__ void __launch_bounds__(SCAN_T) k_scan_excl(const int* __restrict__ in, int* __restrict__ out, int n,
                                                      unsigned long long* __restrict__ desc, uint32_t epoch,
-                                                     Status* st) {
+                                                     Status* st, const int* __restrict__ n_dev, int n_mul) {
   pdl_enter();
+  // optional device-side length (the per-cell tables are sized by block CAPACITY, the scan only
+  // needs the blocks that exist): n = min(n, *n_dev * n_mul + 1)
+  if (n_dev) n = min(n, max(*n_dev, 0) * n_mul + 1);
   if (COMMIT && blockIdx.x == 0 && threadIdx.x == 0) {
     if (!st->err) {
       st->done += 1;

@@ -277,11 +277,12 @@ __global__ void k_nbr(const uint32_t* __restrict__ keys, const int* __restrict__
 
 template <int D>
 __global__ void k_clear_grid(float4* __restrict__ grid, const Status* st, int* __restrict__ z1, int n1,
-                             int* __restrict__ z2, int n2) {
+                             int* __restrict__ z2, int n2, int n1_blocks_mul) {
   pdl_enter();
   // tables the NEXT substep of the batch expects zeroed (per-cell counts; block flags when the
   // coming G2P emits them), so that no memset node sits between the kernels of the chain
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  if (n1_blocks_mul) n1 = min(n1, st->npb * n1_blocks_mul + 1);   // only the cells of existing blocks were counted
   for (int i = gtid; i < n1; i += gsz) z1[i] = 0;
   for (int i = gtid; i < n2; i += gsz) z2[i] = 0;
   if (st->err) return;
