@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the MLS-MPM substep (BASELINE.json metric: particle-substeps/s).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference
+    python bench.py --gpus N --steps K --warmup W             # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...    # CPU restatement of the reference
 
-A "step" is ONE substep (binning -> P2G -> grid op -> G2P) over the whole
-particle set.  Workload at N=1 = BASELINE.json configs[1]: 3D cube drop,
-res 256^3, 2 x 2^21 particles (ELASTIC over WATER), g=(0,-20,0), dt = 3e-3/39.
-Prints one JSON line (see the contract in the task statement).
+A "step" is ONE substep (binning -> P2G -> grid op -> G2P) over the whole particle set.
+
+Default workload = BASELINE.json configs[3] (SURVEY.md 8(d) cfg 4): res 256^3, `unbounded=True`,
+100 M particles in four equal x-slabs WATER / ELASTIC / SNOW / SAND over a slip floor, the slabs
+moving against each other and towards the floor so that the timed window runs on deformed material
+in contact.  N = 1: the whole scene on one B200.  N > 1: the SAME particle set split into N x-slabs
+(strong scaling, the "1 vs 8" of configs[3]); the line also carries `weak_cfg5`, the configs[4]
+brick (125 M particles per GPU, res 512 unbounded, WATER under SAND) timed at the same N.
+`--workload cube_drop_4m` is configs[1].  Prints one JSON line (contract in the task statement).
 """
 import argparse
+import contextlib
+import io
 import json
+import math
 import os
 import sys
 import threading
@@ -25,37 +33,152 @@ B_PARTICLE = 220      # algorithmic bytes per particle-substep, 3D f32 (SURVEY.m
 B_CELL = 88           # algorithmic bytes per active grid cell
 B_P2G_PARTICLE = 144  # P2G share: reads x,v,F,C,Jp,material (104) + writes F,Jp (40)
 B_P2G_CELL = 32       # P2G grid read-modify-write
+B_G2P2G_PARTICLE = 132  # use_g2p2g: reads x,v,F,Jp,material (68) + writes x,v,F,Jp (64)
+
+WATER, ELASTIC, SNOW, SAND = 0, 1, 2, 3
 
 
-def workload(name, rank=0, world=1, seed=2):
-    """Synthetic particle blocks of the named shapes; returns dict."""
-    rng = np.random.default_rng(seed + 1000 * rank)
-    if name == 'cube_drop_4m':          # configs[1]
-        side, res = 0.25, 256
-    elif name == 'cube_drop_sample':     # bounded CPU sample of configs[1]: same density, smaller cubes
-        side, res = 0.16, 256
-    elif name == 'cube_drop_small':      # smoke-sized
-        side, res = 0.0625, 256
-    elif name == 'cube_drop_32m':        # 2 x 128^3 cells x 8 at res 512
-        side, res = 0.25, 512
-    elif name == 'cube_drop_100m':       # 2 x 184^3 cells x 8 = 99.7 M at res 512
-        side, res = 0.359375, 512
+# ------------------------------------------------------------------ workloads
+class Chunk:
+    """`n` particles uniform in a box given in CELL units (so that with dx a power of two the base cell
+    floor(x/dx - 0.5) of every particle lies in [lo - 0.5, hi - 0.5) exactly): rank-independent, seeded per chunk."""
+
+    def __init__(self, lo, hi, n, material, velocity, seed):
+        self.lo, self.hi, self.n, self.material, self.velocity, self.seed = lo, hi, int(n), material, velocity, seed
+
+    def positions(self, dx):
+        rng = np.random.default_rng(self.seed)
+        lo, hi = np.asarray(self.lo, np.float32), np.asarray(self.hi, np.float32)
+        x = rng.random((self.n, 3), dtype=np.float32)
+        x *= (hi - lo)
+        x += lo
+        np.minimum(x, np.nextafter(hi, -np.inf, dtype=np.float32), out=x)
+        x *= np.float32(dx)
+        return x
+
+
+def multimat(name, z_cells=232, chunks_per_material=4, y_cells=120.27, side_walls=False):
+    """configs[3] / SURVEY 8(d) cfg 4: four equal x-slabs WATER, ELASTIC, SNOW, SAND at 8 particles per cell over a
+    slip floor (friction 0.5), res 256 unbounded.  Every slab is `chunks_per_material` chunks of 28 x-cells (7 leaf
+    blocks); consecutive chunks move against each other (+-1 m/s in x) and everything falls at 5 m/s, so the
+    materials are in contact with the floor and with each other and F is away from the identity everywhere after
+    the pre-roll.  The full scene: x in [-0.875, 0.875], y in [0.05, 0.52], z in [-0.453, 0.453], 100 000 000
+    particles.  `side_walls`: slip planes on the two z faces (the CPU sample is a thin z-slice of the scene)."""
+    res, dx = 256, 1.0 / 256
+    nchunk = 4 * chunks_per_material
+    x0 = -28 * nchunk // 2
+    y0 = 0.05 * res
+    per_chunk = int(round(28 * y_cells * z_cells * 8))
+    if name == 'multimat_100m':
+        per_chunk = 6_250_000
+    chunks = []
+    for k in range(nchunk):
+        lo = (x0 + 28 * k + 0.5, y0, -z_cells / 2 + 0.5)
+        hi = (x0 + 28 * (k + 1) + 0.5, y0 + y_cells, z_cells / 2 + 0.5)
+        chunks.append(Chunk(lo, hi, per_chunk, k // chunks_per_material, (1.0 if k % 2 == 0 else -1.0, -5.0, 0.0),
+                            4000 + k))
+    colliders = [((0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 1, 0.5)]      # point, normal, surface (slip), friction
+    if side_walls:
+        colliders.append(((0.0, 0.0, (-z_cells / 2 + 0.5) * dx), (0.0, 0.0, 1.0), 1, 0.0))
+        colliders.append(((0.0, 0.0, (z_cells / 2 + 0.5) * dx), (0.0, 0.0, -1.0), 1, 0.0))
+    return dict(name=name, res=(res, ) * 3, unbounded=True, gravity=(0.0, -9.8, 0.0), frame_dt=3e-3, chunks=chunks,
+                colliders=colliders, preroll=100, n=per_chunk * nchunk,
+                cut_cells=[x0 + 28 * k for k in range(1, nchunk)],   # admissible cut planes (leaf-block aligned)
+                label=f'configs[3]: 3D unbounded res 256^3, {per_chunk * nchunk} particles in four x-slabs '
+                      f'WATER/ELASTIC/SNOW/SAND (8 per cell), slip floor mu=0.5, g=(0,-9.8,0), chunks of 28 cells '
+                      f'colliding at +-1 m/s and falling at 5 m/s, dt=2e-2*dx')
+
+
+def brick(name, world=1, cells=(248, 252, 250)):
+    """configs[4] / SURVEY 8(d) cfg 5: res 512 unbounded, one brick per GPU (248 x 252 x 250 cells x 8 = 124 992 000
+    particles), WATER below SAND, bricks tiled along x (cuts on leaf-block boundaries carry halo and migration),
+    neighbouring bricks approach each other at +-0.5 m/s, all fall at 3 m/s onto a slip floor."""
+    res, dx = 512, 1.0 / 512
+    cx, cy, cz = cells
+    x0 = -cx * world // 2
+    x0 -= x0 % 4
+    y0 = 0.05 * res
+    chunks = []
+    for r in range(world):
+        vel = (0.5 if r % 2 == 0 else -0.5, -3.0, 0.0)
+        for h, mat in enumerate((WATER, SAND)):
+            lo = (x0 + cx * r + 0.5, y0 + h * cy / 2, -cz / 2 + 0.5)
+            hi = (x0 + cx * (r + 1) + 0.5, y0 + (h + 1) * cy / 2, cz / 2 + 0.5)
+            c = Chunk(lo, hi, cx * cy * cz * 4, mat, vel, 5000 + 2 * r + h)
+            c.rank = r
+            chunks.append(c)
+    return dict(name=name, res=(res, ) * 3, unbounded=True, gravity=(0.0, -9.8, 0.0), frame_dt=1.5e-3, chunks=chunks,
+                colliders=[((0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 1, 0.5)], preroll=40, n=cx * cy * cz * 8 * world,
+                cut_cells=[x0 + cx * r for r in range(1, world)],
+                label=f'configs[4]: 3D unbounded res 512^3, {cx * cy * cz * 8} particles per GPU (brick {cx}x{cy}x{cz} '
+                      f'cells, 8 per cell, WATER below SAND), bricks tiled along x, slip floor, dt=2e-2*dx')
+
+
+def cube_drop(name):
+    """configs[1]: 3D cube drop, res 256^3 bounded, ELASTIC cube over WATER cube, 8 per cell, at rest."""
+    side = {'cube_drop_4m': 0.25, 'cube_drop_sample': 0.16, 'cube_drop_small': 0.0625}[name]
+    res = 256
+    ns = int(round(side * res))
+    lo_c = res // 2 - ns // 2
+    chunks = []
+    for k, (y, mat) in enumerate(((0.55, ELASTIC), (0.15, WATER))):
+        lo = (lo_c, y * res, lo_c)
+        hi = (lo_c + ns, y * res + ns, lo_c + ns)
+        chunks.append(Chunk(lo, hi, ns**3 * 8, mat, (0.0, 0.0, 0.0), 2000 + k))
+    return dict(name=name, res=(res, ) * 3, unbounded=False, gravity=(0.0, -20.0, 0.0), frame_dt=3e-3, chunks=chunks,
+                colliders=[], preroll=0, n=2 * ns**3 * 8, cut_cells=[], dt=3e-3 / 39,
+                label=f'configs[1]: 3D cube drop, res 256^3 bounded, {2 * ns**3 * 8} particles (ELASTIC cube over '
+                      f'WATER cube, 8 per cell), g=(0,-20,0), dt=3e-3/39')
+
+
+def workload(name, world=1):
+    w = _workload(name, world)
+    base = 0
+    for c in w['chunks']:          # global particle ids = position in the chunk sequence
+        c.id_base = base
+        base += c.n
+    return w
+
+
+def _workload(name, world=1):
+    if name == 'multimat_100m':
+        return multimat(name)
+    if name == 'multimat_12m':          # same scene, one eighth of the z extent (development / tests)
+        return multimat(name, z_cells=29)
+    if name == 'multimat_sample':       # bounded CPU sample: a 4-cell z-slice between two slip planes, 1 chunk per material
+        return multimat(name, z_cells=4, chunks_per_material=1, side_walls=True)
+    if name == 'multimat_tiny':
+        return multimat(name, z_cells=4, chunks_per_material=1, y_cells=24, side_walls=True)
+    if name.startswith('brick_125m'):
+        return brick(name, world)
+    if name.startswith('brick_2m'):
+        return brick(name, world, cells=(64, 64, 64))
+    if name.startswith('cube_drop'):
+        return cube_drop(name)
+    raise ValueError(name)
+
+
+def substep_dt(w, default_dt):
+    return w.get('dt', default_dt)
+
+
+def rank_chunks(w, rank, world):
+    """Chunks whose particles rank `rank` owns, and the cut planes (absolute leaf-block x) of `world` slabs."""
+    ch = w['chunks']
+    if world == 1:
+        return ch, []
+    if hasattr(ch[0], 'rank'):
+        mine = [c for c in ch if c.rank == rank]
+        cut_cells = w['cut_cells']
     else:
-        raise ValueError(name)
-    n_side = int(round(side * res))
-    n_each = n_side**3 * 8               # 8 particles per cell
-    lo_e = np.array([0.5 - side / 2, 0.55, 0.5 - side / 2], np.float32)
-    lo_w = np.array([0.5 - side / 2, 0.15, 0.5 - side / 2], np.float32)
-    xe = rng.random((n_each, 3), dtype=np.float32)
-    xe *= np.float32(side)
-    xe += lo_e
-    xw = rng.random((n_each, 3), dtype=np.float32)
-    xw *= np.float32(side)
-    xw += lo_w
-    return dict(res=(res, ) * 3, gravity=(0, -20, 0), frame_dt=3e-3, parts=[(xe, 1), (xw, 0)],
-                n=2 * n_each, name=name)
+        per = len(ch) // world
+        assert per * world == len(ch), 'the scene splits into 2, 4, 8 or 16 slabs'
+        mine = ch[rank * per:(rank + 1) * per]
+        cut_cells = [w['cut_cells'][per * k - 1] for k in range(1, world)]
+    return mine, [(c + 2048) // 4 for c in cut_cells]
 
 
+# ------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
@@ -92,7 +215,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
@@ -120,65 +243,230 @@ def peaks():
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-def run_cpu_baseline(sample_name, steps, warmup):
-    """Times the C/OpenMP restatement (oracle/mpm_oracle.c) on the host cores."""
-    from oracle.c_oracle import COracle, build
+def measured_traffic(workload_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `workload_name`, from the committed
+    ncu --set full capture (profiles/traffic.json, written by tools/ncu_summary.py); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f)
+        e = t.get(workload_name, {}).get(kernel)
+        return None if e is None else {'bytes_per_launch': float(e['dram_bytes']), 'source': e.get('source')}
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ CPU arm
+def taichi_probe():
+    """if Taichi is ever importable the real MPMSolver on ti.cpu is the reference arm."""
+    try:
+        import taichi  # noqa: F401
+        return 'importable'
+    except Exception as e:
+        return f'absent ({type(e).__name__})'
+
+
+def run_cpu_baseline(sample_name, steps, warmup, preroll=None):
+    """Times the C/OpenMP restatement (oracle/mpm_oracle.c) on ALL host cores on a bounded sample of the workload.
+    The thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    from oracle.c_oracle import COracle, build, load
     build()
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    load().oracle_set_threads(int(cores))
     w = workload(sample_name)
-    o = COracle(w['res'])
-    o.set_gravity(w['gravity'])
-    for x, m in w['parts']:
-        o.add_particles(x, m)
-    dt = w['frame_dt'] / (int(w['frame_dt'] / o.default_dt) + 1)
-    for _ in range(warmup):
+    o = COracle(w['res'], unbounded=w['unbounded'])
+    o.set_gravity(list(w['gravity']))
+    for point, normal, surface, friction in w['colliders']:
+        o.add_surface_collider(point, normal, surface, friction)
+    for c in w['chunks']:
+        o.add_particles(c.positions(o.dx), c.material, velocity=c.velocity)
+    dt = substep_dt(w, o.default_dt)
+    pre = w['preroll'] if preroll is None else preroll
+    t0 = time.perf_counter()
+    for _ in range(pre + warmup):
         o.substep(dt)
+    t_pre = time.perf_counter() - t0
     t0 = time.perf_counter()
     for _ in range(steps):
         o.substep(dt)
     el = time.perf_counter() - t0
     return dict(value=w['n'] * steps / el, unit='particle-substeps/s', cores=COracle.num_threads(), kind='port',
-                sample=f"{sample_name}: {w['n']} particles (same scene and 8 particles/cell as the workload, "
-                       f"cube side 0.16), {steps} substeps after {warmup} warm-up, oracle/mpm_oracle.c with "
-                       f"OpenMP; CPU restatement of the reference, not Taichi"), el / steps * 1e3, w
+                sample=f"{sample_name}: {w['n']} particles of the workload's scene (same materials, density, velocities, "
+                       f"floor; a thin z-slice between two slip planes for the multi-material scene), {steps} timed "
+                       f"substeps after {pre} pre-roll + {warmup} warm-up substeps ({t_pre:.1f} s), "
+                       f"oracle/mpm_oracle.c with OpenMP on {COracle.num_threads()} threads; CPU restatement of the "
+                       f"reference, not Taichi ({taichi_probe()})"), el / steps * 1e3, w, o
 
 
 def main_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    base, ms, w = run_cpu_baseline('cube_drop_sample', max(args.steps, 1), max(args.warmup, 1))
+    name = args.workload
+    sample = {'multimat_100m': 'multimat_sample', 'multimat_12m': 'multimat_sample', 'cube_drop_4m': 'cube_drop_4m',
+              'multimat_tiny': 'multimat_tiny'}.get(name, name)
+    base, ms, w, _ = run_cpu_baseline(sample, max(args.steps, 1), max(args.warmup, 1))
     line = {
         'impl': 'reference', 'metric': 'particle-substeps/sec', 'value': base['value'],
         'unit': 'particle-substeps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        'config': {'workload': 'configs[1] 3D cube drop res 256^3 WATER+ELASTIC, bounded sample '
-                               f"({w['n']} particles)"},
-        'cpu_baseline': base,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if args.gpus > 1 else 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload(name)['label']},
+        'cpu_baseline': base, 'taichi': taichi_probe(),
         'e2e': {'value': base['value'], 'unit': 'particle-substeps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ GPU arm
+quiet = contextlib.redirect_stdout(io.StringIO())
+
+
+def make_solver(w, world, rank, local, args, cuts):
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    kw = dict(res=w['res'], size=1, unbounded=w['unbounded'], device=local, use_g2p2g=args.g2p2g, quant=args.quant)
+    with quiet:
+        if world == 1:
+            s = MPMSolver(**kw)
+        else:
+            from taichi_elements_b200.distributed import DistributedMPMSolver
+            per_rank = w['n'] // world
+            # a face of the slab in leaf blocks bounds the shared column; leavers per substep are a small
+            # fraction of a face layer of particles
+            face_blocks = 1 << 15
+            s = DistributedMPMSolver(cuts=cuts, mig_capacity=max(1 << 15, per_rank // 256),
+                                     halo_capacity=face_blocks, substep_batch=args.batch,
+                                     comm=os.environ.get('MPM_COMM', 'auto'), **kw)
+    s.set_gravity(w['gravity'])
+    for point, normal, surface, friction in w['colliders']:
+        s.add_surface_collider(point, normal, surface, friction)
+    return s
+
+
+def seed(s, chunks, world, host_cache=None):
+    """add_particles for every chunk of this rank (host arrays in); returns the host arrays."""
+    out = []
+    for i, c in enumerate(chunks):
+        x = host_cache[i] if host_cache is not None else c.positions(s.dx)
+        if world == 1:
+            s.add_particles(x, c.material, velocity=c.velocity)
+        else:
+            s.add_local_particles(x, c.material, velocity=c.velocity, id_base=c.id_base)
+        out.append(x)
+    return out
+
+
+def timed_run(s, dt, args, dev, world, local, min_repeats=1):
+    """W warm-up substeps, then `repeats` x [exactly K substeps between two CUDA events on the solver's stream,
+    bracketed by barrier + synchronize]; the reported time is the MEDIAN repeat, each repeat the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    s._lib.mpm_set_profiling(s._ctx, 0)
+    s._run_substeps(dt, args.warmup)
+    barrier()
+    times, launches, st = [], 0, None
+    with ClockSampler(local) as clk:
+        t_begin = time.perf_counter()
+        while True:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(stream)
+            st = s._run_substeps(dt, args.steps)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            t = torch.tensor([ms, time.perf_counter() - t_begin], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t[0].item()))
+            launches = int(st.launches)
+            if len(times) >= max(min_repeats, args.repeats) or \
+                    (args.repeats == 0 and float(t[1].item()) >= args.min_seconds and len(times) >= 3) or len(times) >= 50:
+                break
+    return times, launches, st, clk.summary()
+
+
+def phase_times(s, dt, steps):
+    """Per-phase CUDA-event times (five records per substep on the kernels' stream; they serialise the PDL
+    chain, so this is a separate pass after the timed one)."""
+    s._lib.mpm_set_profiling(s._ctx, 1)
+    st = s._run_substeps(dt, steps)
+    s._lib.mpm_set_profiling(s._ctx, 0)
+    return {'sort+structure': st.ms_sort, 'p2g': st.ms_p2g, 'grid_op': st.ms_grid, 'g2p': st.ms_g2p}
+
+
+def parity_check(local, args):
+    """Untimed: ONE substep of a sub-box of the benchmarked scene (multimat_tiny: same materials, velocities and
+    floor) on the GPU against oracle/mpm_oracle.c, after a short pre-roll on both; per-particle relative errors."""
+    from oracle.c_oracle import COracle, build
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    build()
+    w = workload('multimat_tiny')
+    with quiet:
+        s = MPMSolver(res=w['res'], unbounded=True, device=local, use_g2p2g=False)
+    o = COracle(w['res'], unbounded=True)
+    for obj in (s, o):
+        obj.set_gravity(list(w['gravity']))
+        for point, normal, surface, friction in w['colliders']:
+            obj.add_surface_collider(point, normal, surface, friction)
+        for c in w['chunks']:
+            obj.add_particles(c.positions(1.0 / 256), c.material, velocity=c.velocity)
+    dt = o.default_dt
+    pre = 12
+    for _ in range(pre):
+        o.substep(dt)
+    s._run_substeps(dt, pre)
+    # one substep from the SAME state: inject the oracle's state into the solver
+    s._inject_state(o.x, o.v, o.F, o.C, o.Jp, o.material, o.color)
+    o.substep(dt)
+    s._run_substeps(dt, 1)
+
+    def rel(a, b, floor):
+        a = np.asarray(a, np.float64).reshape(len(a), -1)
+        b = np.asarray(b, np.float64).reshape(len(b), -1)
+        return float((np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), floor)).max())
+
+    vs = float(np.abs(o.v).max())
+    return {'scene': 'multimat_tiny (sub-box of the workload)', 'particles': int(o.n_particles), 'pre_roll_substeps': pre,
+            'one_substep_rel_err': {'x': rel(s.x.to_numpy(), o.x, 1e-3), 'v': rel(s.v.to_numpy(), o.v, 1e-3 * vs),
+                                    'F': rel(s.F.to_numpy(), o.F, 1e-3)},
+            'tolerance': 1e-4, 'oracle': 'oracle/mpm_oracle.c (parity unpinned: no Taichi)'}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cube_drop_4m')
+    ap.add_argument('--workload', default='multimat_100m')
+    ap.add_argument('--repeats', type=int, default=0, help='timed repeats of K steps (0: until --min-seconds, >= 3)')
+    ap.add_argument('--min-seconds', type=float, default=1.5)
+    ap.add_argument('--batch', type=int, default=20, help='N > 1: substeps enqueued per host synchronisation')
+    ap.add_argument('--preroll', type=int, default=-1, help='untimed substeps before the warm-up (-1: the workload\'s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--g2p2g', action='store_true', help='time the use_g2p2g=True mode (N = 1)')
-    ap.add_argument('--strong', action='store_true', help='N > 1: split the N=1 scene over the ranks (strong scaling)')
+    ap.add_argument('--no-weak', action='store_true', help='N > 1: skip the configs[4] weak-scaling brick')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--g2p2g', action='store_true', help='time the use_g2p2g=True mode')
+    ap.add_argument('--quant', action='store_true', help='time the quant=True storage')
     args = ap.parse_args()
     if args.impl == 'reference':
         return main_reference(args)
 
     import torch
     import torch.distributed as dist
-    from taichi_elements_b200.engine.mpm_solver import MPMSolver
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -188,198 +476,192 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
-
-    w = workload(args.workload, rank=rank, world=world)
-    import contextlib
-    import io
-    quiet = contextlib.redirect_stdout(io.StringIO())
-
-    def make_solver():
-        with quiet:
-            if world == 1:
-                s = MPMSolver(res=w['res'], size=1, unbounded=False, device=local, use_g2p2g=args.g2p2g)
-            else:
-                from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
-                res = w['res'][0]
-                if args.strong:
-                    allx = np.concatenate([x[:, 0] for x, _ in w['parts']])
-                    cuts = SlabDecomposition.balanced_cuts(allx, world, 4, 4096, float(res))
-                else:
-                    cuts = [int((math.floor((x0 + side * k) * res) + 2048) // 4) for k in range(1, world)]
-                s = DistributedMPMSolver(res=w['res'], cuts=cuts, size=1, unbounded=False, device=local,
-                                         mig_capacity=1 << 14 if not args.strong else 1 << 16,
-                                         halo_capacity=1 << 11 if not args.strong else 1 << 13, substep_batch=20,
-                                         comm=os.environ.get('MPM_COMM', 'auto'))
-                s.reserve_blocks(1 << 16)
-        s.set_gravity(w['gravity'])
-        return s
-
-    # N > 1: weak scaling -- one brick of the N=1 scene per rank, bricks contiguous along x so that
-    # every cut carries a shared grid column and migrating particles; every rank builds the same
-    # particle list and keeps its slab
-    import math
-    side = 0.25
-    x0 = 0.5 - side * world / 2
-    if world == 1 or args.strong:
-        bricks = [w['parts']]
-    else:
-        bricks = []
-        for r in range(world):
-            wr = workload(args.workload, rank=r, world=world)
-            shift = np.array([x0 + side * r - (0.5 - side / 2), 0, 0], np.float32)
-            bricks.append([(x + shift, m) for x, m in wr['parts']])
-    mpm = make_solver()
-    for parts in bricks:
-        for x, m in parts:
-            mpm.add_particles(x, m)
-    n_local = mpm.n_particles[None]
-    if world > 1:
-        mpm.reserve_blocks(max(1 << 16, n_local // 128))   # block capacity cannot grow inside a distributed batch
-    dt = w['frame_dt'] / (int(w['frame_dt'] / mpm.default_dt) + 1)
-    if w['res'][0] != 256:
-        dt = mpm.default_dt
-    lib, ctx = mpm._lib, mpm._ctx
-    stream = torch.cuda.current_stream(dev)
+    peak, peak_src = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    lib.mpm_set_profiling(ctx, 0)
-    mpm._run_substeps(dt, args.warmup)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record(stream)
-        st = mpm._run_substeps(dt, args.steps)
-        e1.record(stream)
-        barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = int(st.launches)
-    # per-phase CUDA events (five records per substep on the kernels' stream) perturb the stream, so the
-    # phase times come from a second, untimed-for-`value` pass of the same length right after
-    if world == 1:
-        lib.mpm_set_profiling(ctx, 1)
-        st = mpm._run_substeps(dt, args.steps)
-        lib.mpm_set_profiling(ctx, 0)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total = float(t.item())
-    n_total = int(cnt.item())
-    value = n_total * args.steps / (ms_total * 1e-3)
-    ms_per_step = ms_total / args.steps
-    lib.mpm_set_profiling(ctx, 0)
+    def allsum(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
-    # ---------------- roofline of the dominant kernel (P2G) ----------------
-    peak, peak_src = peaks()
+    # ---------------- the headline workload: device-resident throughput (`value`) ----------------
+    w = workload(args.workload, world)
+    chunks, cuts = rank_chunks(w, rank, world)
+    mpm = make_solver(w, world, rank, local, args, cuts)
+    if world > 1:
+        mpm.reserve_blocks(max(1 << 16, int(sum(c.n for c in chunks) // 160)))
+    host_parts = seed(mpm, chunks, world)
+    n_local = mpm.n_particles[None]
+    n_total = int(allsum(n_local))
+    assert n_total == w['n'], (n_total, w['n'])
+    dt = substep_dt(w, mpm.default_dt)
+    preroll = w['preroll'] if args.preroll < 0 else args.preroll
+    mpm._run_substeps(dt, preroll)
+    times, launches, st, clocks = timed_run(mpm, dt, args, dev, world, local)
+    ms_total = float(np.median(times))
+    ms_per_step = ms_total / args.steps
+    value = n_total * args.steps / (ms_total * 1e-3)
+    n_after = int(allsum(mpm.n_particles[None]))
+
+    # ---------------- roofline of the dominant kernel ----------------
+    phases = phase_times(mpm, dt, args.steps) if world == 1 else None
     cells_active = int(st.n_grid_blocks) * 64
-    b_alg_p2g = B_P2G_PARTICLE * n_local + B_P2G_CELL * cells_active
-    b_alg_step = B_PARTICLE * n_local + B_CELL * cells_active
-    phases = {'sort+structure': st.ms_sort, 'p2g': st.ms_p2g, 'grid_op': st.ms_grid, 'g2p': st.ms_g2p}
-    dom = max(phases, key=phases.get)
-    achieved = b_alg_p2g / (st.ms_p2g * 1e-3) / 1e9 if st.ms_p2g > 0 else 0.0
-    if world > 1:   # phase API: no per-kernel events; report the whole substep per GPU
-        achieved = b_alg_step / (ms_per_step * 1e-3) / 1e9
-    roofline = {
-        'bound': 'hbm', 'kernel': 'k_p2g3<640,4>' if world == 1 else 'whole substep, per GPU (no per-kernel events in the multi-GPU phase path)',
-        'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-        'frac': achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of k_p2g3<640,4> on this workload, one ncu --set full
-        # capture (profiles/r01_ncu_final_v6.md): 471.3 MB + 157.9 MB per launch
-        'traffic': 629.2e6 if (args.workload == 'cube_drop_4m' and world == 1) else None,
-        'peak_source': peak_src,
-        'algorithmic_bytes_per_launch': b_alg_p2g,
-        'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
-        'kernel_ms_note': 'CUDA events on the kernels\' stream, second pass of the same K steps right after the timed one '
-                          '(five event records per substep serialise the PDL chain, so they are kept out of `value`)',
-        'substep': {'algorithmic_bytes': b_alg_step,
-                    'achieved': b_alg_step / (ms_per_step * 1e-3) / 1e9 if world == 1 else None,
-                    'frac': b_alg_step / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None},
-    }
+    n_now = mpm.n_particles[None]
+    bpp = B_G2P2G_PARTICLE if args.g2p2g else B_PARTICLE
+    b_alg_p2g = B_P2G_PARTICLE * n_now + B_P2G_CELL * cells_active
+    b_alg_step = bpp * n_now + B_CELL * cells_active
+    if world == 1:
+        dom = max(phases, key=phases.get)
+        kname = 'k_p2g3<640,4>'
+        achieved = b_alg_p2g / (phases['p2g'] * 1e-3) / 1e9 if phases['p2g'] > 0 else 0.0
+        traffic = measured_traffic(args.workload, 'k_p2g3')
+        roofline = {
+            'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': traffic['bytes_per_launch'] if traffic else None,
+            'traffic_source': traffic['source'] if traffic else 'no ncu capture committed for this workload',
+            'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_alg_p2g,
+            'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
+            'kernel_ms_note': 'CUDA events on the kernels\' stream, separate pass of K steps right after the timed ones '
+                              '(five event records per substep serialise the PDL chain, so they are kept out of `value`)',
+            'substep': {'algorithmic_bytes': b_alg_step, 'achieved': b_alg_step / (ms_per_step * 1e-3) / 1e9,
+                        'frac': b_alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
+                        'frac_of_nominal_8TBs': b_alg_step / (ms_per_step * 1e-3) / 1e9 / 8000.0},
+        }
+    else:
+        # whole job: sum over ranks of the algorithmic bytes / max-over-ranks time, against N x peak
+        b_job = allsum(b_alg_step)
+        achieved = b_job / (ms_per_step * 1e-3) / 1e9
+        roofline = {
+            'bound': 'hbm', 'kernel': 'whole substep, all ranks (per-kernel events are a single-GPU pass)',
+            'achieved': achieved, 'peak': peak * world, 'unit': 'GB/s', 'frac': achieved / (peak * world),
+            'traffic': None, 'peak_source': peak_src + f' x {world} GPUs', 'algorithmic_bytes_per_launch': b_job,
+        }
 
     # ---------------- end to end through the public API, host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        frames = max(1, min(3, args.steps // 40))
-        # N > 1: the inputs of a rank are the rows of its slab (own brick plus the few boundary rows of the
-        # neighbouring bricks whose base block falls on this side of the cut), selected once, outside the timed region
-        if world == 1:
-            host_parts = [(torch.from_numpy(x).pin_memory().numpy(), m) for parts in bricks for x, m in parts]
-        else:
-            host_parts = []
-            for parts in bricks:
-                for x, m in parts:
-                    rows = x[mpm.slab.mine(x[:, 0])]
-                    if len(rows):
-                        host_parts.append((torch.from_numpy(np.ascontiguousarray(rows)).pin_memory().numpy(), m))
-        sub_per_frame = 0
-        with quiet:
-            mpm2 = mpm
-            mpm2.clear_particles()
-            keep = []
-            for _ in range(2):             # warm-up of the same path (also warms the pinned-buffer cache)
-                mpm2.clear_particles()
-                for x, m in host_parts:
-                    mpm2.add_particles(x, m)
-                mpm2.step(w['frame_dt'])
-                if world > 1:
-                    mpm2.flush_migration()
-                keep.append(mpm2.particle_info())
-            del keep
-        barrier()
-        t0 = time.perf_counter()
-        d2h = 0
-        with quiet:
-            for _ in range(frames):
-                mpm2.clear_particles()
-                for x, m in host_parts:
-                    mpm2.add_particles(x, m)
-                before = mpm2.total_substeps
-                mpm2.step(w['frame_dt'])
-                sub_per_frame = mpm2.total_substeps - before
-                if world > 1:
-                    mpm2.flush_migration()
-                info = mpm2.particle_info()      # N > 1: this rank's particles (position, velocity, material, color, id)
-                d2h = sum(a.nbytes for a in info.values())
-        barrier()
-        el = time.perf_counter() - t0
-        te = torch.tensor([el, float(d2h)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        el, d2h = float(te[0].item()), float(te[1].item())
-        h2d = sum(x.nbytes for x, _ in host_parts)                  # this rank's rows
-        e2e = {'value': n_total * sub_per_frame * frames / el, 'unit': 'particle-substeps/s',
-               'h2d_bytes_per_step': h2d / sub_per_frame, 'd2h_bytes_per_step': d2h / sub_per_frame,
-               'what': f'{frames} x [clear_particles, add_particles(host arrays), step({w["frame_dt"]}) = '
-                       f'{sub_per_frame} substeps, particle_info()] through MPMSolver (N > 1: DistributedMPMSolver, each rank its slab); wall clock incl. copies'}
+        e2e = run_e2e(mpm, w, chunks, host_parts, world, dev, args, n_total)
+    del host_parts
+
+    # ---------------- N > 1: the configs[4] weak-scaling brick at the same N ----------------
+    weak = None
+    if not args.no_weak and args.workload == 'multimat_100m':
+        del mpm
+        torch.cuda.empty_cache()
+        weak = run_weak(world, rank, local, dev, args, peak)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _, _ = run_cpu_baseline('cube_drop_sample', 8, 2)
+    parity = None
+    if rank == 0 and world == 1:
+        if not args.no_parity:
+            parity = parity_check(local, args)
+        if not args.no_cpu_baseline:
+            sample = {'multimat_100m': 'multimat_sample', 'multimat_12m': 'multimat_sample'}.get(args.workload, args.workload)
+            if sample == 'cube_drop_4m':
+                sample = 'cube_drop_sample'
+            cpu, _, _, _ = run_cpu_baseline(sample, 8, 2)
 
     if rank == 0:
+        mode = 'use_g2p2g=True (fused g2p2g kernel, SURVEY 8(f)1)' if args.g2p2g else 'default (split p2g / g2p)'
+        if args.quant:
+            mode += ', quant=True (bit-packed particle storage, SURVEY 8(f)2)'
         line = {
             'metric': 'particle-substeps/sec', 'value': value, 'unit': 'particle-substeps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f"configs[1] 3D cube drop, res 256^3 bounded, {n_total} particles "
-                                   f"(ELASTIC cube over WATER cube, 8 per cell), g=(0,-20,0), dt=3e-3/39"
-                                   if args.workload == 'cube_drop_4m' else args.workload,
-                       'mode': 'use_g2p2g=True (fused order, SURVEY 8(f)1)' if args.g2p2g else 'default (split p2g / g2p)',
-                       'particles_per_gpu': n_local, 'l2': 'inputs (2 x 116 B x N particle state) exceed L2',
-                       'active_blocks': int(st.n_grid_blocks), 'particle_blocks': int(st.n_particle_blocks)},
-            'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches,
-            'gpu_launches_note': 'own kernels: 9 per substep inside a batch (scan, rank, scan, scatter, finish, clear, p2g, grid op, g2p), 10 for its first substep, + 2 per batch; more with slabs',
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'scaling': 'strong' if world > 1 and not hasattr(w['chunks'][0], 'rank') else 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': w['label'], 'mode': mode, 'particles': n_total, 'particles_per_gpu': n_local,
+                       'pre_roll_substeps': preroll, 'particles_after': n_after,
+                       'l2': 'inputs (2 x 116 B x N particle state) exceed L2; no flush needed',
+                       'active_blocks': int(st.n_grid_blocks), 'particle_blocks': int(st.n_particle_blocks),
+                       'max_velocity': float(st.max_velocity),
+                       'timing': f'median of {len(times)} repeats of exactly {args.steps} substeps (CUDA events, max over '
+                                 f'ranks per repeat)', 'ms_per_step_repeats': [round(t / args.steps, 5) for t in times]},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+            'gpu_launches_note': 'own kernels enqueued for the K timed substeps of one repeat (9 per substep inside a batch, '
+                                 '+1 for its first, +2 per batch; one more per substep with slabs)',
+            'roofline': roofline, 'cpu_baseline': cpu, 'parity_check': parity, 'weak_cfg5': weak,
+            'taichi': taichi_probe(),
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_e2e(mpm, w, chunks, host_parts, world, dev, args, n_total):
+    """The same metric through the public API with HOST buffers: every frame = clear_particles, add_particles of this
+    rank's chunks from pinned host arrays (H2D), step(frame_dt) (the reference's host loop), particle_info() (D2H
+    into fresh arrays).  Wall clock, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    pinned = [torch.from_numpy(x).pin_memory().numpy() for x in host_parts]
+    frames = 2
+    sub_per_frame, d2h = 0, 0
+    with quiet:
+        for it in range(1 + frames):          # first frame: warm-up of the same path (pinned-buffer cache, growth)
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            mpm.clear_particles()
+            seed(mpm, chunks, world, host_cache=pinned)
+            before = mpm.total_substeps
+            mpm.step(w['frame_dt'])
+            sub_per_frame = mpm.total_substeps - before
+            if world > 1:
+                mpm.flush_migration()
+            info = mpm.particle_info()
+            d2h = sum(a.nbytes for a in info.values())
+            del info
+    barrier()
+    el = time.perf_counter() - t0
+    te = torch.tensor([el, float(d2h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    el, d2h = float(te[0].item()), float(te[1].item())
+    h2d = sum(x.nbytes for x in pinned)
+    return {'value': n_total * sub_per_frame * frames / el, 'unit': 'particle-substeps/s',
+            'h2d_bytes_per_step': h2d / sub_per_frame, 'd2h_bytes_per_step': d2h / sub_per_frame,
+            'what': f'{frames} x [clear_particles, add_particles(host chunks), step({w["frame_dt"]}) = {sub_per_frame} '
+                    f'substeps from the seeded state, particle_info()] through '
+                    f'{"MPMSolver" if world == 1 else "DistributedMPMSolver (each rank its slab)"}; wall clock incl. copies, '
+                    f'bytes per rank'}
+
+
+def run_weak(world, rank, local, dev, args, peak):
+    import torch
+    import torch.distributed as dist
+    w = workload('brick_125m', world)
+    chunks, cuts = rank_chunks(w, rank, world)
+    s = make_solver(w, world, rank, local, args, cuts)
+    if world > 1:
+        s.reserve_blocks(1 << 19)
+    seed(s, chunks, world)
+    n_local = s.n_particles[None]
+    t = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    n_total = int(t.item())
+    dt = substep_dt(w, s.default_dt)
+    s._run_substeps(dt, w['preroll'])
+    times, launches, st, clocks = timed_run(s, dt, args, dev, world, local)
+    ms = float(np.median(times)) / args.steps
+    value = n_total / (ms * 1e-3)
+    b = B_PARTICLE * n_total + B_CELL * int(st.n_grid_blocks) * 64 * world
+    return {'workload': w['label'], 'scaling': 'weak', 'value': value, 'unit': 'particle-substeps/s', 'ms_per_step': ms,
+            'particles': n_total, 'particles_per_gpu': n_local, 'pre_roll_substeps': w['preroll'],
+            'roofline_frac_substep': b / (ms * 1e-3) / 1e9 / (peak * world), 'clocks': clocks,
+            'ms_per_step_repeats': [round(x / args.steps, 5) for x in times]}
 
 
 if __name__ == '__main__':

@@ -44,6 +44,8 @@ def load():
         _lib = ctypes.CDLL(LIB)
         _lib.oracle_num_threads.restype = ctypes.c_int
         _lib.oracle_substep.restype = ctypes.c_int
+        _lib.oracle_set_threads.argtypes = [ctypes.c_int]
+        _lib.oracle_set_threads.restype = None
     return _lib
 
 

@@ -47,6 +47,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* explicit thread count: launchers such as torchrun export OMP_NUM_THREADS=1 */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ---- ti.svd restated ----------------------------------------------------- */
 static void svd2(const float* F, float* U, float* sig, float* V) {
   /* Taichi's closed form, SURVEY.md Appendix B */

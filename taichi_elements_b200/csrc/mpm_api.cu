@@ -5,6 +5,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -523,30 +524,41 @@ static int update_layout(mpm_ctx* ctx) {
   return MPM_OK;
 }
 
+// Launch configuration of one kernel instance, per device: the dynamic shared-memory opt-in
+// (cudaFuncSetAttribute) and the occupancy-derived persistent grid apply to the CURRENT device only, and a
+// process may drive several GPUs from several host threads (one ctx per device).
+static constexpr int MAX_DEVICES = 64;
+struct LaunchCache {
+  std::atomic<int> grid[MAX_DEVICES];
+  LaunchCache() { for (auto& g : grid) g.store(0); }
+};
+template <typename K>
+static int cached_grid(LaunchCache& lc, mpm_ctx* ctx, K kernel, int threads, size_t smem) {
+  const int dev = std::min(std::max(ctx->P.device, 0), MAX_DEVICES - 1);
+  int g = lc.grid[dev].load(std::memory_order_acquire);
+  if (g) return g;
+  int occ = 1;
+  if (smem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+  g = ctx->sm_count * std::max(occ, 1);
+  lc.grid[dev].store(g, std::memory_order_release);   // racing threads compute the same value
+  return g;
+}
+
 // P2G (cell-owner) launch configurations: particles staged per pass, CTAs per SM; MPM_P2G_CFG picks one.
 template <int D, int CH, int MB>
 static void launch_p2g_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
-  static int grid = 0;
+  static LaunchCache lc;
   constexpr size_t smem = p2g_smem_bytes<D, CH>();
-  if (!grid) {
-    int occ = 1;
-    cudaFuncSetAttribute(k_p2g_cell<D, CH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_cell<D, CH, MB>, P2GCfg<D>::THREADS, smem);
-    grid = ctx->sm_count * std::max(occ, 1);
-  }
+  const int grid = cached_grid(lc, ctx, k_p2g_cell<D, CH, MB>, P2GCfg<D>::THREADS, smem);
   k_p2g_cell<D, CH, MB><<<grid, P2GCfg<D>::THREADS, smem, s>>>(a);
 }
 // third revision (mpm_p2g3.cuh): 3D, needs the counting sort's per-cell bucket starts
 template <int CH, int MB>
 static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t s) {
-  static int grid = 0;
+  static LaunchCache lc;
   constexpr size_t smem = p2g3_smem_bytes<CH>();
-  if (!grid) {
-    int occ = 1;
-    cudaFuncSetAttribute(k_p2g3<CH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g3<CH, MB>, P2G3::T, smem);
-    grid = ctx->sm_count * std::max(occ, 1);
-  }
+  const int grid = cached_grid(lc, ctx, k_p2g3<CH, MB>, P2G3::T, smem);
   launch_chain(ctx->pdl, k_p2g3<CH, MB>, grid, P2G3::T, smem, s, a);
 }
 template <int D>
@@ -577,12 +589,8 @@ static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
 // G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
 template <int D, int T, int MB>
 static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
-  static int grid = 0;
-  if (!grid) {
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<D, T, MB>, T, 0);
-    grid = ctx->sm_count * std::max(occ, 1);
-  }
+  static LaunchCache lc;
+  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB>, T, 0);
   launch_chain(ctx->pdl, k_g2p<D, T, MB>, grid, T, 0, s, a);
 }
 template <int D>
@@ -1326,6 +1334,9 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
   if (!dst_dev) return MPM_E_INVALID;
   CK(cudaSetDevice(ctx->P.device));
   const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
+  // rows whose id is not present (ids that are not a permutation of [0, n): the distributed solver's
+  // global ids) read as zero instead of uninitialised memory
+  CK(cudaMemsetAsync(dst_dev, 0, (size_t)(end - begin) * nwords * 4, (cudaStream_t)stream));
   if (ctx->K.g2p2g && ctx->have_pending) {
     // F and Jp were already advanced by the pending scatter half (see k_gather_rows_pending)
     cudaStream_t s = (cudaStream_t)stream;

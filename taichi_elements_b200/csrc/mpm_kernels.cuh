@@ -1239,6 +1239,7 @@ __global__ void k_pack_particles(const uint32_t* __restrict__ state, size_t cap,
   using FL = Fld<D>;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
     const uint32_t id = ldu(state, cap, FL::ID, s);
+    if (id >= (uint32_t)n) continue;   // ids are a permutation of [0, n) on a single-device solver; never write outside
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       // ((a - lo) * (1 / (hi - lo)) * (2^bits - 1) + 0.499).astype(uint32), every step rounded to f32 (:50-55)
@@ -1280,6 +1281,7 @@ __global__ void k_debug_binning(const uint32_t* __restrict__ state, size_t cap, 
   using G = Geo<D>;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
     uint32_t id = ldu(state, cap, Fld<D>::ID, p);
+    if (id >= (uint32_t)n) continue;
 #pragma unroll
     for (int d = 0; d < D; ++d)
       out[(size_t)id * D + d] = (base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + half) >> G::LOG_LEAF;

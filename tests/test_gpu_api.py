@@ -284,30 +284,3 @@ def test_conservation_over_1000_substeps():
     assert np.abs(p1 - p0).max() < 1e-3 * scale          # APIC transfers conserve linear momentum
     assert e1 < e0 * 1.001 and np.isfinite(e1)           # kinetic energy does not grow (it feeds strain energy)
     assert s.n_particles[None] == 4000 and np.isfinite(s.x.to_numpy()).all()
-
-
-def test_full_size_properties():
-    """BASELINE config sizes: properties that need no oracle (4.19 M particles)."""
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from bench import workload
-    w = workload('cube_drop_4m')
-    s = _solver(res=w['res'])
-    s.set_gravity(w['gravity'])
-    for x, mat in w['parts']:
-        s.add_particles(x, mat)
-    n = s.n_particles[None]
-    assert n == 4194304
-    dt = 3e-3 / 39
-    s._run_substeps(dt, 3)
-    pb, cnt, gb = s.debug_blocks()
-    assert cnt.sum() == n and len(np.unique(pb, axis=0)) == len(pb)       # every particle binned once
-    gbs = {tuple(b) for b in gb}
-    assert all(tuple(b) in gbs for b in pb)                               # particle blocks are active blocks
-    cells, gv, gm = s.debug_grid()
-    mass = s.p_mass * n
-    assert abs(gm.sum(dtype=np.float64) - mass) < 1e-4 * mass            # P2G conserves mass at full size
-    v = s.v.to_numpy()
-    assert np.allclose(v[:, 1], -20 * 3 * dt, atol=2e-4) and np.abs(v[:, [0, 2]]).max() < 2e-4   # free fall
-    ids = np.sort(s.x.to_numpy()[:, 1])                                   # read-back restores insertion order
-    assert np.array_equal(s.material.to_numpy()[:n // 2], np.ones(n // 2, np.int32)) and ids[0] > 0.1

@@ -1,0 +1,273 @@
+"""Parity cases added in round 2 (VERDICT r01 "close the parity holes"): the bounding box on all six
+faces (bounded and unbounded), a configs[2]-style SNOW/SAND scene against friction planes over 50 substeps,
+one full-size configs[1] substep and a slice of configs[3] against the C oracle, restart / emitter round trips.
+All through the C ABI (ctypes) on the GPU; oracles are test infrastructure."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from scenes import state_errors, tracking_errors
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_ONE = 1e-4
+TOL_MANY = 5e-3
+
+
+def _pair(res, unbounded=False, oracle='numpy', **kw):
+    from oracle.mpm_oracle import OracleMPM
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    if oracle == 'c':
+        from oracle.c_oracle import COracle
+        o = COracle((res, ) * 3, unbounded=unbounded, **kw)
+    else:
+        o = OracleMPM((res, ) * 3, unbounded=unbounded, **kw)
+    s = MPMSolver((res, ) * 3, unbounded=unbounded, **kw)
+    return o, s
+
+
+def _grid_match(s, o, tol):
+    """Every cell the oracle touched exists on the GPU with the same mass and velocity (after the grid op)."""
+    cells, gv, gm = s.debug_grid()
+    key = {tuple(c): i for i, c in enumerate(o.grid_cells)}
+    idx = np.array([key.get(tuple(c), -1) for c in cells])
+    touched = idx >= 0
+    assert touched.sum() == len(o.grid_cells) and np.all(gm[~touched] == 0)
+    np.testing.assert_allclose(gm[touched], o.grid_m[idx[touched]], rtol=2e-5, atol=1e-12)
+    vscale = max(1.0, float(np.abs(o.grid_v).max()))
+    assert float(np.abs(gv[touched] - o.grid_v[idx[touched]]).max()) <= tol * vscale
+    return cells[touched], gv[touched]
+
+
+def _face_blobs(res, centre_cells, n_per=350, seed=0, speed=2.0):
+    """One blob per entry of `centre_cells` (cell coordinates), moving away from the domain centre along the
+    axis on which it is closest to a face; five materials in turn."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k, (c, vel) in enumerate(centre_cells):
+        p = ((rng.random((n_per, 3)) - 0.5) * 3.0 + np.asarray(c, np.float64)) / res
+        out.append((p.astype(np.float32), k % 5, [speed * a for a in vel]))
+    return out
+
+
+def test_bounding_box_bounded_all_six_faces():
+    """grid_bounding_box (ref engine/mpm_solver.py:600-616), bounded: blobs sit INSIDE the padding zone of each of
+    the six faces (cells < 3 and >= res - 3) and move outwards; the velocity component towards the wall is zeroed on
+    the padding nodes.  One substep per-particle parity, the grid cell by cell, then 12 substeps of tracking."""
+    res = 32
+    blobs = _face_blobs(res, [((2.5, 16, 16), (-1, 0.2, 0)), ((29.5, 16, 10), (1, 0, 0.2)), ((16, 2.5, 16), (0.2, -1, 0)),
+                              ((10, 29.5, 16), (0, 1, 0.2)), ((16, 16, 2.5), (0, 0.2, -1)), ((16, 10, 29.5), (0.2, 0, 1)),
+                              ((2.6, 2.6, 2.6), (-1, -1, -1)), ((29.4, 29.4, 29.4), (1, 1, 1))], seed=31)
+    o, s = _pair(res)
+    for p, m, vel in blobs:
+        o.add_particles(p, m, velocity=vel)
+        s.add_particles(p, m, velocity=vel)
+    dt = o.default_dt
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    cells, gv = _grid_match(s, o, TOL_ONE)
+    # the clamp really acted: padding nodes carry no velocity towards their wall, and some node was clamped
+    for d in range(3):
+        lo, hi = cells[:, d] < 3, cells[:, d] >= res - 3
+        assert lo.any() and hi.any()
+        assert np.all(gv[lo, d] >= 0) and np.all(gv[hi, d] <= 0)
+        assert np.any(gv[lo, d] == 0) and np.any(gv[hi, d] == 0)
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    for _ in range(12):
+        o.substep(dt)
+    assert s._run_substeps(dt, 12).substeps_done == 12
+    err = tracking_errors(s, o)
+    assert max(err.values()) <= TOL_MANY, err
+
+
+@pytest.mark.parametrize('corner', [+1, -1])
+def test_bounding_box_unbounded_faces(corner):
+    """grid_bounding_box with unbounded=True: the walls are at +-(grid_size/2 - padding) cells of the 4096^3 virtual
+    domain (ref :604-611).  A blob in the (+,+,+) corner covers the three upper faces, one in (-,-,-) the lower
+    ones (both at once would need a key layout spanning the whole domain)."""
+    res, half = 32, 2048
+    c = (half - 4.5) if corner > 0 else (-half + 3.5)
+    blobs = _face_blobs(res, [((c, c, c), (corner, corner, corner)),
+                              ((c, c - corner * 6, c), (corner, 0.3 * corner, corner))], n_per=500, seed=32, speed=3.0)
+    o, s = _pair(res, unbounded=True)
+    for p, m, vel in blobs:
+        o.add_particles(p, 1 + m, velocity=vel)     # ELASTIC, SNOW
+        s.add_particles(p, 1 + m, velocity=vel)
+    assert np.array_equal(o.binning()[0].astype(np.int32), s.debug_binning())
+    dt = o.default_dt
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    cells, gv = _grid_match(s, o, TOL_ONE)
+    for d in range(3):
+        pad = cells[:, d] >= half - 3 if corner > 0 else cells[:, d] < -half + 3
+        assert pad.any() and np.all(corner * gv[pad, d] <= 0) and np.any(gv[pad, d] == 0)
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    for _ in range(8):
+        o.substep(dt)
+    assert s._run_substeps(dt, 8).substeps_done == 8
+    err = tracking_errors(s, o)
+    assert max(err.values()) <= TOL_MANY, err
+
+
+def _ellipsoid_points(rng, centre, radius, n):
+    pts = []
+    while sum(len(p) for p in pts) < n:
+        q = rng.random((2 * n, 3)) * 2 - 1
+        pts.append(q[(q * q).sum(1) <= 1])
+    q = np.concatenate(pts)[:n]
+    return (np.asarray(centre) + q * np.asarray(radius)).astype(np.float32)
+
+
+def test_config2_style_snow_sand_on_friction_planes_50_substeps():
+    """BASELINE configs[2] in small: unbounded domain, g = (0, -25, 0), the six slip planes with friction 0.5 of
+    ref demo/demo_3d_bunnies.py:76-107, SNOW and SAND ellipsoids launched at the floor, a wall and the floor/wall
+    edge at 5 m/s (ref :111-118): 50 substeps against the oracle, every particle on the SVD path and the
+    colliders in contact from about substep 10."""
+    res = 64
+    o, s = _pair(res, unbounded=True)
+    for m in (o, s):
+        m.set_gravity((0, -25, 0))
+        m.add_surface_collider((0, 0, 0), (0, 1, 0), 1, 0.5)
+        m.add_surface_collider((0, 1.9, 0), (0, -1, 0), 1, 0.5)
+        m.add_surface_collider((-1.9, 0, 0), (1, 0, 0), 1, 0.5)
+        m.add_surface_collider((1.9, 0, 0), (-1, 0, 0), 1, 0.5)
+        m.add_surface_collider((0, 0, -0.95), (0, 0, 1), 1, 0.5)
+        m.add_surface_collider((0, 0, 0.95), (0, 0, -1), 1, 0.5)
+    rng = np.random.default_rng(33)
+    r = 0.09
+    scene = [((0.3, r + 0.02, 0.1), 2, (0, -5, 0)), ((-0.3, r + 0.02, -0.2), 3, (0, -5, 0)),
+             ((-1.9 + r + 0.02, 0.6, 0.0), 3, (-5, 0, 0)), ((1.9 - r - 0.02, 0.5, 0.3), 2, (5, -1, 0)),
+             ((-1.9 + r + 0.03, r + 0.03, 0.95 - r - 0.03), 2, (-3, -3, 3)),
+             ((0.0, 0.45, 0.0), 3, (0, -5, 0)), ((0.0, 0.25, 0.0), 2, (0, 2, 0))]     # the last two collide in flight
+    for centre, mat, vel in scene:
+        p = _ellipsoid_points(rng, centre, (r, r * 0.8, r), 1500)
+        o.add_particles(p, mat, velocity=list(vel))
+        s.add_particles(p, mat, velocity=list(vel))
+    dt = o.default_dt
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    for _ in range(19):
+        o.substep(dt)
+    assert s._run_substeps(dt, 19).substeps_done == 19
+    err = tracking_errors(s, o)
+    assert max(err.values()) <= TOL_MANY, err
+    for _ in range(30):
+        o.substep(dt)
+    assert s._run_substeps(dt, 30).substeps_done == 30
+    err = tracking_errors(s, o)
+    # impacts + plastic flow amplify round-off: the two CPU restatements of this algorithm (NumPy and C/OpenMP,
+    # independent SVDs, different summation orders) are 3e-3 .. 5e-3 of max |v| apart at substep 50 of this scene
+    assert max(err.values()) <= 2e-2, err
+    # the planes acted: nothing moved below the floor / beyond the wall, and plastic flow happened
+    x = s.x.to_numpy()
+    assert x[:, 1].min() > -0.5 / res and x[:, 0].min() > -1.9 - 0.5 / res
+    jp = s.Jp.to_numpy()
+    mat = s.material.to_numpy()
+    assert np.abs(jp[mat == 2] - 1).max() > 1e-3 and np.abs(jp[mat == 3]).max() > 1e-4
+
+
+def test_config1_full_size_one_substep_against_c_oracle():
+    """BASELINE configs[1] at FULL size (4 194 304 particles, res 256^3): three substeps so that v, C and F are
+    non-trivial, then ONE substep from identical bits against oracle/mpm_oracle.c (dense 256^3 grid, OpenMP):
+    block structure bit-exact, x/v/F/C/Jp per particle within 1e-4; plus the invariants of the whole set."""
+    sys.path.insert(0, ROOT)
+    from bench import workload
+    w = workload('cube_drop_4m')
+    o, s = _pair(256, oracle='c')
+    for m in (o, s):
+        m.set_gravity(list(w['gravity']))
+    for c in w['chunks']:
+        x = c.positions(o.dx)
+        o.add_particles(x, c.material, velocity=list(c.velocity))
+        s.add_particles(x, c.material, velocity=list(c.velocity))
+    n = s.n_particles[None]
+    assert n == 4194304 == o.n_particles
+    assert np.array_equal(o.binning()[0].astype(np.int32), s.debug_binning())
+    dt = w['dt']
+    for _ in range(3):
+        o.substep(dt)
+    s._inject_state(o.x, o.v, o.F, o.C, o.Jp, o.material, o.color)
+    blk, _ = o.binning()
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    pb, cnt, gb = s.debug_blocks()
+    ub, uc = np.unique(blk, axis=0, return_counts=True)
+    order = np.lexsort(pb.T[::-1])
+    assert np.array_equal(pb[order], ub.astype(np.int32)) and np.array_equal(cnt[order], uc.astype(np.int32))
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    cells, gv, gm = s.debug_grid()
+    mass = s.p_mass * n
+    assert abs(gm.sum(dtype=np.float64) - mass) < 1e-4 * mass            # P2G conserves mass at full size
+    v = s.v.to_numpy()
+    assert np.allclose(v[:, 1], -20 * 4 * dt, atol=5e-4) and np.abs(v[:, [0, 2]]).max() < 5e-4   # free fall
+    assert np.array_equal(s.material.to_numpy()[:n // 2], np.ones(n // 2, np.int32))   # insertion order restored
+
+
+def test_config3_slice_in_contact_against_c_oracle():
+    """A z-slice of the benchmarked configs[3] scene (bench.py `multimat_sample`: 431 k particles, the four materials,
+    slip floor, colliding chunks): 40 substeps of pre-roll on the C oracle, then ONE substep from identical bits
+    (per-particle 1e-4) and ten more (tracking)."""
+    sys.path.insert(0, ROOT)
+    from bench import workload
+    w = workload('multimat_sample')
+    o, s = _pair(256, unbounded=True, oracle='c')
+    for m in (o, s):
+        m.set_gravity(list(w['gravity']))
+        for point, normal, surface, friction in w['colliders']:
+            m.add_surface_collider(point, normal, surface, friction)
+    for c in w['chunks']:
+        o.add_particles(c.positions(o.dx), c.material, velocity=list(c.velocity))
+    dt = o.default_dt
+    for _ in range(40):
+        o.substep(dt)
+    assert np.abs(o.F - np.eye(3, dtype=np.float32)).reshape(len(o.F), -1).max(axis=1).mean() > 1e-4   # deformed
+    s._inject_state(o.x, o.v, o.F, o.C, o.Jp, o.material, o.color)
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    err = state_errors(s, o)
+    assert max(err.values()) <= TOL_ONE, err
+    for _ in range(10):
+        o.substep(dt)
+    assert s._run_substeps(dt, 10).substeps_done == 10
+    err = tracking_errors(s, o)
+    assert max(err.values()) <= TOL_MANY, err
+
+
+def test_read_restart_and_emitter_id_round_trip():
+    """read_restart (ref :1106-1144) restores position, velocity, material and colour per particle; F, C, Jp restart
+    from the seeded values like the reference's recover_from_external_array; use_emitter_id exposes the id passed to
+    add_mesh (ref :1049-1079, 1181-1182)."""
+    from oracle.seeding_oracle import icosphere
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    a = MPMSolver((64, ) * 3, use_emitter_id=True)
+    rng = np.random.default_rng(34)
+    p = (rng.random((3000, 3)) * 0.3 + 0.3).astype(np.float32)
+    a.add_particles(p[:1000], a.material_sand, color=0x010203, velocity=(1, 0, 0))
+    a.add_particles(p[1000:], a.material_water, color=0x0A0B0C, velocity=(0, -2, 0))
+    a.add_mesh(icosphere((0.7, 0.7, 0.7), 0.08, 2), a.material_elastic, color=0x445566, velocity=(0, 0, 1), emmiter_id=7)
+    a.step(2e-3)
+    info = a.particle_info()
+    n = a.n_particles[None]
+    assert n > 3000 and set(info) == {'position', 'velocity', 'material', 'color', 'emitter_ids'}
+    assert np.all(info['emitter_ids'][:3000] == 0) and np.all(info['emitter_ids'][3000:] == 7)
+    b = MPMSolver((64, ) * 3)
+    b.read_restart(n, info['position'], info['velocity'], info['material'], info['color'])
+    got = b.particle_info()
+    assert b.n_particles[None] == n and 'emitter_ids' not in got
+    for k in ('position', 'velocity', 'material', 'color'):
+        assert np.array_equal(got[k], info[k]), k
+    assert np.array_equal(b.F.to_numpy(), np.tile(np.eye(3, dtype=np.float32), (n, 1, 1)))
+    assert np.all(b.Jp.to_numpy()[info['material'] == 3] == 0) and np.all(b.Jp.to_numpy()[info['material'] != 3] == 1)
+    b.step(1e-3)
+    assert np.isfinite(b.particle_info()['position']).all()
+    # a partial restart keeps the first `num_particles` rows (ref :1112-1116)
+    c = MPMSolver((64, ) * 3)
+    c.read_restart(500, info['position'], info['velocity'], info['material'], info['color'])
+    assert c.n_particles[None] == 500 and np.array_equal(c.particle_info()['position'], info['position'][:500])

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from scenes import build_pair, mixed_scene, state_errors
+from scenes import build_pair, mixed_scene, state_errors, tracking_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -99,7 +99,7 @@ def test_multi_substep_tracking(dim):
         o.substep(dt)
     st = s._run_substeps(dt, 20)     # one batch, one host sync
     assert st.substeps_done == 20
-    err = state_errors(s, o)
+    err = tracking_errors(s, o)
     assert max(err.values()) <= TOL_MANY, err
     assert np.isfinite(s.x.to_numpy()).all()
 
@@ -121,7 +121,7 @@ def test_dense_blocks_take_the_multi_chunk_path(dim):
     for _ in range(5):
         o.substep(dt)
     s._run_substeps(dt, 5)
-    err = state_errors(s, o)
+    err = tracking_errors(s, o)
     assert max(err.values()) <= TOL_MANY, err
 
 
