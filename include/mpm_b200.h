@@ -44,7 +44,7 @@ extern "C" {
 #define MPM_E_CUDA (-2)
 #define MPM_E_UNBOUND (-3)
 
-#define MPM_ABI_VERSION 2
+#define MPM_ABI_VERSION 3
 
 typedef struct mpm_ctx mpm_ctx;
 
@@ -216,6 +216,19 @@ int mpm_peer_open(mpm_ctx* ctx, int32_t side, const void* handle64);
 /* `count` substeps (or, deliver_only != 0, just the pending particle delivery) inside
  * mpm_batch_begin/mpm_batch_end; every rank must call it with the same arguments */
 int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t deliver_only, void* stream);
+/* Seeding and read-back with slabs (every rank makes the same add_* calls, or hands in pre-partitioned rows):
+ * mpm_seed_positions_slab: seed_from_external_array (:1081-1095) for the rows of x_dev[n][dim] whose base block
+ *   lies in this rank's slab (all rows without a slab); row i carries the id id_base + i; *kept = rows appended.
+ *   n <= bound capacity.  Synchronises.
+ * mpm_seed_generate: the positions seed (:840-850, mode 1: lower, size) / seed_ellipsoid (:959-978, mode 2: center,
+ *   radius) would give the particles with ids [id0, id0 + n), to x_out_dev[n][dim]; appends nothing.
+ * mpm_export_local: particle_info (:1172-1180) of the rows this rank owns: [x[dim] v[dim] material color id] per
+ *   row into out_dev (room for n_particles rows of 2 dim + 3 words), *count = rows written.  Synchronises. */
+int mpm_seed_positions_slab(mpm_ctx* ctx, const float* x_dev, int64_t n, int64_t id_base, int32_t material,
+                            int32_t color, const double* velocity, int32_t emitter, int64_t* kept, void* stream);
+int mpm_seed_generate(mpm_ctx* ctx, int32_t mode, int64_t n, int64_t id0, const double* a, const double* b,
+                      uint64_t seed, float* x_out_dev, void* stream);
+int mpm_export_local(mpm_ctx* ctx, void* out_dev, int64_t* count, void* stream);
 /* rows [0, n) of one state word in storage order (pair with the `id` word) */
 int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream);
 

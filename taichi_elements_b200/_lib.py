@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 MPM_OK = 0
 MPM_E_BLOCK_CAPACITY = 1
 MPM_E_KEY_BITS = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
@@ -104,6 +104,9 @@ SYMBOLS = [
     ('mpm_peer_open', _i32, [_vp, _i32, _vp]),
     ('mpm_peer_substeps', _i32, [_vp, _dbl, _i32, _i32, _vp]),
     ('mpm_download_raw', _i32, [_vp, _i32, _vp, _vp]),
+    ('mpm_seed_positions_slab', _i32, [_vp, _vp, _i64, _i64, _i32, _i32, _dp, _i32, ctypes.POINTER(_i64), _vp]),
+    ('mpm_seed_generate', _i32, [_vp, _i32, _i64, _i64, _dp, _dp, ctypes.c_uint64, _vp, _vp]),
+    ('mpm_export_local', _i32, [_vp, _vp, ctypes.POINTER(_i64), _vp]),
     ('mpm_voxelize', _i32, [_i32, _vp, _i64, _vp, _dbl, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_voxel_sample', _i32, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dp, _i32, _i32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_debug_binning', _i32, [_vp, _vp, _vp]),

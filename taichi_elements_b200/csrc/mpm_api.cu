@@ -47,10 +47,12 @@ struct mpm_ctx {
   int64_t table_cap = 0;
   bool dense = false;   // counting-sort path usable for the current layout
   Slab slab{0, INT_MIN, INT_MAX};
-  CommBufs comm{{nullptr, nullptr}, {nullptr, nullptr}, 0, 0, {nullptr, nullptr}, {nullptr, nullptr}};
+  CommBufs comm{};
   // peer path (NVLink writes into the neighbour's buffers)
   uint32_t* peer_region = nullptr;     // cudaMalloc'ed by mpm_peer_alloc: flags + the four receive buffers
-  size_t peer_mig_words = 0, peer_halo_words = 0;
+  size_t peer_mig_words = 0, peer_halo_words = 0, peer_plane_words = 0;   // plane: one of the 3 rotating halo planes of a side
+  int defer_svd = 0;                   // MPM_DEFER_SVD=0: SVD inline in the first pass of k_p2g3
+  int fused_halo = 1;                  // MPM_FUSED_HALO=0: legacy pack / wait / add kernels on the peer path
   void* peer_open[2] = {nullptr, nullptr};
   uint32_t epoch = 0;                  // substeps completed since mpm_peer_alloc (same on every rank)
   bool ext_box = false;          // layout box supplied by the host (global box of all ranks)
@@ -262,6 +264,8 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
+  if (const char* v = getenv("MPM_FUSED_HALO")) ctx->fused_halo = atoi(v);
+  if (const char* v = getenv("MPM_DEFER_SVD")) ctx->defer_svd = atoi(v);
   if (const char* v = getenv("MPM_SCAN")) ctx->own_scan = strcmp(v, "cub") != 0;
   {
     int occ = 1;
@@ -385,6 +389,7 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   a.state = ctx->state[ctx->cur];
   a.cap = ctx->cap;
   a.n0 = ctx->n;
+  if (a.id_base < 0) a.id_base = ctx->n;
   int blocks = gs_blocks(a.n, 256, ctx->sm_count);
   // A large array of external positions is stored sorted by leaf block (ids keep the insertion order): the
   // first substep then reads block-local rows instead of gathering 26 words per particle at random.  The sort
@@ -393,8 +398,9 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   if (a.mode == 0 && ctx->sort_seed && a.n >= (1 << 15) && !ctx->K.g2p2g && !ctx->slab.enabled && !ctx->in_batch &&
       ctx->P.grid_size == 4096 && (size_t)a.n <= ctx->cap) {
     const int half = ctx->P.grid_size / 2;
-    if (ctx->dim == 3) k_seed_keys<3><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a);
-    else k_seed_keys<2><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a);
+    const Slab none{0, INT_MIN, INT_MAX};
+    if (ctx->dim == 3) k_seed_keys<3><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a, none, nullptr);
+    else k_seed_keys<2><<<blocks, 256, 0, s>>>(a.x, a.n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a, none, nullptr);
     cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
     size_t tb = ctx->cub_bytes;
     CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, (int)a.n, 0, 10 * ctx->dim, s));
@@ -415,15 +421,99 @@ extern "C" int mpm_seed_positions(mpm_ctx* ctx, const float* x_dev, int64_t n, i
                                   const double* velocity, int32_t emitter, void* stream) {
   if (!ctx || (n > 0 && !x_dev)) return MPM_E_INVALID;
   SeedArgs a{};
-  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.x = x_dev; a.mode = 0;
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.x = x_dev; a.mode = 0; a.id_base = -1;
   fill3(a.vel, velocity, ctx->dim, 0.f);
   return seed_common(ctx, a, stream);
+}
+
+// Multi-GPU seeding: of the n positions x_dev[n][dim] keep the rows whose base block lies in this rank's slab
+// (all of them without a slab), stored sorted by leaf block; row i gets the id id_base + i.  Selection, ordering
+// and the count come from one radix sort of (owned ? block key : 1 << 30).  n must not exceed the bound capacity
+// (the sort borrows the binning scratch); the kept rows must fit behind the live ones.
+extern "C" int mpm_seed_positions_slab(mpm_ctx* ctx, const float* x_dev, int64_t n, int64_t id_base, int32_t material,
+                                       int32_t color, const double* velocity, int32_t emitter, int64_t* kept_out,
+                                       void* stream) {
+  if (!ctx || n < 0 || (n > 0 && !x_dev) || id_base < 0) return MPM_E_INVALID;
+  if (kept_out) *kept_out = 0;
+  if (n == 0) return MPM_OK;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  if ((size_t)n > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_seed_positions_slab: n exceeds the bound capacity");
+  if (ctx->in_batch || ctx->K.g2p2g) return fail(ctx, MPM_E_INVALID, "mpm_seed_positions_slab: not inside a batch / g2p2g");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->stage);
+  CK(cudaMemsetAsync(cnt, 0, 8, s));
+  const int blocks = gs_blocks(n, 256, ctx->sm_count), half = ctx->P.grid_size / 2;
+  if (ctx->dim == 3) k_seed_keys<3><<<blocks, 256, 0, s>>>(x_dev, n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a, ctx->slab, cnt);
+  else k_seed_keys<2><<<blocks, 256, 0, s>>>(x_dev, n, ctx->K.inv_dx, half, ctx->keys_a, ctx->vals_a, ctx->slab, cnt);
+  cub::DoubleBuffer<uint32_t> dk(ctx->keys_a, ctx->keys_b), dv(ctx->vals_a, ctx->vals_b);
+  size_t tb = ctx->cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, dk, dv, (int)n, 0, 31, s));
+  unsigned long long kept = 0;
+  CK(cudaMemcpyAsync(&kept, cnt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (kept_out) *kept_out = (int64_t)kept;
+  if (kept == 0) return MPM_OK;
+  if ((size_t)(ctx->n + (int64_t)kept) > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_seed_positions_slab: capacity exceeded");
+  SeedArgs a{};
+  a.n = (int64_t)kept; a.material = material; a.color = color; a.emitter = emitter; a.x = x_dev; a.mode = 0;
+  a.id_base = id_base; a.order = dv.Current();
+  fill3(a.vel, velocity, ctx->dim, 0.f);
+  a.state = ctx->state[ctx->cur]; a.cap = ctx->cap; a.n0 = ctx->n;
+  const int sb = gs_blocks(a.n, 256, ctx->sm_count);
+  if (ctx->dim == 3) k_seed<3><<<sb, 256, 0, s>>>(a); else k_seed<2><<<sb, 256, 0, s>>>(a);
+  CK(cudaGetLastError());
+  ctx->n += a.n;
+  ctx->bbox_valid = false;
+  ctx->last_valid = false;
+  return MPM_OK;
+}
+
+// Positions of seed (:840-850, mode 1) / seed_ellipsoid (:959-978, mode 2) for the particle ids [id0, id0 + n),
+// written to x_out_dev[n][dim] without appending anything: the distributed add_cube / add_ellipsoid generate the
+// same points as the single-device solver on every rank and keep their slab (mpm_seed_positions_slab).
+extern "C" int mpm_seed_generate(mpm_ctx* ctx, int32_t mode, int64_t n, int64_t id0, const double* a3, const double* b3,
+                                 uint64_t seed, float* x_out_dev, void* stream) {
+  if (!ctx || (mode != 1 && mode != 2) || n < 0 || id0 < 0 || !a3 || !b3 || (n > 0 && !x_out_dev)) return MPM_E_INVALID;
+  if (n == 0) return MPM_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  SeedArgs a{};
+  a.n = n; a.mode = mode; a.seed = seed; a.id_base = id0; a.x_out = x_out_dev;
+  fill3(a.a, a3, ctx->dim, 0.f);
+  fill3(a.b, b3, ctx->dim, 0.f);
+  const int blocks = gs_blocks(n, 256, ctx->sm_count);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ctx->dim == 3) k_seed<3><<<blocks, 256, 0, s>>>(a); else k_seed<2><<<blocks, 256, 0, s>>>(a);
+  CK(cudaGetLastError());
+  return MPM_OK;
+}
+
+// particle_info() of this rank (multi-GPU): rows [x[dim] v[dim] material color id] (2 dim + 3 words) of the
+// particles this rank owns, to out_dev (room for n_particles rows); the number of rows to *count_out.
+extern "C" int mpm_export_local(mpm_ctx* ctx, void* out_dev, int64_t* count_out, void* stream) {
+  if (!ctx || !count_out) return MPM_E_INVALID;
+  *count_out = 0;
+  if (ctx->n == 0) return MPM_OK;
+  if (!out_dev) return MPM_E_INVALID;
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->stage);
+  CK(cudaMemsetAsync(cnt, 0, 8, s));
+  const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count), half = ctx->P.grid_size / 2;
+  if (ctx->dim == 3) k_export_local<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
+  else k_export_local<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
+  CK(cudaGetLastError());
+  unsigned long long c = 0;
+  CK(cudaMemcpyAsync(&c, cnt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *count_out = (int64_t)c;
+  return MPM_OK;
 }
 extern "C" int mpm_seed_cube(mpm_ctx* ctx, int64_t n, const double* lower, const double* size, int32_t material,
                              int32_t color, const double* velocity, int32_t emitter, uint64_t seed, void* stream) {
   if (!ctx || !lower || !size) return MPM_E_INVALID;
   SeedArgs a{};
-  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 1; a.seed = seed;
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 1; a.seed = seed; a.id_base = -1;
   fill3(a.vel, velocity, ctx->dim, 0.f);
   fill3(a.a, lower, ctx->dim, 0.f);
   fill3(a.b, size, ctx->dim, 0.f);
@@ -434,7 +524,7 @@ extern "C" int mpm_seed_ellipsoid(mpm_ctx* ctx, int64_t n, const double* center,
                                   uint64_t seed, void* stream) {
   if (!ctx || !center || !radius) return MPM_E_INVALID;
   SeedArgs a{};
-  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 2; a.seed = seed;
+  a.n = n; a.material = material; a.color = color; a.emitter = emitter; a.mode = 2; a.seed = seed; a.id_base = -1;
   fill3(a.vel, velocity, ctx->dim, 0.f);
   fill3(a.a, center, ctx->dim, 0.f);
   fill3(a.b, radius, ctx->dim, 0.f);
@@ -444,7 +534,7 @@ extern "C" int mpm_seed_restart(mpm_ctx* ctx, const float* x_dev, const float* v
                                 const int32_t* c_dev, int64_t n, void* stream) {
   if (!ctx || (n > 0 && (!x_dev || !v_dev || !m_dev || !c_dev))) return MPM_E_INVALID;
   SeedArgs a{};
-  a.n = n; a.x = x_dev; a.v = v_dev; a.mats = m_dev; a.colors = c_dev; a.mode = 3;
+  a.n = n; a.x = x_dev; a.v = v_dev; a.mats = m_dev; a.colors = c_dev; a.mode = 3; a.id_base = -1;
   return seed_common(ctx, a, stream);
 }
 
@@ -556,10 +646,22 @@ static void launch_p2g_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s
 // third revision (mpm_p2g3.cuh): 3D, needs the counting sort's per-cell bucket starts
 template <int CH, int MB>
 static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t s) {
-  static LaunchCache lc;
   constexpr size_t smem = p2g3_smem_bytes<CH>();
-  const int grid = cached_grid(lc, ctx, k_p2g3<CH, MB>, P2G3::T, smem);
-  launch_chain(ctx->pdl, k_p2g3<CH, MB>, grid, P2G3::T, smem, s, a);
+  if (a.cb.fused) {          // multi-GPU: halo inside the kernel (mpm_comm.cuh)
+    static LaunchCache lcf;
+    const int grid = cached_grid(lcf, ctx, k_p2g3<CH, MB, true, true>, P2G3::T, smem);
+    launch_chain(ctx->pdl, k_p2g3<CH, MB, true, true>, grid, P2G3::T, smem, s, a);
+    return;
+  }
+  if (!ctx->defer_svd) {     // MPM_DEFER_SVD=0: single-pass constitutive phase (comparison)
+    static LaunchCache lcn;
+    const int grid = cached_grid(lcn, ctx, k_p2g3<CH, MB, false, false>, P2G3::T, smem);
+    launch_chain(ctx->pdl, k_p2g3<CH, MB, false, false>, grid, P2G3::T, smem, s, a);
+    return;
+  }
+  static LaunchCache lc;
+  const int grid = cached_grid(lc, ctx, k_p2g3<CH, MB, false, true>, P2G3::T, smem);
+  launch_chain(ctx->pdl, k_p2g3<CH, MB, false, true>, grid, P2G3::T, smem, s, a);
 }
 template <int D>
 static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
@@ -618,6 +720,7 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.slab = ctx->slab; a.cb = ctx->comm;
   a.n_rows = (int)ctx->n;
   a.pf_mode = ctx->pf_mode;
+  a.defer_svd = ctx->defer_svd;
   return a;
 }
 
@@ -677,7 +780,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
                     ctx->fscan, ctx->cellstart, ctx->vals_b, st));
     CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
                     ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr,
-                    ctx->gb_key, ctx->max_blocks, st));
+                    ctx->gb_key, ctx->max_blocks, st, ctx->slab));
     keys = ctx->keys_a;
     perm = ctx->vals_b;
     cellstart = ctx->cellstart;
@@ -724,8 +827,16 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
         ctx->flags_zeroed = true;
       }
     }
+    float4 *zp0 = nullptr, *zp1 = nullptr;
+    int nzp = 0;
+    if (ctx->comm.fused) {
+      const size_t off = (size_t)((ctx->comm.epoch + 1u) % 3u) * ctx->comm.plane_blocks * G::CELLS;
+      if (ctx->comm.plane_in[0]) zp0 = ctx->comm.plane_in[0] + off;
+      if (ctx->comm.plane_in[1]) zp1 = ctx->comm.plane_in[1] + off;
+      nzp = D == 3 ? ctx->L.eb[1] * ctx->L.eb[2] * G::CELLS : 0;
+    }
     CK(launch_chain(ctx->pdl, k_clear_grid<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s,
-                    ctx->grid, (const Status*)st, z1, n1, z2, n2, (int)G::CELLS));
+                    ctx->grid, (const Status*)st, z1, n1, z2, n2, (int)G::CELLS, zp0, zp1, nzp));
   }
   if (prof) cudaEventRecord(ev[1], s);
   ctx->cur_keys = keys; ctx->cur_perm = perm; ctx->cur_cellstart = cellstart;
@@ -746,7 +857,7 @@ static int enqueue_grid_op(mpm_ctx* ctx, float dt, cudaStream_t s, int* zero = n
   CK(launch_chain(ctx->pdl, k_grid_op<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, ctx->sm_count), 256, 0, s,
                   ctx->grid, (const uint32_t*)ctx->gb_key, ctx->L, (const ColliderTable*)ctx->d_ct, ctx->grav, ctx->gcfg,
                   ctx->K.dx, dt, (ctx->K.g2p2g && ctx->K.v_allowed_cfl > 0.f) ? ctx->K.v_allowed_cfl / dt : 0.f,
-                  ctx->d_status, zero, nzero));
+                  ctx->d_status, zero, nzero, ctx->slab, ctx->comm));
   CK(cudaGetLastError());
   ctx->launches += 1;
   return MPM_OK;
@@ -772,7 +883,10 @@ static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cud
     ctx->keys_ready = true;
   }
   launch_g2p<D>(ctx, a, s);
-  if (ctx->slab.enabled) { CK(launch_chain(ctx->pdl, k_mig_headers, 1, 1, 0, s, ctx->comm, (uint32_t)(ctx->epoch + 1), st)); ctx->launches += 1; }
+  if (ctx->slab.enabled && !ctx->comm.fused) {   // (fused exchange: G2P's last CTA writes the headers)
+    CK(launch_chain(ctx->pdl, k_mig_headers, 1, 1, 0, s, ctx->comm, (uint32_t)(ctx->epoch + 1), st));
+    ctx->launches += 1;
+  }
   if (prof) cudaEventRecord(ev[4], s);
   CK(cudaGetLastError());
   ctx->launches += 1;   // g2p
@@ -1083,16 +1197,19 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
   int nlin = 1;
   for (int d = 0; d < ctx->dim; ++d) nlin *= ctx->L.eb[d];
   if (ctx->dim == 3)
-    CK(launch_chain(ctx->pdl, k_mig_unpack<3>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (const uint32_t*)from_lo,
-                    (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
-                    ctx->K.inv_dx));
+    CK(launch_chain(ctx->pdl, k_mig_unpack<3>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (uint32_t*)from_lo,
+                    (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
+                    ctx->K.inv_dx, ctx->comm));
   else
-    CK(launch_chain(ctx->pdl, k_mig_unpack<2>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (const uint32_t*)from_lo,
-                    (const uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
-                    ctx->K.inv_dx));
-  CK(launch_chain(ctx->pdl, k_mig_commit, 1, 1, 0, s, (uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status));
+    CK(launch_chain(ctx->pdl, k_mig_unpack<2>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (uint32_t*)from_lo,
+                    (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
+                    ctx->K.inv_dx, ctx->comm));
+  ctx->launches += 1;
+  if (!ctx->comm.fused) {   // (fused exchange: the last CTA of the unpack kernel commits)
+    CK(launch_chain(ctx->pdl, k_mig_commit, 1, 1, 0, s, (uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status));
+    ctx->launches += 1;
+  }
   CK(cudaGetLastError());
-  ctx->launches += 2;
   return MPM_OK;
 }
 
@@ -1200,6 +1317,10 @@ extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
 //   flag 0/1: migration epoch published by the lo/hi neighbour, flag 2/3: halo epoch
 static uint32_t* region_mig(mpm_ctx* c, uint32_t* base, int from_side) { return base + 16 + (size_t)from_side * c->peer_mig_words; }
 static uint32_t* region_halo(mpm_ctx* c, uint32_t* base, int from_side) { return base + 16 + 2 * c->peer_mig_words + (size_t)from_side * c->peer_halo_words; }
+//   ... then [3 planes from lo][3 planes from hi] (fused halo, 3D): dense (y, z) block planes of float4 node records
+static float4* region_plane(mpm_ctx* c, uint32_t* base, int from_side) {
+  return reinterpret_cast<float4*>(base + 16 + 2 * c->peer_mig_words + 2 * c->peer_halo_words + (size_t)from_side * 3 * c->peer_plane_words);
+}
 
 extern "C" int mpm_peer_alloc(mpm_ctx* ctx, int32_t mig_cap, int32_t halo_cap) {
   if (!ctx || mig_cap < 1 || halo_cap < 1) return MPM_E_INVALID;
@@ -1207,12 +1328,14 @@ extern "C" int mpm_peer_alloc(mpm_ctx* ctx, int32_t mig_cap, int32_t halo_cap) {
   if (ctx->peer_region) return fail(ctx, MPM_E_INVALID, "mpm_peer_alloc: already allocated");
   ctx->peer_mig_words = mpm_comm_bytes(ctx->dim, 0, mig_cap) / 4;
   ctx->peer_halo_words = mpm_comm_bytes(ctx->dim, 1, halo_cap) / 4;
-  const size_t words = 16 + 2 * ctx->peer_mig_words + 2 * ctx->peer_halo_words;
+  ctx->peer_plane_words = ctx->dim == 3 ? (size_t)halo_cap * 64 * 4 : 0;
+  const size_t words = 16 + 2 * ctx->peer_mig_words + 2 * ctx->peer_halo_words + 6 * ctx->peer_plane_words;
   // the one allocation this library owns: it has to be a whole cudaMalloc block to be exported over CUDA IPC
   CK(cudaMalloc((void**)&ctx->peer_region, words * 4));
   CK(cudaMemset(ctx->peer_region, 0, words * 4));
   ctx->comm.mig_cap = mig_cap;
   ctx->comm.halo_cap = halo_cap;
+  ctx->comm.plane_blocks = halo_cap;
   ctx->epoch = 0;
   return MPM_OK;
 }
@@ -1241,6 +1364,12 @@ extern "C" int mpm_peer_open(mpm_ctx* ctx, int32_t side, const void* handle64) {
   ctx->comm.halo[side] = region_halo(ctx, pb, there);
   ctx->comm.flag_mig[side] = pb + there;
   ctx->comm.flag_halo[side] = pb + 2 + there;
+  if (ctx->peer_plane_words) {
+    ctx->comm.plane_out[side] = region_plane(ctx, pb, there);            // the neighbour's planes "from" my side
+    ctx->comm.plane_in[side] = region_plane(ctx, ctx->peer_region, side);  // mine, filled by that neighbour
+  }
+  ctx->comm.wait_mig[side] = ctx->peer_region + side;
+  ctx->comm.wait_halo[side] = ctx->peer_region + 2 + side;
   return MPM_OK;
 }
 static void peer_close(mpm_ctx* ctx) {
@@ -1258,6 +1387,26 @@ extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t
   uint32_t* mig_from[2] = {has[0] ? region_mig(ctx, me, 0) : nullptr, has[1] ? region_mig(ctx, me, 1) : nullptr};
   uint32_t* halo_from[2] = {has[0] ? region_halo(ctx, me, 0) : nullptr, has[1] ? region_halo(ctx, me, 1) : nullptr};
   const int n_iter = deliver_only ? 1 : count;
+  // Fused exchange (3D, cell-owner P2G rev. 3): the shared grid column travels inside P2G as vector reductions
+  // into the neighbour's halo plane, the grid op waits for the neighbours' epoch and adds the planes, G2P's last
+  // CTA publishes the migration message, the unpack kernel waits for it and commits: 10 launches per substep, no
+  // one-thread kernels, and the boundary blocks go first so the transfer overlaps the interior scatter.
+  const bool fused = ctx->fused_halo && ctx->dim == 3 && ctx->p2g_ver == 3 && ctx->p2g_variant == 1 && ctx->dense &&
+                     ctx->peer_plane_words && (int64_t)ctx->L.eb[1] * ctx->L.eb[2] <= ctx->comm.plane_blocks;
+  if (fused) {
+    for (int i = 0; i < n_iter; ++i) {
+      ctx->comm.fused = 1;
+      ctx->comm.epoch = ctx->epoch;
+      int rc = mpm_phase_unpack(ctx, mig_from[0], mig_from[1], stream);
+      if (!rc && !deliver_only) rc = mpm_phase_p2g(ctx, dt, stream);
+      if (!rc && !deliver_only) rc = mpm_phase_g2p(ctx, dt, stream);
+      ctx->comm.fused = 0;
+      if (rc) return rc;
+      if (!deliver_only) ctx->epoch += 1;
+    }
+    CK(cudaGetLastError());
+    return MPM_OK;
+  }
   for (int i = 0; i < n_iter; ++i) {
     // leavers of the neighbours' last G2P (epoch = substeps completed so far)
     CK(launch_chain(ctx->pdl, k_wait_flags, 1, 1, 0, s, (const uint32_t*)(has[0] ? me + 0 : nullptr),

@@ -290,7 +290,7 @@ template <int D>
 __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restrict__ fscan, int nlin, KeyLayout L,
                              const uint32_t* __restrict__ pb_key, const int* __restrict__ cellstart,
                              int* __restrict__ pb_start, int* __restrict__ pb_nbr, uint32_t* __restrict__ gb_key,
-                             int max_blocks, Status* st) {
+                             int max_blocks, Status* st, Slab slab) {
   using G = Geo<D>;
   pdl_enter();
   if (st->err) return;
@@ -313,6 +313,19 @@ __global__ void k_bin_finish(const int* __restrict__ flags, const int* __restric
     st->maxv_bits = 0;
     st->maxgv_bits = 0;
     for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
+    // slabs: particle blocks of the first and of the last block column (keys are x-major, so they are the first
+    // bnd_lo and the last bnd_hi entries of the block list); P2G takes them first (fused halo, mpm_comm.cuh)
+    int blo = 0, bhi = 0;
+    if (slab.enabled) {
+      int plane = 1;
+      for (int d = 1; d < D; ++d) plane *= L.eb[d];
+      const long long rl = (long long)slab.lo - L.ob[0], rh = (long long)slab.hi - 1 - L.ob[0];
+      if (rl >= 0 && rl < L.eb[0]) blo = fscan[(int)(rl + 1) * plane] - fscan[(int)rl * plane];
+      if (rh >= 0 && rh < L.eb[0]) bhi = fscan[(int)(rh + 1) * plane] - fscan[(int)rh * plane];
+      if (blo + bhi > npb) blo = npb - bhi;          // a one-column slab: the same blocks
+    }
+    st->bnd_lo = blo; st->bnd_hi = bhi;
+    st->halo_done = 0;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npb * G::NO; i += gridDim.x * blockDim.x) {
     const int b = i / G::NO, o = i % G::NO;

@@ -86,22 +86,6 @@ __global__ void k_halo_add(float4* __restrict__ grid, const int* __restrict__ fl
   }
 }
 
-// ---- peer path: producer kernels write straight into the neighbour's receive buffers
-// over NVLink; a release-store of the substep epoch tells the neighbour the data is
-// complete, an acquire-spin on the local epoch word (with a time-out) gates its consumer.
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 // one thread: wait until both neighbours have published `epoch` (null = no neighbour)
 __global__ void k_wait_flags(const uint32_t* f0, const uint32_t* f1, uint32_t epoch, Status* st) {
   pdl_enter();
@@ -130,44 +114,39 @@ __global__ void k_halo_headers(CommBufs cb, uint32_t epoch, Status* st) {
 }
 __global__ void k_mig_headers(CommBufs cb, uint32_t epoch, Status* st) {
   pdl_enter();
-  for (int s = 0; s < 2; ++s) {
-    if (!cb.mig[s]) continue;
-    int c = st->err ? 0 : st->mig_cnt[s];
-    if (c > cb.mig_cap) { st->err |= ERR_COMM_CAPACITY; c = 0; }
-    cb.mig[s][0] = (uint32_t)c;
-    if (cb.flag_mig[s]) { __threadfence_system(); st_release_sys(cb.flag_mig[s], epoch); }
-  }
-  if (!st->err) st->n_cur = st->n_live;    // rows of the set G2P just wrote
+  publish_migration(cb, epoch, st);
 }
 
 // append the particles received from the -x and +x neighbours to the live set; when the last
 // G2P already emitted the coming substep's sort keys and block flags (fused key pass), do the
 // same for the appended rows (same arithmetic as k_bin_keys)
 template <int D>
-__global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uint32_t* __restrict__ from_lo,
-                             const uint32_t* __restrict__ from_hi, int mig_cap, Status* st,
+__global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, uint32_t* __restrict__ from_lo,
+                             uint32_t* __restrict__ from_hi, int mig_cap, Status* st,
                              uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, KeyLayout L, Slab slab,
-                             float inv_dx) {
+                             float inv_dx, CommBufs cb) {
   using G = Geo<D>;
   constexpr int NF = Fld<D>::N;
   pdl_enter();
-  if (st->err) return;
-  const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
-  const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
+  // fused exchange: the neighbours publish the epoch of the substep whose leavers these buffers hold
+  if (cb.fused) cta_wait_epochs(from_lo ? cb.wait_mig[0] : nullptr, from_hi ? cb.wait_mig[1] : nullptr, cb.epoch, st);
+  bool active = *(volatile int*)&st->err == 0;
+  const int c0 = (active && from_lo) ? min((int)*(volatile uint32_t*)from_lo, mig_cap) : 0;
+  const int c1 = (active && from_hi) ? min((int)*(volatile uint32_t*)from_hi, mig_cap) : 0;
   const int base = st->n_cur;
-  if ((size_t)base + c0 + c1 > cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->err |= ERR_PARTICLE_CAPACITY;
-    return;
+  if (active && (size_t)base + c0 + c1 > cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, ERR_PARTICLE_CAPACITY);
+    active = false;
   }
-  const int total = (c0 + c1) * NF;
+  const int total = active ? (c0 + c1) * NF : 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int f = i / (c0 + c1), r = i % (c0 + c1);
     const uint32_t v = r < c0 ? from_lo[COMM_HEADER + (size_t)f * mig_cap + r]
                               : from_hi[COMM_HEADER + (size_t)f * mig_cap + (r - c0)];
     state[(size_t)f * cap + base + r] = v;
   }
-  if (!keys) return;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < c0 + c1; r += gridDim.x * blockDim.x) {
+  const int nrows = (active && keys) ? c0 + c1 : 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
     uint32_t lin = 0, cell = 0, sp = 0;
     bool bad = false, mine = true;
 #pragma unroll
@@ -191,6 +170,17 @@ __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, const uin
 #pragma unroll
     for (uint32_t o = 0; o < (uint32_t)G::NO; ++o)
       if ((o & ~sp) == 0) gf[(int)lin + oct_delta_l<D>(L, (int)o)] = 1;
+  }
+  if (cb.fused) {
+    // the LAST CTA to finish commits the appended rows and marks the messages consumed (no commit kernel)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&st->unpack_done, 1) == (int)gridDim.x - 1) {
+      st->unpack_done = 0;
+      if (active) st->n_cur = base + c0 + c1;
+      if (from_lo) from_lo[0] = 0;
+      if (from_hi) from_hi[0] = 0;
+    }
   }
 }
 __global__ void k_mig_commit(uint32_t* from_lo, uint32_t* from_hi, int mig_cap, Status* st) {

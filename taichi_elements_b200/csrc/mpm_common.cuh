@@ -62,6 +62,12 @@ struct Status {
   unsigned maxgv_bits;  // max |grid v|_inf after the grid op (compute_max_grid_velocity)
   int half;         // g2p2g: gather halves completed in this batch
   int next_err;     // error bits raised for the NEXT substep by G2P's fused key pass
+  // multi-GPU, fused exchange (mpm_comm.cuh): particle blocks of the first / last block column of the slab
+  // (their tiles touch a column shared with a neighbour; P2G takes them first), and "last CTA" counters
+  int bnd_lo, bnd_hi;
+  int halo_done;    // boundary blocks whose shared-column nodes have been sent (P2G)
+  int g2p_done;     // CTAs of G2P that have finished (the last one publishes the migration message)
+  int unpack_done;  // CTAs of k_mig_unpack that have finished (the last one commits the appended rows)
 };
 
 // Slab decomposition along x (multi-GPU): this rank owns leaf-block columns
@@ -79,6 +85,16 @@ struct CommBufs {
   int mig_cap, halo_cap;
   uint32_t* flag_mig[2];   // peer path: the neighbour's "data ready" epoch words to release-store
   uint32_t* flag_halo[2];
+  // fused halo (peer path, 3D): the shared grid column travels inside P2G as vector reductions into a dense
+  // plane in the NEIGHBOUR's memory, indexed by the (y, z) block coordinates of the common key layout; three
+  // planes per side rotate with the substep epoch (one being filled, one being read, one being cleared)
+  float4* plane_out[2];    // neighbour's planes for what I send to the -x / +x side (3 * plane_blocks * 64 records)
+  float4* plane_in[2];     // my planes, filled by the -x / +x neighbour
+  const uint32_t* wait_mig[2];    // my epoch words, written by the neighbours
+  const uint32_t* wait_halo[2];
+  int plane_blocks;        // capacity of one plane in leaf blocks (>= eb[1] * eb[2] of the key layout)
+  int fused;               // 1: the fused exchange is active for this substep
+  uint32_t epoch;          // substeps completed before this one
 };
 
 struct Grav { float g[3]; };

@@ -58,6 +58,52 @@ __device__ __forceinline__ void prefetch_l2_range(const void* p, uint32_t bytes)
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- peer path: producer kernels write straight into the neighbour's receive buffers
+// over NVLink; a release-store of the substep epoch tells the neighbour the data is
+// complete, an acquire-spin on the local epoch word (with a time-out) gates its consumer.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// every thread of the CTA waits (through thread 0) until the epoch words f0 / f1 (null = no neighbour on that
+// side), written by the neighbours with st_release_sys, have reached `epoch`; 4 s time-out -> error bit, never a hang
+__device__ __forceinline__ void cta_wait_epochs(const uint32_t* f0, const uint32_t* f1, uint32_t epoch, Status* st) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = global_ns();
+    const uint32_t* f[2] = {f0, f1};
+    for (int s = 0; s < 2; ++s) {
+      if (!f[s]) continue;
+      while ((int32_t)(ld_acquire_sys(f[s]) - epoch) < 0) {
+        if (global_ns() - t0 > 4000000000ull) { atomicOr(&st->err, ERR_COMM_TIMEOUT); break; }
+        __nanosleep(100);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// migration message headers: counts, overflow detection and (peer path) the "data ready" epoch.  They are
+// written even after a device error (count 0) so that a neighbour never waits for ever.
+__device__ __forceinline__ void publish_migration(const CommBufs& cb, uint32_t epoch, Status* st) {
+  for (int s = 0; s < 2; ++s) {
+    if (!cb.mig[s]) continue;
+    int c = *(volatile int*)&st->err ? 0 : *(volatile int*)&st->mig_cnt[s];
+    if (c > cb.mig_cap) { atomicOr(&st->err, ERR_COMM_CAPACITY); c = 0; }
+    cb.mig[s][0] = (uint32_t)c;
+    if (cb.flag_mig[s]) { __threadfence_system(); st_release_sys(cb.flag_mig[s], epoch); }
+  }
+  if (!*(volatile int*)&st->err) st->n_cur = *(volatile int*)&st->n_live;    // rows of the set G2P just wrote
+}
+
 template <int D> __device__ __forceinline__ int oct_delta_l(const KeyLayout& L, int o) {
   if constexpr (D == 3) return ((o & 1) ? L.eb[1] * L.eb[2] : 0) + ((o & 2) ? L.eb[2] : 0) + ((o & 4) ? 1 : 0);
   else return ((o & 1) ? L.eb[1] : 0) + ((o & 2) ? 1 : 0);
@@ -277,8 +323,18 @@ __global__ void k_nbr(const uint32_t* __restrict__ keys, const int* __restrict__
 
 template <int D>
 __global__ void k_clear_grid(float4* __restrict__ grid, const Status* st, int* __restrict__ z1, int n1,
-                             int* __restrict__ z2, int n2, int n1_blocks_mul) {
+                             int* __restrict__ z2, int n2, int n1_blocks_mul, float4* __restrict__ zp0,
+                             float4* __restrict__ zp1, int nzp) {
   pdl_enter();
+  // fused halo: the planes the neighbours fill during the NEXT substep (the ones of this substep are being
+  // filled right now, the previous ones were read by the last grid op) -- see CommBufs
+  {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzp; i += gridDim.x * blockDim.x) {
+      if (zp0) zp0[i] = z;
+      if (zp1) zp1[i] = z;
+    }
+  }
   // tables the NEXT substep of the batch expects zeroed (per-cell counts; block flags when the
   // coming G2P emits them), so that no memset node sits between the kernels of the chain
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -326,6 +382,7 @@ template <int D> struct SubstepArgs {
   int* next_flags;      //   (same key layout, see mpm_bin.cuh); saves the k_bin_keys pass
   int next_nlin;
   int pf_mode;    // next-block L2 prefetch: 0 off, 1 one prefetch per 128 B, 2 bulk range prefetch, 3 one per 32 B
+  int defer_svd;  // k_p2g3: particles that need the SVD run in a second, compacted pass (MPM_DEFER_SVD)
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
   CommBufs cb;    // multi-GPU: migration / halo send buffers
@@ -447,11 +504,21 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
 template <int D>
 __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict__ gb_key, KeyLayout L,
                           const ColliderTable* __restrict__ ct, Grav grav, GridCfg cfg, float dx, float dt,
-                          float v_allowed, Status* st, int* __restrict__ zero, int nzero) {
+                          float v_allowed, Status* st, int* __restrict__ zero, int nzero, Slab slab, CommBufs cb) {
   using G = Geo<D>;
   pdl_enter();
   // (slab runs) the block-flag table the coming G2P fills for the next substep
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;
+  // fused halo: the neighbours' partial sums of the shared columns arrive in my planes while P2G runs; they are
+  // complete once both have published this substep's epoch
+  const float4* pl_lo = nullptr;
+  const float4* pl_hi = nullptr;
+  if (cb.fused) {
+    cta_wait_epochs(cb.wait_halo[0], cb.wait_halo[1], cb.epoch + 1u, st);
+    const size_t off = (size_t)(cb.epoch % 3u) * cb.plane_blocks * G::CELLS;
+    if (cb.plane_in[0]) pl_lo = cb.plane_in[0] + off;
+    if (cb.plane_in[1]) pl_hi = cb.plane_in[1] + off;
+  }
   if (st->err) return;
   float gvmax = 0.0f;
   const size_t total = (size_t)st->ngb * G::CELLS;
@@ -461,13 +528,23 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
     const int cell = (int)(i % G::CELLS);
     float4 rec = grid[i];
     float v[3] = {rec.x, rec.y, (D == 3) ? rec.z : 0.0f};
-    const float m = (D == 3) ? rec.w : rec.z;
     int rel[D], I[3] = {0, 0, 0};
     key_to_rel<D>(L, gb_key[slot], rel);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       int lc = (cell >> (G::LOG_LEAF * (D - 1 - d))) & (G::LEAF - 1);
       I[d] = ((rel[d] + L.ob[d]) << G::LOG_LEAF) + lc - L.half;
+    }
+    float m = (D == 3) ? rec.w : rec.z;
+    if constexpr (D == 3) {
+      if (cb.fused) {
+        const int col = rel[0] + L.ob[0];
+        const float4* pl = col == slab.lo ? pl_lo : (col == slab.hi ? pl_hi : nullptr);
+        if (pl) {
+          const float4 h = pl[(size_t)(rel[1] * L.eb[2] + rel[2]) * G::CELLS + cell];
+          v[0] += h.x; v[1] += h.y; v[2] += h.z; m += h.w;
+        }
+      }
     }
     if (m > 0.0f) {                                            // :591-593
       float inv = __fdiv_rn(1.0f, m);
@@ -566,7 +643,10 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
   __shared__ float4 tile_buf[2][G::TN];
   __shared__ int s_b;
   pdl_enter();
-  if (a.st->err) return;
+  if (a.st->err) {
+    if (a.cb.fused && blockIdx.x == 0 && threadIdx.x == 0) publish_migration(a.cb, a.cb.epoch + 1u, a.st);
+    return;
+  }
   const int npb = a.st->npb;
   const int tid = threadIdx.x;
   const size_t cap = a.cap;
@@ -857,7 +937,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
             m[FL::COLOR * mc] = color;
             m[FL::ID * mc] = pid;
             m[FL::EMIT * mc] = emit;
-            __threadfence_system();   // peer path: the row may live in the neighbour's memory
+            if (!a.cb.fused) __threadfence_system();   // peer path: the row may live in the neighbour's memory
           }
         }
       }
@@ -897,6 +977,17 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
     for (int d = 0; d < D; ++d)
       if (lo[d] <= hi[d]) { atomicMin(&a.st->bb_min[d], lo[d]); atomicMax(&a.st->bb_max[d], hi[d]); }
+  }
+  if (a.cb.fused) {
+    // fused exchange: the leavers of this CTA are in the neighbours' buffers (system-scope fence by every thread);
+    // the LAST CTA to finish writes the message headers and publishes the epoch -- no separate header kernel
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && atomicAdd(&a.st->g2p_done, 1) == (int)gridDim.x - 1) {
+      a.st->g2p_done = 0;
+      __threadfence();
+      publish_migration(a.cb, a.cb.epoch + 1u, a.st);
+    }
   }
 }
 
@@ -976,25 +1067,38 @@ struct SeedArgs {
   const int* colors;
   int mode;             // 0 external, 1 cube, 2 ellipsoid, 3 restart
   const uint32_t* order; // non-null (mode 0): row n0 + i takes input order[i] (inputs pre-sorted by leaf block)
+  int64_t id_base;       // id of input 0 (the insertion index n0 on a single-device solver; global ids with slabs)
+  float* x_out;          // non-null (modes 1, 2): positions only, [n][D] -- nothing is appended (mpm_seed_generate)
 };
 
 // Sort key of an external position for block-sorted seeding: absolute leaf-block coordinates, 10 bits per
 // axis (the 4096^3 virtual grid of 4^3 leaves), x slowest like the substep's key.  Only the storage order
 // of the new rows depends on it (ids keep the insertion order); it spares the first substep after a large
 // add_particles the random gather through `perm` that an arbitrary input order causes.
+// With a slab (multi-GPU) rows whose base block lies outside this rank's columns get the key 1 << 30, which sorts
+// behind every owned row, and the owned rows are counted: selection and block-sorting in one sort.
 template <int D>
 __global__ void k_seed_keys(const float* __restrict__ x, int64_t n, float inv_dx, int half, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
+                            uint32_t* __restrict__ vals, Slab slab, unsigned long long* __restrict__ kept) {
   using G = Geo<D>;
+  unsigned long long mine_cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t k = 0;
+    bool mine = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const int b = (base_index(x[i * D + d], inv_dx) + half) >> G::LOG_LEAF;
+      if (d == 0 && slab.enabled) mine = b >= slab.lo && b < slab.hi;
       k = (k << 10) | (uint32_t)min(max(b, 0), 1023);
     }
-    keys[i] = k;
+    keys[i] = mine ? k : (1u << 30);
     vals[i] = (uint32_t)i;
+    mine_cnt += mine ? 1u : 0u;
+  }
+  if (kept) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine_cnt += __shfl_xor_sync(0xffffffffu, mine_cnt, o);
+    if ((threadIdx.x & 31) == 0 && mine_cnt) atomicAdd(kept, mine_cnt);
   }
 }
 
@@ -1006,7 +1110,7 @@ __global__ void k_seed(SeedArgs a) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t p = (uint32_t)(a.n0 + i);
     const int64_t src = a.order ? (int64_t)a.order[i] : i;     // input this row takes (block-sorted seeding)
-    const uint64_t id = (uint64_t)(a.n0 + src);
+    const uint64_t id = (uint64_t)(a.id_base + src);
     float x[D], v[D];
     int material = a.material, color = a.color;
 #pragma unroll
@@ -1035,6 +1139,11 @@ __global__ void k_seed(SeedArgs a) {
       }
 #pragma unroll
       for (int d = 0; d < D; ++d) x[d] = __fadd_rn(a.a[d], __fmul_rn(r[d], a.b[d]));
+    }
+    if (a.x_out) {                                             // positions only (distributed add_cube / add_ellipsoid)
+#pragma unroll
+      for (int d = 0; d < D; ++d) a.x_out[i * D + d] = x[d];
+      continue;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) { stf(a.state, a.cap, FL::X + d, p, x[d]); stf(a.state, a.cap, FL::V + d, p, v[d]); }
@@ -1186,6 +1295,36 @@ __global__ void k_gather_rows(const uint32_t* __restrict__ state, size_t cap, in
     const int64_t id = state[(size_t)idf * cap + s];
     if (id >= begin && id < end)
       for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = state[(size_t)(first + w) * cap + s];
+  }
+}
+
+// particle_info() of one slab rank: rows [x[D] v[D] material color id] of the particles whose base block lies in
+// this rank's columns (rows already handed to a neighbour are skipped), compacted in storage order groups
+template <int D>
+__global__ void k_export_local(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, int half, Slab slab,
+                               uint32_t* __restrict__ out, unsigned long long* __restrict__ count) {
+  using G = Geo<D>;
+  using FL = Fld<D>;
+  constexpr int W = 2 * D + 3;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
+    bool mine = s < (uint32_t)n;
+    if (mine && slab.enabled) {
+      const int bx = (base_index(ldf(state, cap, FL::X, s), inv_dx) + half) >> G::LOG_LEAF;
+      mine = bx >= slab.lo && bx < slab.hi;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    unsigned long long base = 0;
+    if (lane == 0 && m) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!mine) continue;
+    uint32_t* o = out + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * W;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { o[d] = ldu(state, cap, FL::X + d, s); o[D + d] = ldu(state, cap, FL::V + d, s); }
+    o[2 * D] = ldu(state, cap, FL::MAT, s);
+    o[2 * D + 1] = ldu(state, cap, FL::COLOR, s);
+    o[2 * D + 2] = ldu(state, cap, FL::ID, s);
   }
 }
 

@@ -11,8 +11,10 @@
 
 #if defined(__CUDACC__)
 #define MPM_HD __host__ __device__ __forceinline__
+#define MPM_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define MPM_HD inline
+#define MPM_HD_NOINLINE inline
 #endif
 
 namespace mpm {
@@ -339,13 +341,31 @@ template <int D> MPM_HD void sand_projection(const Consts& K, float* sig, float&
 }
 
 // ---------------------------------------------------------------------------
-// The per-particle part of p2g (engine/mpm_solver.py:506-574).
+// The per-particle part of p2g (engine/mpm_solver.py:506-574), in three pieces so that the 3D P2G kernel can
+// run the particles that need the full SVD in a second, compacted pass (mpm_p2g3.cuh):
+//   trial_F               F_trial = (I + dt C) F_in                                  (:507-513)
+//   particle_update_fast  every case that does NOT need the SVD; returns false otherwise
+//   particle_update_svd   the general path (ti.svd, plasticity, stress)           (:525-566)
+// particle_update() chains them (2D kernels, the first P2G variants, the host harness).
 //   in : F (stored), C, Jp, material, dt
 //   out: F (new stored), Jp (new), affine = stress + mass*C, mass
+//
+// Which cases avoid the SVD, and why the results are the reference's up to round-off:
+//   WATER                only J = det F.
+//   ELASTIC, STATIONARY  sigma is not clamped, Jp *= 1: only R = U V^T (Newton polar) and J = det F.
+//   SNOW                 if every singular value already lies inside the clamp interval [1 - 2.5e-2, 1 + 4.5e-3]
+//                        the clamp is the identity: F and Jp are unchanged and the stress is the elastic formula
+//                        with the hardened mu, lambda.  The test needs no decomposition: sigma_i in (lo, hi) for all
+//                        i  <=>  F^T F - lo^2 I and hi^2 I - F^T F are positive definite (Sylvester's criterion).
+//                        A value within round-off of a bound may be classified either way; both branches then
+//                        agree to round-off (the clamp moves it by ~1e-7).
+//   SAND                 sand_projection only needs tr = sum_i log sigma_i + Jp = log det F + Jp to pick its case;
+//                        for tr >= 0 ("expanding", :331-333) Sigma' = I: F' = U V^T = R, Jp' = tr, and the stress
+//                        (all log sigma'_i = 0) vanishes.  At tr = 0 both cases give Sigma' = I and Jp' = 0, so a
+//                        round-off difference in tr is harmless.
 // ---------------------------------------------------------------------------
 template <int D>
-MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, const float* C,
-                            float& Jp, float* affine, float& mass) {
+MPM_HD void trial_F(const Consts& K, float dt, int material, const float* F, const float* C, float Jp, float* Fn) {
   constexpr int DD = D * D;
   const bool fused = K.g2p2g != 0;   // [g2p2g] differences, SURVEY Appendix D-1
   float Fin[DD];
@@ -364,19 +384,46 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
   for (int i = 0; i < DD; ++i) A[i] = dt * C[i];
 #pragma unroll
   for (int i = 0; i < D; ++i) A[i * D + i] += 1.0f;
-  float Fn[DD];
   matmul<D>(A, Fin, Fn);
   if (fused && K.clamp_F) {                                  // [g2p2g] :415-416
 #pragma unroll
     for (int i = 0; i < DD; ++i) Fn[i] = fmaxf(-4.0f, fminf(4.0f, Fn[i]));
   }
+}
 
+// hardening (:515-524): mu, lambda for this particle
+MPM_HD void lame(const Consts& K, int material, float Jp, float& mu, float& la) {
+  const bool fused = K.g2p2g != 0;
   float h = 1.0f;                                            // :515-521 ([g2p2g] hardens water too, :419-421)
   if (K.support_plasticity && (material != WATER || fused)) h = expf(10.0f * (1.0f - Jp));
   if (material == ELASTIC) h = 0.3f;
-  float mu = K.mu_0 * h, la = K.lambda_0 * h;
+  mu = K.mu_0 * h;
+  la = K.lambda_0 * h;
   if (material == WATER) mu = 0.0f;
+}
 
+template <int D> MPM_HD void finish_affine(const Consts& K, float dt, const float* stress, const float* C, float mass,
+                                           float* affine) {
+  const float scale = -dt * K.p_vol * 4.0f * K.inv_dx2;      // :569
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) affine[i] = scale * stress[i] + mass * C[i];   // :574
+}
+
+// symmetric 3x3 (a00 a01 a02 / a11 a12 / a22) positive definite? (leading principal minors > 0)
+MPM_HD bool spd3(float a00, float a01, float a02, float a11, float a12, float a22) {
+  const float m2 = a00 * a11 - a01 * a01;
+  const float d = a00 * (a11 * a22 - a12 * a12) - a01 * (a01 * a22 - a12 * a02) + a02 * (a01 * a12 - a11 * a02);
+  return a00 > 0.0f && m2 > 0.0f && d > 0.0f;
+}
+
+// Fn: in = trial F, out = new stored F (only when true is returned)
+template <int D>
+MPM_HD bool particle_update_fast(const Consts& K, float dt, int material, float* Fn, const float* C, float& Jp,
+                                 float* affine, float& mass) {
+  constexpr int DD = D * D;
+  const bool fused = K.g2p2g != 0;
+  float mu, la;
+  lame(K, material, Jp, mu, la);
   float stress[DD];
   mass = K.p_mass;
   if (material == WATER) {
@@ -394,14 +441,27 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
 #pragma unroll
     for (int i = 0; i < D; ++i) stress[i * D + i] = p;
     if (!fused) mass *= K.water_density;                     // :571-573 ([g2p2g]: p_mass, :472)
-  } else {
+    finish_affine<D>(K, dt, stress, C, mass, affine);
+    return true;
+  }
+  if constexpr (D == 3) {
     float Rp[DD], Jpol = 1.0f;
-    bool fast = false;
-    if constexpr (D == 3) {
-      // ELASTIC / STATIONARY: polar rotation only (no sigma clamp, Jp *= 1)
-      if (material == ELASTIC || material == STATIONARY) fast = polar3_newton(Fn, Rp, Jpol);
+    bool elastic_like = material == ELASTIC || material == STATIONARY;
+    if (material == SNOW) {
+      // clamp interval of :529-531 squared, as f32 constants
+      const float lo = 1.0f - 2.5e-2f, hi = 1.0f + 4.5e-3f;
+      const float lo2 = lo * lo, hi2 = hi * hi;
+      const float a00 = Fn[0] * Fn[0] + Fn[3] * Fn[3] + Fn[6] * Fn[6];
+      const float a11 = Fn[1] * Fn[1] + Fn[4] * Fn[4] + Fn[7] * Fn[7];
+      const float a22 = Fn[2] * Fn[2] + Fn[5] * Fn[5] + Fn[8] * Fn[8];
+      const float a01 = Fn[0] * Fn[1] + Fn[3] * Fn[4] + Fn[6] * Fn[7];
+      const float a02 = Fn[0] * Fn[2] + Fn[3] * Fn[5] + Fn[6] * Fn[8];
+      const float a12 = Fn[1] * Fn[2] + Fn[4] * Fn[5] + Fn[7] * Fn[8];
+      elastic_like = spd3(a00 - lo2, a01, a02, a11 - lo2, a12, a22 - lo2) &&
+                     spd3(hi2 - a00, -a01, -a02, hi2 - a11, -a12, hi2 - a22);
     }
-    if (fast) {
+    if (elastic_like) {
+      if (!polar3_newton(Fn, Rp, Jpol)) return false;        // inverted / singular: the SVD convention decides
       float T[DD];
 #pragma unroll
       for (int i = 0; i < DD; ++i) T[i] = 2.0f * mu * (Fn[i] - Rp[i]);
@@ -409,52 +469,89 @@ MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, c
       float p = la * Jpol * (Jpol - 1.0f);
 #pragma unroll
       for (int i = 0; i < D; ++i) stress[i * D + i] += p;
-    } else {
-    float U[DD], V[DD], sig[D];
-    svd<D>(Fn, U, sig, V);                                   // :525
-    if (material != SAND) {
-      float J = 1.0f;                                        // :527-536
-      bool clamped = false;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        float ns = sig[d];
-        if (material == SNOW) ns = fminf(fmaxf(sig[d], 1.0f - 2.5e-2f), 1.0f + 4.5e-3f);
-        if (K.support_plasticity) Jp *= sig[d] / ns;
-        clamped = clamped || (ns != sig[d]);
-        sig[d] = ns;
-        J *= ns;
-      }
-      // :543-545 rebuilds F = U sig V^T for every snow particle; without a clamp that is F itself
-      if (material == SNOW && clamped) usvt<D>(U, sig, V, Fn);
-      // :547-551  2 mu (F - U V^T) F^T + la J (J - 1) I with F = U sig V^T:
-      //   (F - R) F^T = U (sig - 1) V^T V sig U^T = U diag(sig (sig - 1)) U^T -- no V, no F - R cancellation
-      const float p = la * J * (J - 1.0f);
-      float dg[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) dg[d] = 2.0f * mu * sig[d] * (sig[d] - 1.0f) + p;
-      udut<D>(U, dg, stress);
-    } else if (K.support_plasticity) {                       // :553-566
-      sand_projection<D>(K, sig, Jp);
-      usvt<D>(U, sig, V, Fn);
-      // center_i = (2 mu_0 log sig_i + lambda_0 sum log sig) / sig_i; U center V^T F^T = U diag(center sig) U^T
-      float ls[D], lsum = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) { ls[i] = logf(sig[i]); lsum += ls[i]; }
-      float dg[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) dg[i] = 2.0f * K.mu_0 * ls[i] + K.lambda_0 * lsum;
-      udut<D>(U, dg, stress);
-    } else {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
+      finish_affine<D>(K, dt, stress, C, mass, affine);
+      return true;
     }
+    if (material == SAND && K.support_plasticity) {
+      const float J = det<D>(Fn);
+      float n2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < DD; ++i) n2 += Fn[i] * Fn[i];
+      // (J > 1e-2 and sum sigma^2 < 12 bound every sigma away from the 1e-4 floor of :326)
+      if (!(J > 1e-2f) || !(n2 < 12.0f)) return false;
+      const float tr = logf(J) + Jp;
+      if (!(tr >= 0.0f)) return false;
+      if (!polar3_newton(Fn, Rp, Jpol)) return false;
+      Jp = tr;                                               // :331-333
+#pragma unroll
+      for (int i = 0; i < DD; ++i) { Fn[i] = Rp[i]; stress[i] = 0.0f; }
+      finish_affine<D>(K, dt, stress, C, mass, affine);
+      return true;
     }
   }
+  return false;
+}
+
+// the general path: Fn in = trial F, out = new stored F
+template <int D>
+MPM_HD void particle_update_svd(const Consts& K, float dt, int material, float* Fn, const float* C, float& Jp,
+                                float* affine, float& mass) {
+  constexpr int DD = D * D;
+  float mu, la;
+  lame(K, material, Jp, mu, la);
+  float stress[DD];
+  mass = K.p_mass;
+  float U[DD], V[DD], sig[D];
+  svd<D>(Fn, U, sig, V);                                     // :525
+  if (material != SAND) {
+    float J = 1.0f;                                          // :527-536
+    bool clamped = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      float ns = sig[d];
+      if (material == SNOW) ns = fminf(fmaxf(sig[d], 1.0f - 2.5e-2f), 1.0f + 4.5e-3f);
+      if (K.support_plasticity) Jp *= sig[d] / ns;
+      clamped = clamped || (ns != sig[d]);
+      sig[d] = ns;
+      J *= ns;
+    }
+    // :543-545 rebuilds F = U sig V^T for every snow particle; without a clamp that is F itself
+    if (material == SNOW && clamped) usvt<D>(U, sig, V, Fn);
+    // :547-551  2 mu (F - U V^T) F^T + la J (J - 1) I with F = U sig V^T:
+    //   (F - R) F^T = U (sig - 1) V^T V sig U^T = U diag(sig (sig - 1)) U^T -- no V, no F - R cancellation
+    const float p = la * J * (J - 1.0f);
+    float dg[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) dg[d] = 2.0f * mu * sig[d] * (sig[d] - 1.0f) + p;
+    udut<D>(U, dg, stress);
+  } else if (K.support_plasticity) {                         // :553-566
+    sand_projection<D>(K, sig, Jp);
+    usvt<D>(U, sig, V, Fn);
+    // center_i = (2 mu_0 log sig_i + lambda_0 sum log sig) / sig_i; U center V^T F^T = U diag(center sig) U^T
+    float ls[D], lsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { ls[i] = logf(sig[i]); lsum += ls[i]; }
+    float dg[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dg[i] = 2.0f * K.mu_0 * ls[i] + K.lambda_0 * lsum;
+    udut<D>(U, dg, stress);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DD; ++i) stress[i] = 0.0f;
+  }
+  finish_affine<D>(K, dt, stress, C, mass, affine);
+}
+
+template <int D>
+MPM_HD void particle_update(const Consts& K, float dt, int material, float* F, const float* C,
+                            float& Jp, float* affine, float& mass) {
+  constexpr int DD = D * D;
+  float Fn[DD];
+  trial_F<D>(K, dt, material, F, C, Jp, Fn);
+  if (!particle_update_fast<D>(K, dt, material, Fn, C, Jp, affine, mass))
+    particle_update_svd<D>(K, dt, material, Fn, C, Jp, affine, mass);
 #pragma unroll
   for (int i = 0; i < DD; ++i) F[i] = Fn[i];                 // :567
-  float scale = -dt * K.p_vol * 4.0f * K.inv_dx2;            // :569
-#pragma unroll
-  for (int i = 0; i < DD; ++i) affine[i] = scale * stress[i] + mass * C[i];   // :574
 }
 
 }  // namespace mpm

@@ -65,7 +65,21 @@ __device__ __forceinline__ void p2g3_prepare(const SubstepArgs<3>& a, int nb, in
   order[hist[m1] + r1] = lane + 32;
 }
 
-template <int CHUNK, int MINB>
+// Work-queue position -> particle block.  With slabs the blocks of the last and of the first block column come
+// first: their tiles hold the nodes of the grid columns shared with the neighbours, which travel (as vector
+// reductions into the neighbour's halo plane over NVLink) while the interior of the slab is still being scattered.
+__device__ __forceinline__ int p2g3_block_of(int q, int npb, int n_hi) {
+  return q < n_hi ? npb - n_hi + q : q - n_hi;
+}
+// tell the neighbours that every node of the shared columns has been sent for substep epoch + 1
+__device__ __forceinline__ void p2g3_publish_halo(const CommBufs& cb) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    if (cb.flag_halo[s]) st_release_sys(cb.flag_halo[s], cb.epoch + 1u);
+}
+
+// FUSED: the multi-GPU variant (fused halo); the single-device kernel carries none of its state.
+template <int CHUNK, int MINB, bool FUSED, bool DEFER>
 __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
   constexpr int D = 3;
   using G = Geo<3>;
@@ -76,12 +90,21 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
   __shared__ int s_cs[2][G::CELLS + 1];
   __shared__ int s_order[2][G::CELLS];
   __shared__ int s_nbr[G::NO];
-  __shared__ int s_b, s_next, s_ticket;
+  __shared__ int s_b, s_next, s_ticket, s_ticket_q;
   __shared__ int s_hist[32];
+  __shared__ unsigned short s_queue[(P2G3::T / 32) * ((CHUNK + P2G3::T - 1) / P2G3::T) * 32];   // per warp: deferred particles (chunk-relative index | material << 12)
+  static_assert(CHUNK <= 4096, "queue entries hold a 12-bit index");
   pdl_enter();
-  if (a.st->err) return;
-  const int npb = a.st->npb;
   const int tid = threadIdx.x, lane = tid & 31;
+  constexpr bool fused = FUSED;
+  if (a.st->err) {
+    // a neighbour must never wait for a message that will not come
+    if (fused && blockIdx.x == 0 && tid == 0) p2g3_publish_halo(a.cb);
+    return;
+  }
+  const int npb = a.st->npb;
+  const int n_bhi = fused ? a.st->bnd_hi : 0, n_bnd = fused ? a.st->bnd_hi + a.st->bnd_lo : 0;
+  if (fused && n_bnd == 0 && blockIdx.x == 0 && tid == 0) p2g3_publish_halo(a.cb);   // nothing to send
   const size_t cap = a.cap;
   const int sl = tid % P2G3::SL;
   const float slf = (float)sl;
@@ -91,15 +114,21 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
 
   if (tid == 0) { s_b = atomicAdd(&a.st->work_p2g, 1); s_ticket = 0; }
   __syncthreads();
-  int b = s_b;
+  int qpos = s_b;                                           // position in the work queue
+  int b = qpos < npb ? p2g3_block_of(qpos, npb, n_bhi) : npb;
   if (tid < 32) p2g3_prepare(a, b, npb, lane, s_cs[0], s_order[0], s_hist);
   int u = 0;
   __syncthreads();
   while (b < npb) {
-    if (tid == 0) s_next = atomicAdd(&a.st->work_p2g, 1);   // claimed one block ahead
+    if (tid == 0) {                                         // claimed one block ahead
+      const int qn = atomicAdd(&a.st->work_p2g, 1);
+      s_next = qn < npb ? p2g3_block_of(qn, npb, n_bhi) : npb;
+      s_ticket_q = qn;
+    }
     const int start = a.pb_start[b], end = a.pb_start[b + 1];
     const int cnt = end - start;
     if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
+    const bool boundary = fused && qpos < n_bnd;            // fused halo: this block's tile touches a shared column
     const int* cs = s_cs[u];
     const int cell = s_order[u][tid / P2G3::SL];
     const int c_lo = cs[cell], c_hi = cs[cell + 1];
@@ -109,7 +138,8 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
     for (int c0 = 0; c0 < cnt; c0 += CH) {
       const int cn = min(CH, cnt - c0);
       const bool last = c0 + CH >= cnt;
-      // ---- phase 1: constitutive update (engine/mpm_solver.py:506-574), payload to shared memory
+      if constexpr (!DEFER) {
+      // ---- phase 1 (single pass): constitutive update (engine/mpm_solver.py:506-574), payload to shared memory
       constexpr int NIT = (CH + T - 1) / T;
       uint32_t pq[NIT];
 #pragma unroll
@@ -147,6 +177,98 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
         pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
         pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
         pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
+      }
+      } else {
+      // ---- phase 1: constitutive update (engine/mpm_solver.py:506-574), payload to shared memory.
+      // Pass a: every particle; the cases that need no SVD (water, elastic, snow inside its clamp interval,
+      // expanding sand: mpm_math.cuh) finish here.  The others park their trial F, Jp, v and fx in their own
+      // (still unused) payload slot and join their WARP's queue; pass b runs that queue COMPACTED (a warp owns ~107 of
+      // the 640 particles of a chunk), so the lanes are all on the ~1500-instruction SVD path instead of a few lanes
+      // dragging 32 through it in every iteration -- with no CTA barrier between the passes.
+      constexpr int NIT = (CH + T - 1) / T;
+      uint32_t pq[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
+      unsigned short* wq = s_queue + (tid >> 5) * (NIT * 32);
+      int nq = 0;
+#pragma unroll 1
+      for (int q = tid; q < ((cn + 31) & ~31); q += T) {
+        const bool live = q < cn;
+        const int s = start + c0 + q;
+        const uint32_t p = pq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
+        bool done = true;
+        int mat = 0;
+        if (live) {
+          float x[D], v[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            x[d] = ldf(a.src, cap, FL::X + d, p);
+            v[d] = ldf(a.src, cap, FL::V + d, p);
+          }
+          float F[D * D], C[D * D], aff[D * D], mass;
+#pragma unroll
+          for (int i = 0; i < D * D; ++i) {
+            F[i] = ldf(a.src, cap, FL::F + i, p);
+            C[i] = ldf(a.src, cap, FL::C + i, p);
+          }
+          float Jp = ldf(a.src, cap, FL::JP, p);
+          mat = (int)ldu(a.src, cap, FL::MAT, p);
+          float Fn[D * D];
+          trial_F<D>(a.K, a.dt, mat, F, C, Jp, Fn);
+          done = particle_update_fast<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
+          float fx[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
+          const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
+          if (done) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, Fn[i]);
+            stf(a.dst, cap, FL::JP, s, Jp);
+            const float dx = a.K.dx;                                     // dpos = (o - fx) * dx
+            pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+            pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
+            pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
+            pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
+          } else {
+            pay[q * PS + (0 ^ sw)] = make_float4(Fn[0], Fn[1], Fn[2], Fn[3]);
+            pay[q * PS + (1 ^ sw)] = make_float4(Fn[4], Fn[5], Fn[6], Fn[7]);
+            pay[q * PS + (2 ^ sw)] = make_float4(Fn[8], Jp, v[0], v[1]);
+            pay[q * PS + (3 ^ sw)] = make_float4(v[2], fx[0], fx[1], fx[2]);
+          }
+        }
+        // append to this WARP's queue of deferred particles (the count is warp-uniform: no atomics)
+        const unsigned dm = __ballot_sync(0xffffffffu, !done);
+        if (!done) wq[nq + __popc(dm & ((1u << lane) - 1u))] = (unsigned short)(q | (mat << 12));
+        nq += __popc(dm);
+      }
+      __syncwarp();                                                     // this warp's queue and stashes are visible
+#pragma unroll 1
+      for (int i = lane; i < nq; i += 32) {
+        const unsigned e = wq[i];
+        const int q = (int)(e & 0xfffu), mat = (int)(e >> 12);
+        const int s = start + c0 + q;
+        const uint32_t p = a.perm[s];
+        const int sw = (q >> 1) & 3;
+        const float4 s0 = pay[q * PS + (0 ^ sw)], s1 = pay[q * PS + (1 ^ sw)], s2 = pay[q * PS + (2 ^ sw)],
+                     s3 = pay[q * PS + (3 ^ sw)];
+        float Fn[D * D] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x};
+        float Jp = s2.y;
+        const float v[D] = {s2.z, s2.w, s3.x}, fx[D] = {s3.y, s3.z, s3.w};
+        float C[D * D], aff[D * D], mass;
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) C[k] = ldf(a.src, cap, FL::C + k, p);
+        particle_update_svd<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) stf(a.dst, cap, FL::F + k, s, Fn[k]);
+        stf(a.dst, cap, FL::JP, s, Jp);
+        const float dx = a.K.dx;
+        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
+        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
+        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
+      }
       }
       __syncthreads();                                                  // payload ready
       // next block's particle rows towards L2 while this one computes (storage order is last
@@ -233,7 +355,7 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
             my[j * P2G3::CP + 2] = make_float4(acc01[j * 3 + 2].x, acc01[j * 3 + 2].y, acc23[j * 3 + 2].x,
                                                acc23[j * 3 + 2].y);
         }
-        if (tid == 0) s_ticket = 0;
+        if (tid == 0) { s_ticket = 0; }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 3; ++j) {                                   // z = cz + 1
@@ -253,6 +375,12 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
       }
       __syncthreads();                                                  // copies ready
       // ---- phase 4: node = sum of the copies (i, j) with 0 <= nx - i, ny - j < 4 -> global grid
+      int hb_x = 0, hb_y = 0, hb_z = 0;      // absolute block column, (y, z) position in the halo plane
+      if (boundary) {
+        int rel[3];
+        key_to_rel<3>(a.L, a.pb_key[b], rel);
+        hb_x = rel[0] + a.L.ob[0]; hb_y = rel[1]; hb_z = rel[2];
+      }
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int n = tid + pass * T;
@@ -273,11 +401,32 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
             tile_node<D>(n, oct, cellg);
             const int slot = s_nbr[oct];
             if (slot >= 0) red_add_v4(a.grid + (size_t)slot * G::CELLS + cellg, val);
+            if (boundary) {
+              // a node of a grid column shared with a neighbour rank: the same partial sum also goes into that
+              // neighbour's halo plane (peer memory over NVLink); its grid op adds the plane to its own sums
+              const int col = hb_x + (oct & 1);
+              const int side = col == a.slab.hi ? 1 : (col == a.slab.lo ? 0 : -1);
+              if (side >= 0 && a.cb.plane_out[side]) {
+                const int py = hb_y + ((oct >> 1) & 1), pz = hb_z + ((oct >> 2) & 1);
+                float4* plane = a.cb.plane_out[side] + (size_t)(a.cb.epoch % 3u) * a.cb.plane_blocks * G::CELLS;
+                red_add_v4(plane + (size_t)(py * a.L.eb[2] + pz) * G::CELLS + cellg, val);
+              }
+            }
           }
         }
       }
+      if (boundary && last) __threadfence_system();                     // my reductions are performed before ...
+      int q_next = 0;
+      if (fused) q_next = s_ticket_q;
       if (last) { b = s_next; u ^= 1; }
       __syncthreads();                                                  // copies dead, s_next consumed
+      if (boundary && last && tid == 0) {                               // ... the block is counted as sent
+        if (atomicAdd(&a.st->halo_done, 1) == n_bnd - 1) {
+          __threadfence_system();
+          p2g3_publish_halo(a.cb);
+        }
+      }
+      if (fused && last) qpos = q_next;
     }
   }
 }

@@ -119,6 +119,8 @@ def _make_distributed_solver():
                                           self.inv_dx)
             self.substep_batch = substep_batch
             self._global_n = 0
+            self._global_ids = True      # `id` holds global ids: the insertion-order read-backs are disabled
+            self._next_box = None
             self._mig_cap, self._halo_cap = int(mig_capacity), int(halo_capacity)
             lib, dev = self._lib, self._device
             mig_bytes = lib.mpm_comm_bytes(self.dim, 0, self._mig_cap)
@@ -144,13 +146,15 @@ def _make_distributed_solver():
                 self._setup_peer()
 
         def _setup_peer(self):
-            """Exchange CUDA IPC handles of the receive regions and map the neighbours' ones."""
+            """Exchange CUDA IPC handles of the receive regions and map the neighbours' ones.  The handles travel by
+            any backend (NCCL, or gloo when several ranks share one GPU in the tests); the data path is peer memory."""
             lib, ctx = self._lib, self._ctx
             self._check(lib.mpm_peer_alloc(ctx, self._mig_cap, self._halo_cap), 'mpm_peer_alloc')
             h = (ctypes.c_uint8 * 64)()
             self._check(lib.mpm_peer_handle(ctx, h), 'mpm_peer_handle')
-            mine = torch.tensor(list(h), dtype=torch.uint8, device=self._device)
-            allh = [torch.empty(64, dtype=torch.uint8, device=self._device) for _ in range(self.world)]
+            cdev = self._coll_device()
+            mine = torch.tensor(list(h), dtype=torch.uint8, device=cdev)
+            allh = [torch.empty(64, dtype=torch.uint8, device=cdev) for _ in range(self.world)]
             dist.all_gather(allh, mine, group=self.group)
             for side, peer in ((0, self.slab.left), (1, self.slab.right)):
                 if peer is not None:
@@ -158,71 +162,150 @@ def _make_distributed_solver():
                     self._check(lib.mpm_peer_open(ctx, side, buf), 'mpm_peer_open')
             dist.barrier(group=self.group)
 
+        # ---- collectives that work on any backend (NCCL: device tensors, gloo: host tensors) ----
+        def _coll_device(self):
+            if dist.is_initialized() and dist.get_backend(self.group) == 'gloo':
+                return torch.device('cpu')
+            return self._device
+
+        def _allreduce_ints(self, values, op):
+            t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=self._coll_device())
+            if self.world > 1 and dist.is_initialized():
+                dist.all_reduce(t, op=op, group=self.group)
+            return [int(v) for v in t.tolist()]
+
         # ---- seeding: same call on every rank, each keeps its slab -------------
+        _SLICE = 1 << 22     # rows selected per call of mpm_seed_positions_slab (it borrows the binning scratch)
+
+        def _add_device_positions(self, dev, id_base, material, color, velocity, emitter=0):
+            """Append the rows of `dev` ((n, dim) f32 on the device) that fall into this rank's slab; row i of `dev`
+            carries the global id id_base + i.  Selection, block-sorted storage order and the count come from the
+            library (mpm_seed_positions_slab: one radix sort), no eager tensor ops."""
+            n_all = int(dev.shape[0])
+            kept_total = 0
+            self._next_box = None
+            for lo in range(0, n_all, self._SLICE):
+                part = dev[lo:lo + self._SLICE]
+                m = int(part.shape[0])
+                self._reserve(m)        # worst case: every row is mine (and the sort needs m <= capacity)
+                kept = ctypes.c_int64()
+                self._check(
+                    self._lib.mpm_seed_positions_slab(self._ctx, part.data_ptr(), m, int(id_base) + lo, int(material),
+                                                      int(color), self._vec(velocity), int(emitter),
+                                                      ctypes.byref(kept), self._stream()), 'mpm_seed_positions_slab')
+                self._n += int(kept.value)
+                kept_total += int(kept.value)
+            return kept_total
+
         def add_particles(self, particles, material, color=0xFFFFFF, velocity=None):
-            """Same call on every rank; each keeps the rows whose base block lies in its slab.  The rows are
-            uploaded once and selected on the device (same f32 arithmetic as the binning kernel and as
-            SlabDecomposition.block_x), global ids = position in the call sequence."""
+            """Same call with the same data on every rank (like every add_* of this class): each rank keeps the rows
+            whose base block lies in its slab; global ids = position in the call sequence."""
             particles = np.ascontiguousarray(np.asarray(particles, dtype=np.float32))
             assert particles.ndim == 2 and particles.shape[1] == self.dim
+            self.set_source_velocity(velocity)
             n_all = len(particles)
             if n_all == 0:
                 return
             with torch.cuda.device(self._device):
-                dev = torch.from_numpy(particles).to(self._device)
-                base = torch.floor(dev[:, 0] * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
-                bx = torch.div(base + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor')
-                keep = (bx >= self.slab.lo) & (bx < self.slab.hi)
-                cnt = int(keep.sum().item())
-                if cnt == n_all:
-                    ids = torch.arange(self._global_n, self._global_n + n_all, dtype=torch.int32, device=self._device)
-                else:
-                    idx = torch.nonzero(keep).squeeze(1)
-                    dev = dev.index_select(0, idx).contiguous()
-                    ids = (idx + self._global_n).to(torch.int32)
-                if cnt >= (1 << 15) and self.grid_size == 4096:
-                    # store the rows sorted by leaf block (ids keep the call order), as the single-GPU solver does for
-                    # large arrays: the first substep then reads block-local rows instead of gathering at random
-                    b = torch.floor(dev * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
-                    b = torch.div(b + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor').clamp_(0, 1023)
-                    key = b[:, 0]
-                    for d in range(1, self.dim):
-                        key = key * 1024 + b[:, d]
-                    order = torch.argsort(key)
-                    dev = dev.index_select(0, order).contiguous()
-                    ids = ids.index_select(0, order)
-                self._global_n += n_all
-                n0 = self._n
-                self._seed_from_device(dev, material, color, velocity)
-                if cnt:
-                    cur = ctypes.c_int32()
-                    self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
-                    id_row = self._nf - 2          # x v F C Jp material color id emitter
-                    self._state[cur.value, id_row, n0:n0 + cnt] = ids
+                for lo in range(0, n_all, self._SLICE):      # bounded staging: never the whole array on the device
+                    dev = torch.from_numpy(particles[lo:lo + self._SLICE]).to(self._device)
+                    self._add_device_positions(dev, self._global_n + lo, material, color, velocity)
+            self._global_n += n_all
+
+        def add_local_particles(self, particles, material, color=0xFFFFFF, velocity=None, id_base=0):
+            """Pre-partitioned seeding: `particles` are rows of THIS rank only (rows outside its slab are dropped),
+            row i gets the global id id_base + i; the caller keeps the id ranges of the ranks disjoint.  Large runs
+            use this so that no rank ever touches another rank's rows."""
+            particles = np.ascontiguousarray(np.asarray(particles, dtype=np.float32))
+            assert particles.ndim == 2 and particles.shape[1] == self.dim
+            self.set_source_velocity(velocity)
+            kept = 0
+            with torch.cuda.device(self._device):
+                for lo in range(0, len(particles), self._SLICE):
+                    dev = torch.from_numpy(particles[lo:lo + self._SLICE]).to(self._device)
+                    kept += self._add_device_positions(dev, int(id_base) + lo, material, color, velocity)
+            self._global_n = max(self._global_n, int(id_base) + len(particles))
+            return kept
+
+        def _add_generated(self, mode, num, a3, b3, material, color, velocity):
+            """add_cube / add_ellipsoid: every rank generates the SAME points as the single-device solver would
+            (counter-based generator keyed by the global id) slice by slice on the device and keeps its slab."""
+            seed = self._next_seed()
+            self.set_source_velocity(velocity)
+            with torch.cuda.device(self._device):
+                for lo in range(0, num, self._SLICE):
+                    m = min(self._SLICE, num - lo)
+                    x = torch.empty((m, self.dim), dtype=torch.float32, device=self._device)
+                    self._check(
+                        self._lib.mpm_seed_generate(self._ctx, mode, m, self._global_n + lo, self._vec(a3), self._vec(b3),
+                                                    seed, x.data_ptr(), self._stream()), 'mpm_seed_generate')
+                    self._add_device_positions(x, self._global_n + lo, material, color, velocity)
+            self._global_n += num
+
+        def add_cube(self, lower_corner, cube_size, material, color=0xFFFFFF, sample_density=None, velocity=None):
+            if sample_density is None:
+                sample_density = 2**self.dim
+            vol = 1
+            for i in range(self.dim):
+                vol = vol * cube_size[i]
+            num = int(sample_density * vol / self.dx**self.dim + 1)              # reference :873
+            assert self._global_n + num <= self.max_num_particles
+            self._add_generated(1, num, lower_corner, cube_size, material, color, velocity)
+
+        def add_ellipsoid(self, center, radius, material, color=0xFFFFFF, sample_density=None, velocity=None):
+            import math
+            import numbers
+            if sample_density is None:
+                sample_density = 2**self.dim
+            if isinstance(radius, numbers.Number):
+                radius = [radius] * self.dim
+            radius = list(radius)
+            num = math.pi if self.dim == 2 else 4 / 3 * math.pi
+            for i in range(self.dim):
+                num *= radius[i] * self.inv_dx
+            num = int(math.ceil(num * sample_density))                            # reference :997-1005
+            assert self._global_n + num <= self.max_num_particles
+            self._add_generated(2, num, center, radius, material, color, velocity)
+
+        def add_mesh(self, triangles, material, color=0xFFFFFF, sample_density=None, velocity=None, translation=None,
+                     emmiter_id=0):
+            assert self.dim == 3
+            if sample_density is None:
+                sample_density = 2**self.dim
+            self.set_source_velocity(velocity)
+            if self.voxelizer is None:
+                raise RuntimeError('add_mesh needs use_voxelizer=True')
+            self.voxelizer.voxelize(triangles)          # every rank rasterises the (small) mesh; each keeps its slab
+            pos = self.voxelizer.sample_particles(sample_density=sample_density, translation=translation,
+                                                  grid_size=self.grid_size, seed=self._next_seed())
+            n = int(pos.shape[0])
+            if n:
+                with torch.cuda.device(self._device):
+                    self._add_device_positions(pos, self._global_n, material, color, velocity, emitter=emmiter_id)
+            self._global_n += n
+
+        def add_ngon(self, *a, **k):
+            MPMSolver.add_ngon(self, *a, **k)           # host-generated points -> add_particles (same on every rank)
+
+        def read_restart(self, num_particles, pos, vel, material, color):
+            raise NotImplementedError('restart a distributed run through add_particles per material')
 
         def clear_particles(self):
             if self.comm == 'peer':
                 self.flush_migration()       # collective: drain what the last substep published to the neighbours
             super().clear_particles()
             self._global_n = 0
+            self._next_box = None
             for t in self._mig_send:
                 if t is not None:
                     t[0] = 0
 
-        def add_cube(self, *a, **k):
-            raise NotImplementedError('seed through add_particles on the distributed solver')
-
-        add_ellipsoid = add_cube
-        add_mesh = add_cube
-
         # ---- stepping -------------------------------------------------------------
         def _global_box(self):
+            """Base-cell bounding box of the particles of ALL ranks: one all-reduce (MAX of (-lo, hi))."""
             lo, hi = self._local_box()
-            t_lo = torch.tensor(lo, dtype=torch.int64, device=self._device)
-            t_hi = torch.tensor(hi, dtype=torch.int64, device=self._device)
-            dist.all_reduce(t_lo, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(t_hi, op=dist.ReduceOp.MAX, group=self.group)
-            return [int(v) for v in t_lo.tolist()], [int(v) for v in t_hi.tolist()]
+            r = self._allreduce_ints([-v for v in lo] + list(hi), dist.ReduceOp.MAX)
+            return [-v for v in r[:3]], r[3:]
 
         def _local_box(self):
             lo = (ctypes.c_int32 * 3)()
@@ -274,10 +357,15 @@ def _make_distributed_solver():
                                s.right, self.group)
 
         def _run_substeps(self, dt, count):
+            """`count` substeps in batches of `substep_batch`.  Per batch the host does ONE synchronisation
+            (mpm_batch_end) and ONE all-reduce that carries both the agreement on success and the bounding box the
+            next batch's key layout needs (G2P measured it on the device)."""
             left = count
+            box = getattr(self, '_next_box', None)
+            self._next_box = None
             while left > 0:
                 nb = min(left, max(1, self.substep_batch))
-                glo, ghi = self._global_box()
+                glo, ghi = box if box is not None else self._global_box()
                 if glo[0] > ghi[0]:
                     return self.stats()          # no particles anywhere
                 self._batch_begin(glo, ghi)
@@ -291,17 +379,45 @@ def _make_distributed_solver():
                         self._exchange_halo()
                         self._substep_post(dt)
                 rc = self._batch_end()
+                st = self.stats()
+                have = self._n > 0 and st.bbox_min[0] <= st.bbox_max[0]
+                lo = list(st.bbox_min) if have else [INT_MAX] * 3
+                hi = list(st.bbox_max) if have else [INT_MIN] * 3
                 # every rank must agree on success before the next batch is enqueued
-                flag = torch.tensor([abs(rc)], dtype=torch.int32, device=self._device)
-                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-                worst = int(flag.item())
+                r = self._allreduce_ints([abs(rc)] + [-v for v in lo] + hi, dist.ReduceOp.MAX)
+                worst = r[0]
                 if rc != 0 or worst != 0:
                     raise _lib.MPMError(f'distributed batch failed (local rc {rc}, worst {worst}): '
                                         + self._lib.mpm_last_error(self._ctx).decode()
                                         + ' -- capacities (reserve_blocks, mig_capacity, halo_capacity) cannot be '
                                           'grown inside a distributed batch')
+                box = ([-v for v in r[1:4]], r[4:7])
                 left -= nb
+            self._next_box = box                  # valid until particles are added or cleared
             return self.stats()
+
+        def _advance(self, dt, count, smry_writer):
+            """A substep is a collective (neighbour exchanges, the global box): a rank that holds no particle right
+            now must still take part -- it may be about to receive some."""
+            st = self._run_substeps(dt, count)
+            cur_frame_velocity = self._allmax_float(float(st.max_velocity) if self._n > 0 else 0.0)
+            self.t += dt * count
+            if smry_writer is not None:
+                smry_writer.add_scalar("substep_max_CFL", cur_frame_velocity * dt / self.dx, self.total_substeps)
+            self.all_time_max_velocity = max(self.all_time_max_velocity, cur_frame_velocity)
+
+        def _allmax_float(self, v):
+            t = torch.tensor([float(v)], dtype=torch.float64, device=self._coll_device())
+            if self.world > 1 and dist.is_initialized():
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return float(t.item())
+
+        def compute_max_velocity(self):
+            return self._allmax_float(MPMSolver.compute_max_velocity(self))
+
+        def compute_max_grid_velocity(self, grid_v=None):
+            """Global maximum: with use_adaptive_dt every rank must derive the same dt (reference :762-770)."""
+            return self._allmax_float(MPMSolver.compute_max_grid_velocity(self))
 
         def reserve_blocks(self, max_blocks):
             """Pre-size the leaf-block workspace (a capacity miss cannot be retried inside a distributed batch)."""
@@ -335,35 +451,62 @@ def _make_distributed_solver():
         # ---- read-back ----------------------------------------------------------------
         def particle_info(self):
             """MPMSolver.particle_info() (ref engine/mpm_solver.py:1172-1180) for THIS rank's particles, in storage
-            order, plus their global ids ('id').  Call flush_migration() first: rows of particles that have been
-            handed to a neighbour are excluded here (same f32 arithmetic as the binning), arrivals must have been
-            appended.  One device-side selection, one copy into pinned host memory per field."""
+            order, plus their global ids ('id').  Call flush_migration() first (arrivals must have been appended);
+            rows already handed to a neighbour are skipped.  One library kernel compacts the owned rows
+            (mpm_export_local), one copy into pinned host memory."""
             n, d = self._n, self.dim
-            names = ('position', 'velocity', 'material', 'color', 'id')
-            if n == 0:
-                out = {'position': np.zeros((0, d), np.float32), 'velocity': np.zeros((0, d), np.float32)}
-                out.update({k: np.zeros(0, np.int32) for k in names[2:]})
-                return out
-            cur = ctypes.c_int32()
-            self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
+            w = 2 * d + 3
+            cnt = ctypes.c_int64()
             with torch.cuda.device(self._device):
-                torch.cuda.current_stream(self._device).synchronize()
-                st = self._state[cur.value]
-                x0 = st[0, :n].view(torch.float32)
-                base = torch.floor(x0 * np.float32(self.inv_dx) - np.float32(0.5)).to(torch.int64)
-                bx = torch.div(base + self.grid_size // 2, self.leaf_block_size, rounding_mode='floor')
-                keep = (bx >= self.slab.lo) & (bx < self.slab.hi)
-                idx = torch.nonzero(keep).squeeze(1)
-                jp = 2 * d + 2 * d * d
-                rows = [st[0:d], st[d:2 * d], st[jp + 1:jp + 2], st[jp + 2:jp + 3], st[jp + 3:jp + 4]]
-                out = {}
-                for name, r in zip(names, rows):
-                    sel = r[:, :n].index_select(1, idx).t().contiguous()          # (count, words)
-                    host = torch.empty(sel.shape, dtype=torch.int32, pin_memory=True)
-                    host.copy_(sel)
-                    a = host.numpy()
-                    out[name] = a.view(np.float32) if name in ('position', 'velocity') else a[:, 0]
-            return out
+                dev = torch.empty((max(n, 1), w), dtype=torch.int32, device=self._device)
+                self._check(self._lib.mpm_export_local(self._ctx, dev.data_ptr(), ctypes.byref(cnt), self._stream()),
+                            'mpm_export_local')
+                k = int(cnt.value)
+                host = torch.empty((k, w), dtype=torch.int32, pin_memory=k > 0)
+                if k:
+                    host.copy_(dev[:k])
+            a = host.numpy()
+            return {'position': np.ascontiguousarray(a[:, 0:d]).view(np.float32),
+                    'velocity': np.ascontiguousarray(a[:, d:2 * d]).view(np.float32),
+                    'material': a[:, 2 * d].copy(), 'color': a[:, 2 * d + 1].copy(), 'id': a[:, 2 * d + 2].copy()}
+
+        # The insertion-order read-back paths of MPMSolver index device buffers by `id`, which is a permutation of
+        # [0, n) only on a single-device solver.  Here ids are global: gather by id across the ranks instead.
+        def gather_particle_info(self):
+            """particle_info() of ALL ranks ordered by global id, on every rank (collective)."""
+            mine = self.particle_info()
+            parts = [None] * self.world
+            if self.world > 1 and dist.is_initialized():
+                dist.all_gather_object(parts, mine, group=self.group)
+            else:
+                parts = [mine]
+            merged = {k: np.concatenate([p[k] for p in parts]) for k in mine}
+            order = np.argsort(merged['id'], kind='stable')
+            return {k: v[order] for k, v in merged.items()}
+
+        def _pack_particles(self):
+            return None            # ParticleIO falls back to copy_ranged, which gathers (below)
+
+        def write_particles(self, fn, slice_size=1000000):
+            """Collective: the particles of all ranks in global-id order, written by rank 0 in the reference's
+            .npz format (ref engine/particle_io.py:12-76)."""
+            info = self.gather_particle_info()
+            if self.rank == 0:
+                from .engine.particle_io import ParticleIO
+                ParticleIO.write_arrays(fn, info['position'], info['velocity'], info['color'])
+
+        def write_particles_ply(self, fn):
+            info = self.gather_particle_info()
+            if self.rank == 0:
+                data = np.hstack([info['position'], info['color'].astype(np.uint32)[:, None].view(np.float32)])
+                from .engine.mesh_io import write_point_cloud
+                write_point_cloud(fn, data)
+
+        def _no_insertion_order(self, *a, **k):
+            raise NotImplementedError('insertion-order field read-back is single-device; use particle_info() '
+                                      '(this rank) or gather_particle_info() (all ranks, by global id)')
+
+        copy_ranged = copy_ranged_nd = copy_dynamic = copy_dynamic_nd = debug_binning = _no_insertion_order
 
         def local_rows(self):
             """This rank's live particles: dict of arrays in storage order, with global ids.

@@ -63,6 +63,9 @@ class _Field:
         """Rows [begin, end) in insertion order: gathered on the device, one copy into pinned
         host memory; the returned array is a fresh, caller-owned buffer."""
         s = self._s
+        if getattr(s, '_global_ids', False):
+            raise NotImplementedError('insertion-order field read-back is single-device; use particle_info() / '
+                                      'gather_particle_info() on a DistributedMPMSolver')
         n = s.n_particles[None]
         end = n if end is None else end
         cnt = max(end - begin, 0)

@@ -1,4 +1,11 @@
-"""torchrun worker: N ranks (NCCL) against the undecomposed solver on rank 0's GPU."""
+"""torchrun worker: N ranks against the undecomposed solver on rank 0's GPU.
+
+    MPM_DIST_BACKEND = nccl (default; one GPU per rank) | gloo (ranks may share GPU 0: the control plane -- IPC handle
+                       exchange, per-batch all-reduce -- runs on gloo, the data path is CUDA peer memory as usual)
+    MPM_COMM         = auto | peer | nccl          MPM_FUSED_HALO = 1 | 0 (peer path: fused exchange or legacy kernels)
+    MPM_SCENE        = mixed (five blobs crossing the cuts) | empty_rank (rank > 0 starts with no particle and receives
+                       them by migration, driven through the public step())
+"""
 import os
 import sys
 
@@ -14,41 +21,73 @@ from scenes import mixed_scene  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    backend = os.environ.get('MPM_DIST_BACKEND', 'nccl')
+    local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if backend == 'nccl':
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group('gloo')
     from taichi_elements_b200.distributed import DistributedMPMSolver, SlabDecomposition
     from taichi_elements_b200.engine.mpm_solver import MPMSolver
     dim, res, steps = 3, 32, 24
     comm = os.environ.get('MPM_COMM', 'auto')
+    which = os.environ.get('MPM_SCENE', 'mixed')
     scene = []
-    for i, (p, m, vel) in enumerate(mixed_scene(dim, n_per=500, seed=11)):
-        vel = list(vel)
-        vel[0] = 4.0 if i % 2 == 0 else -4.0
-        scene.append((p, m, vel))
-    allx = np.concatenate([p for p, _, _ in scene])
-    s = DistributedMPMSolver((res, ) * dim, cuts=[0] * 0 if world == 1 else
-                             SlabDecomposition.balanced_cuts(allx[:, 0], world, 4, 4096, float(res)),
-                             mig_capacity=4096, halo_capacity=512, substep_batch=6, device=local, comm=comm)
+    if which == 'mixed':
+        for i, (p, m, vel) in enumerate(mixed_scene(dim, n_per=500, seed=11)):
+            vel = list(vel)
+            vel[0] = 4.0 if i % 2 == 0 else -4.0
+            scene.append((p, m, vel))
+        allx = np.concatenate([p for p, _, _ in scene])
+        cuts = SlabDecomposition.balanced_cuts(allx[:, 0], world, 4, 4096, float(res)) if world > 1 else []
+    else:
+        rng = np.random.default_rng(12)
+        for m, y in ((1, 0.3), (2, 0.5), (0, 0.7)):
+            p = (rng.random((800, 3)) * np.array([0.12, 0.12, 0.2]) + np.array([0.30, y, 0.4])).astype(np.float32)
+            scene.append((p, m, [6.0, 0.0, 0.5]))
+        cut0 = (16 + 2048) // 4                       # first cut at cell 16 (x = 0.5): everything starts left of it
+        cuts = [cut0 + 2 * k for k in range(world - 1)]
+    s = DistributedMPMSolver((res, ) * dim, cuts=cuts, mig_capacity=4096, halo_capacity=1024, substep_batch=6,
+                             device=local, comm=comm)
     for p, m, vel in scene:
         s.add_particles(p, m, velocity=vel)
     s.reserve_blocks(4096)
     dt = s.default_dt
-    s._run_substeps(dt, steps)
+    n0 = s.n_particles[None]
+    if which == 'mixed':
+        s._run_substeps(dt, steps)
+    else:
+        assert (n0 > 0) == (rank == 0), (rank, n0)
+        for _ in range(8):
+            s.step(6 * dt * 0.999)                     # the public path: 6 substeps per frame
+        steps = s.total_substeps
+        dt = 6 * dt * 0.999 / 6
     s.flush_migration()
     got = s.gather_rows()
+    info = s.gather_particle_info()
     ok = True
     if rank == 0:
         ref = MPMSolver((res, ) * dim, device=local)
         for p, m, vel in scene:
             ref.add_particles(p, m, velocity=vel)
-        ref._run_substeps(dt, steps)
+        if which == 'mixed':
+            ref._run_substeps(dt, steps)
+        else:
+            for _ in range(8):
+                ref.step(6 * s.default_dt * 0.999)
         n = ref.n_particles[None]
         vs = float(np.abs(ref.v.to_numpy()).max())
         ok = (len(got['id']) == n and np.array_equal(got['id'], np.arange(n))
               and np.abs(got['x'] - ref.x.to_numpy()).max() <= 2e-5
-              and np.abs(got['v'] - ref.v.to_numpy()).max() <= 5e-3 * vs)
-        print('comm', s.comm, 'max dx', np.abs(got['x'] - ref.x.to_numpy()).max(), 'max dv', np.abs(got['v'] - ref.v.to_numpy()).max())
-    flag = torch.tensor([int(ok)], device='cuda')
+              and np.abs(got['v'] - ref.v.to_numpy()).max() <= 5e-3 * vs
+              and np.array_equal(info['id'], np.arange(n)) and np.array_equal(info['position'], got['x'])
+              and np.array_equal(info['material'], ref.material.to_numpy()))
+        print('comm', s.comm, 'scene', which, 'substeps', steps, 'max dx', np.abs(got['x'] - ref.x.to_numpy()).max(),
+              'max dv', np.abs(got['v'] - ref.v.to_numpy()).max(), 'launches', s.stats().launches)
+    if which == 'empty_rank' and world > 1:
+        ok = ok and (s.n_particles[None] > 0 or rank == 0)          # the other ranks received particles
+    flag = torch.tensor([int(ok)], device='cuda' if backend == 'nccl' else 'cpu')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print('DIST_OK' if int(flag.item()) == 1 else 'DIST_FAIL')

@@ -12,7 +12,7 @@ void host_svd2(const float* F, int n, float* U, float* sig, float* V) {
 // arrays are AoS row-major per particle
 void host_particle_update(int dim, const float* consts12, int support_plasticity, float dt, int n,
                           const int* material, float* F, const float* C, float* Jp,
-                          float* affine, float* mass) {
+                          float* affine, float* mass, int* fast_taken) {
   mpm::Consts K{};
   K.dx = consts12[0]; K.inv_dx = consts12[1]; K.p_vol = consts12[2]; K.p_mass = consts12[3];
   K.mu_0 = consts12[4]; K.lambda_0 = consts12[5]; K.alpha = consts12[6]; K.sand_coef = consts12[7];
@@ -21,6 +21,13 @@ void host_particle_update(int dim, const float* consts12, int support_plasticity
   K.g2p2g = (int)consts12[11] & 1;      // fused-mode variant
   K.clamp_F = ((int)consts12[11] >> 1) & 1;
   for (int i = 0; i < n; ++i) {
+    if (fast_taken) {     // which particles avoid the SVD (the 3D P2G kernel runs the others in a second pass)
+      float Fn[9], a9[9], m, jp = Jp[i];
+      if (dim == 2) { mpm::trial_F<2>(K, dt, material[i], F + 4 * i, C + 4 * i, jp, Fn);
+                      fast_taken[i] = mpm::particle_update_fast<2>(K, dt, material[i], Fn, C + 4 * i, jp, a9, m); }
+      else { mpm::trial_F<3>(K, dt, material[i], F + 9 * i, C + 9 * i, jp, Fn);
+             fast_taken[i] = mpm::particle_update_fast<3>(K, dt, material[i], Fn, C + 9 * i, jp, a9, m); }
+    }
     if (dim == 2)
       mpm::particle_update<2>(K, dt, material[i], F + 4 * i, C + 4 * i, Jp[i], affine + 4 * i, mass[i]);
     else

@@ -78,27 +78,3 @@ def test_neighbour_exchange_gloo(world):
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world)) and len(out) == world
-
-
-def test_device_side_slab_selection_uses_the_binning_arithmetic():
-    """DistributedMPMSolver.add_particles / particle_info select a rank's rows with torch ops
-    (floor(x * inv_dx - 0.5), f32, then integer block arithmetic).  On any backend those ops must agree
-    with SlabDecomposition.block_x (NumPy, the host mirror of the binning kernel), including positions
-    that sit exactly on and next to the cut planes."""
-    import torch
-    from taichi_elements_b200.distributed import SlabDecomposition
-    inv_dx, leaf, grid_size = np.float32(256.0), 4, 4096
-    cuts = [2048 // 4 + 20, 2048 // 4 + 37]
-    rng = np.random.default_rng(9)
-    x = rng.random(200000).astype(np.float32)
-    edges = (np.array([c * leaf - grid_size // 2 for c in cuts], np.float32) + np.float32(0.5)) / inv_dx
-    near = np.array([np.nextafter(e, np.float32(d)) for e in edges for d in (-1, 2)] + list(edges), np.float32)
-    x = np.concatenate([x, near, np.float32(-0.3) + x[:1000]])
-    for rank in range(3):
-        slab = SlabDecomposition(3, rank, cuts, leaf, grid_size, float(inv_dx))
-        t = torch.from_numpy(x)
-        base = torch.floor(t * inv_dx - np.float32(0.5)).to(torch.int64)
-        bx = torch.div(base + grid_size // 2, leaf, rounding_mode='floor')
-        keep = ((bx >= slab.lo) & (bx < slab.hi)).numpy()
-        assert np.array_equal(bx.numpy(), slab.block_x(x))
-        assert np.array_equal(keep, slab.mine(x))

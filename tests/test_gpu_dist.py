@@ -131,15 +131,97 @@ def test_phase_api_equals_substeps_single_rank():
     assert np.abs(got['v'] - ref.v.to_numpy()).max() <= 1e-4 * float(np.abs(ref.v.to_numpy()).max())
 
 
+def _torchrun(world, env, timeout=600):
+    port = 29600 + (os.getpid() * 7 + hash(tuple(sorted(env.items())))) % 2000
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr',
+           '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'dist_worker.py')]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **env))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'DIST_OK' in out.stdout, out.stdout[-3000:]
+    return out.stdout
+
+
 @pytest.mark.parametrize('comm', ['peer', 'nccl'])
 def test_two_ranks_match_single_domain(comm):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    os.environ['MPM_COMM'] = comm
-    port = 29600 + os.getpid() % 1000 + (7 if comm == 'peer' else 0)
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
-           '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'dist_worker.py')]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert 'DIST_OK' in out.stdout
+    _torchrun(2, {'MPM_COMM': comm})
+
+
+@pytest.mark.parametrize('fused', ['1', '0'])
+@pytest.mark.parametrize('world', [2, 3])
+def test_peer_path_ranks_sharing_one_gpu(world, fused):
+    """The transport the scaling runs use -- kernels writing into the neighbour's memory (CUDA IPC mapping), epoch
+    words published with st.release.sys and awaited with ld.acquire.sys -- on ONE GPU: the ranks are separate
+    processes that share device 0 (time-sliced), the control plane runs on gloo.  fused=1: halo inside P2G, waits
+    inside the grid op / unpack kernels; fused=0: the pack / wait / add kernels.  Both must reproduce the
+    undecomposed solver, with particles crossing the cuts."""
+    out = _torchrun(world, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_FUSED_HALO': fused})
+    assert 'comm peer' in out
+
+
+def test_step_with_an_initially_empty_rank():
+    """DistributedMPMSolver.step() must run its collectives on a rank that holds no particle yet; here
+    rank 1 starts empty and is filled by migration (public step() path, peer transport, one GPU)."""
+    _torchrun(2, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_SCENE': 'empty_rank'})
+
+
+def _loopback_ranks(world, res, cuts, **kw):
+    from taichi_elements_b200.distributed import DistributedMPMSolver
+    return [DistributedMPMSolver((res, ) * 3, cuts=cuts, world=world, rank=r, mig_capacity=1024, halo_capacity=256, **kw)
+            for r in range(world)]
+
+
+def test_slab_seeding_and_export_follow_the_host_partition():
+    """mpm_seed_positions_slab / mpm_export_local select a rank's rows with the binning's f32 arithmetic: they must
+    agree with SlabDecomposition.mine (NumPy mirror), including positions exactly on and next to the cut planes."""
+    res, leaf, gs = 32, 4, 4096
+    cuts = [2048 // 4 + 3, 2048 // 4 + 5]
+    rng = np.random.default_rng(9)
+    x = rng.random((60000, 3)).astype(np.float32)
+    edges = (np.array([c * leaf - gs // 2 for c in cuts], np.float32) + np.float32(0.5)) / np.float32(res)
+    near = np.array([np.nextafter(e, np.float32(d)) for e in edges for d in (-1, 2)] + list(edges), np.float32)
+    x[:len(near), 0] = near
+    ranks = _loopback_ranks(3, res, cuts)
+    total = 0
+    for s in ranks:
+        s.add_particles(x[:40000], 1, color=0x123456, velocity=(1, 2, 3))
+        s.add_particles(x[40000:], 2)
+        info = s.particle_info()
+        want = np.nonzero(s.slab.mine(x[:, 0]))[0]
+        assert np.array_equal(np.sort(info['id']), want)
+        order = np.argsort(info['id'])
+        assert np.array_equal(info['position'][order], x[want])
+        assert np.array_equal(info['material'][order], np.where(want < 40000, 1, 2))
+        assert np.allclose(info['velocity'][order][want < 40000], [1, 2, 3])
+        total += len(want)
+        with pytest.raises(NotImplementedError):
+            s.x.to_numpy()                      # insertion-order read-back is single-device (ADVICE r01)
+    assert total == len(x)
+
+
+def test_distributed_add_cube_ellipsoid_mesh_equal_the_single_device_seeders():
+    """add_cube / add_ellipsoid / add_mesh on the distributed solver (every rank the same calls) give exactly the
+    particles of the single-device solver, split by slab (global id = insertion index)."""
+    from oracle.seeding_oracle import icosphere
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    res = 64
+    cuts = [2048 // 4 + 7]
+    ref = MPMSolver((res, ) * 3)
+    ranks = _loopback_ranks(2, res, cuts)
+    mesh = icosphere((0.45, 0.6, 0.5), 0.09, 2)
+    for s in [ref] + ranks:
+        s.rng_seed = 5
+        s.add_cube((0.3, 0.2, 0.3), (0.3, 0.15, 0.2), s.material_water, color=0x010203, velocity=(0, -1, 0))
+        s.add_ellipsoid((0.45, 0.5, 0.4), (0.12, 0.05, 0.1), s.material_sand)
+        s.add_mesh(mesh, s.material_elastic, velocity=(1, 0, 0), emmiter_id=3)
+    want = ref.particle_info()
+    n = ref.n_particles[None]
+    parts = [s.particle_info() for s in ranks]
+    assert all(len(p['id']) > 0 for p in parts) and sum(len(p['id']) for p in parts) == n
+    ids = np.concatenate([p['id'] for p in parts])
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], np.arange(n))
+    for k in ('position', 'velocity', 'material', 'color'):
+        assert np.array_equal(np.concatenate([p[k] for p in parts])[order], want[k]), k

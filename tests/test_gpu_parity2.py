@@ -156,11 +156,13 @@ def test_config2_style_snow_sand_on_friction_planes_50_substeps():
         o.substep(dt)
     assert s._run_substeps(dt, 19).substeps_done == 19
     err = tracking_errors(s, o)
+    print('substep 20:', err)
     assert max(err.values()) <= TOL_MANY, err
     for _ in range(30):
         o.substep(dt)
     assert s._run_substeps(dt, 30).substeps_done == 30
     err = tracking_errors(s, o)
+    print('substep 50:', err)
     # impacts + plastic flow amplify round-off: the two CPU restatements of this algorithm (NumPy and C/OpenMP,
     # independent SVDs, different summation orders) are 3e-3 .. 5e-3 of max |v| apart at substep 50 of this scene
     assert max(err.values()) <= 2e-2, err
@@ -200,7 +202,7 @@ def test_config1_full_size_one_substep_against_c_oracle():
     ub, uc = np.unique(blk, axis=0, return_counts=True)
     order = np.lexsort(pb.T[::-1])
     assert np.array_equal(pb[order], ub.astype(np.int32)) and np.array_equal(cnt[order], uc.astype(np.int32))
-    err = state_errors(s, o)
+    err = state_errors(s, o, dt)
     assert max(err.values()) <= TOL_ONE, err
     cells, gv, gm = s.debug_grid()
     mass = s.p_mass * n

@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "^Voxelizer\|^$" | tail -40 > gpurun_out/r2d_tests.log
+timeout 600 python bench.py --workload multimat_12m --no-weak --no-cpu-baseline --no-parity --no-e2e > gpurun_out/r2d_bench12.json 2> gpurun_out/r2d_bench.err
+timeout 900 python bench.py --no-weak --no-cpu-baseline --no-e2e > gpurun_out/r2d_bench.json 2>> gpurun_out/r2d_bench.err
+timeout 600 python bench.py --workload cube_drop_4m --no-weak --no-cpu-baseline --no-parity --no-e2e > gpurun_out/r2d_bench4.json 2>> gpurun_out/r2d_bench.err

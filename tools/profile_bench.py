@@ -1,6 +1,8 @@
 """Process for ncu to attach to: builds a bench.py workload (default multimat_12m = configs[3] with one eighth of
 the z extent), pre-rolls it and runs a few batches.
-    ncu --set full -k regex:k_p2g3 -s <preroll + warm-up substeps> -c 1 ... python tools/profile_bench.py"""
+    ncu --profile-from-start off --set full -k regex:k_p2g3 -c 1 ... python tools/profile_bench.py
+Only the final `--steps` substeps lie between cudaProfilerStart/Stop (the pre-roll includes capacity-growth retries whose
+kernels are no-ops)."""
 import argparse
 import os
 import sys
@@ -25,11 +27,14 @@ bench.seed(s, chunks, 1)
 dt = bench.substep_dt(w, s.default_dt)
 pre = w['preroll'] if args.preroll < 0 else args.preroll
 s._run_substeps(dt, pre)
+s._run_substeps(dt, args.batch)      # one batch outside the profiled range: steady-state capacities
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
 left = args.steps
 while left > 0:
     st = s._run_substeps(dt, min(args.batch, left))
     left -= args.batch
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print(f'{s.n_particles[None]} particles, {st.n_grid_blocks} active blocks, {st.n_particle_blocks} particle blocks, '
       f'max |v| {st.max_velocity:.3f}, pre-roll {pre}, {args.steps} substeps in batches of {args.batch}')
