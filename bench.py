@@ -77,8 +77,10 @@ def multimat(name, z_cells=232, chunks_per_material=4, y_cells=120.27, side_wall
     for k in range(nchunk):
         lo = (x0 + 28 * k + 0.5, y0, -z_cells / 2 + 0.5)
         hi = (x0 + 28 * (k + 1) + 0.5, y0 + y_cells, z_cells / 2 + 0.5)
-        chunks.append(Chunk(lo, hi, per_chunk, k // chunks_per_material, (0.25 if k % 2 == 0 else -0.25, -1.0, 0.0),
-                            4000 + k))
+        mat = k // chunks_per_material
+        if os.environ.get('MPM_BENCH_MATERIAL'):         # development: the whole scene of ONE material (cost per material)
+            mat = int(os.environ['MPM_BENCH_MATERIAL'])
+        chunks.append(Chunk(lo, hi, per_chunk, mat, (0.25 if k % 2 == 0 else -0.25, -1.0, 0.0), 4000 + k))
     colliders = [((0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 1, 0.5)]      # point, normal, surface (slip), friction
     if side_walls:
         colliders.append(((0.0, 0.0, (-z_cells / 2 + 0.5) * dx), (0.0, 0.0, 1.0), 1, 0.0))
@@ -164,20 +166,40 @@ def substep_dt(w, default_dt):
     return w.get('dt', default_dt)
 
 
+# Relative cost of a particle-substep by material (WATER, ELASTIC, SNOW, SAND), measured on one B200 with the whole
+# configs[3] scene made of ONE material (MPM_BENCH_MATERIAL=k, profiles/README.md): the strong-scaling cuts give every
+# rank the same COST, not the same count (with equal counts the ranks that hold snow and sand set the pace).
+MATERIAL_COST = (1.0, 1.09, 1.21, 1.18)
+
+
 def rank_chunks(w, rank, world):
-    """Chunks whose particles rank `rank` owns, and the cut planes (absolute leaf-block x) of `world` slabs."""
+    """Chunks whose particles rank `rank` needs to generate, and the cut planes (absolute leaf-block x) of `world`
+    slabs.  Bricks (weak scaling): one brick per rank.  Otherwise (strong scaling): cost-balanced cuts on leaf-block
+    boundaries; a rank generates every chunk that overlaps its slab and the solver keeps the rows inside it."""
     ch = w['chunks']
     if world == 1:
         return ch, []
     if hasattr(ch[0], 'rank'):
         mine = [c for c in ch if c.rank == rank]
-        cut_cells = w['cut_cells']
-    else:
-        per = len(ch) // world
-        assert per * world == len(ch), 'the scene splits into 2, 4, 8 or 16 slabs'
-        mine = ch[rank * per:(rank + 1) * per]
-        cut_cells = [w['cut_cells'][per * k - 1] for k in range(1, world)]
-    return mine, [(c + 2048) // 4 for c in cut_cells]
+        return mine, [(c + 2048) // 4 for c in w['cut_cells']]
+    cost = np.array([MATERIAL_COST[c.material] * c.n for c in ch], np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    edges = [c.lo[0] - 0.5 for c in ch] + [ch[-1].hi[0] - 0.5]        # chunk boundaries in base-cell units
+    cuts_cells = []
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        i = int(np.searchsorted(cum, target, side='right')) - 1
+        i = min(max(i, 0), len(ch) - 1)
+        frac = (target - cum[i]) / cost[i]
+        cell = edges[i] + frac * (edges[i + 1] - edges[i])
+        cell = int(round(cell / 4.0)) * 4                               # leaf-block boundary
+        if cuts_cells and cell <= cuts_cells[-1]:
+            cell = cuts_cells[-1] + 4
+        cuts_cells.append(cell)
+    lo = cuts_cells[rank - 1] if rank > 0 else -10**9
+    hi = cuts_cells[rank] if rank < world - 1 else 10**9
+    mine = [c for c in ch if c.hi[0] - 0.5 > lo and c.lo[0] - 0.5 < hi]
+    return mine, [(c + 2048) // 4 for c in cuts_cells]
 
 
 # ------------------------------------------------------------------ clocks

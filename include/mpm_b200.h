@@ -20,12 +20,18 @@
  *     call), matching Blender's use of MPMSolver from a worker thread
  *     (blender/operators.py:403-405).
  *
- * Particle state layout (device, 32-bit words, structure of arrays):
- *   state[set][field][capacity], set in {0,1} (ping-pong), fields in order
- *     x[dim] v[dim] F[dim*dim] C[dim*dim] Jp material color id emitter
- *   (engine/mpm_solver.py:101-136, 263-273).  `id` is the insertion index:
- *   particles are physically kept in grid-block order, `id` restores the
- *   reference's append order on read-back.
+ * Particle state layout (device, 32-bit words): two sets (ping-pong), each an array of TILES of 32 particles;
+ * inside a tile one 128-byte row of 32 lanes per state word:
+ *     state[set][capacity / 32][nf][32],   word(f, p) = ((p / 32) * nf + f) * 32 + p % 32
+ *   nf = mpm_state_fields(dim) words in order  x[dim] v[dim] F[dim*dim] C[dim*dim] Jp tag
+ *   (engine/mpm_solver.py:101-136, 263-273).  A warp reading one word of 32 consecutive particles touches one
+ *   128-byte line (as in a structure of arrays), and every word of a particle sits at a constant offset from one
+ *   address.  Particles are physically kept in grid-block order (every substep writes them to their sorted slot in
+ *   the other set), so only what the physics needs travels: tag = material << 29 | sid, where sid is the row of the
+ *   particle in the STATIC side arrays  statics[3][capacity] = colour, id, emitter  (:117, 129-136), which never
+ *   move.  `id` is the insertion index and restores the reference's append order on read-back.
+ * Read-back calls number the words as the reference orders its fields (mpm_virtual_fields(dim) of them):
+ *     x[dim] v[dim] F[dim*dim] C[dim*dim] Jp material color id emitter.
  */
 #ifndef MPM_B200_H
 #define MPM_B200_H
@@ -44,7 +50,7 @@ extern "C" {
 #define MPM_E_CUDA (-2)
 #define MPM_E_UNBOUND (-3)
 
-#define MPM_ABI_VERSION 3
+#define MPM_ABI_VERSION 4
 
 typedef struct mpm_ctx mpm_ctx;
 
@@ -98,8 +104,10 @@ typedef struct mpm_stats {
 
 int mpm_abi_version(void);
 
-/* words per particle for `dim` (2*dim + 2*dim*dim + 5) */
+/* physical words per particle in a state set (2*dim + 2*dim*dim + 2) */
 int mpm_state_fields(int dim);
+/* words of the read-back numbering (2*dim + 2*dim*dim + 5) */
+int mpm_virtual_fields(int dim);
 /* bytes the workspace must have for `capacity` particles and `max_blocks` leaf blocks */
 size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks);
 
@@ -108,9 +116,15 @@ int mpm_create(const mpm_params* params, mpm_ctx** out);
 int mpm_destroy(mpm_ctx* ctx);
 const char* mpm_last_error(mpm_ctx* ctx);
 
-/* Bind host-owned device memory.  state0/state1: [fields][capacity] words each. */
-int mpm_bind(mpm_ctx* ctx, void* state0_dev, void* state1_dev, int64_t capacity, void* workspace_dev,
-             size_t workspace_bytes, int32_t max_blocks);
+/* Bind host-owned device memory.  state0/state1: [capacity / 32][nf][32] words each (capacity % 64 == 0,
+ * capacity <= 2^29); statics_dev: [3][capacity] words. */
+int mpm_bind(mpm_ctx* ctx, void* state0_dev, void* state1_dev, void* statics_dev, int64_t capacity,
+             void* workspace_dev, size_t workspace_bytes, int32_t max_blocks);
+/* rows of the static side arrays in use (== n_particles on a single device; with slabs departures leave holes) */
+int mpm_get_static_rows(mpm_ctx* ctx, int64_t* n_static);
+int mpm_set_static_rows(mpm_ctx* ctx, int64_t n_static);
+/* renumber the static rows by storage slot (n_static = n_particles); between batches only */
+int mpm_compact_statics(mpm_ctx* ctx, void* stream);
 /* Which set holds the live state, and how many particles (n_particles[None], :81). */
 int mpm_get_state(mpm_ctx* ctx, int32_t* current_set, int64_t* n_particles);
 int mpm_set_state(mpm_ctx* ctx, int32_t current_set, int64_t n_particles);
@@ -185,7 +199,7 @@ int mpm_pack_particles(mpm_ctx* ctx, const float* lo_inv_host, uint32_t* x_and_v
  *                mpm_phase_g2p
  *   mpm_batch_end        (the only host synchronisation)
  * Message buffers (device, 32-bit words): 16-word header (word 0 = count), then
- *   migration: [field][capacity] rows of the particle state layout above
+ *   migration: [word][capacity], the mpm_virtual_fields(dim) words of each particle (its static attributes travel)
  *   halo:      keys[capacity] ((by << 16) | bz), then records[capacity][cells] float4 */
 int mpm_set_slab(mpm_ctx* ctx, int32_t enabled, int32_t lo_block, int32_t hi_block);
 /* bytes of a message buffer: kind 0 = migration (capacity in particles), 1 = halo (capacity in leaf blocks) */

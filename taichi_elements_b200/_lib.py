@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 MPM_OK = 0
 MPM_E_BLOCK_CAPACITY = 1
 MPM_E_KEY_BITS = 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
@@ -69,7 +69,11 @@ SYMBOLS = [
     ('mpm_create', _i32, [ctypes.POINTER(MPMParams), ctypes.POINTER(_vp)]),
     ('mpm_destroy', _i32, [_vp]),
     ('mpm_last_error', ctypes.c_char_p, [_vp]),
-    ('mpm_bind', _i32, [_vp, _vp, _vp, _i64, _vp, ctypes.c_size_t, _i32]),
+    ('mpm_virtual_fields', _i32, [_i32]),
+    ('mpm_bind', _i32, [_vp, _vp, _vp, _vp, _i64, _vp, ctypes.c_size_t, _i32]),
+    ('mpm_get_static_rows', _i32, [_vp, ctypes.POINTER(_i64)]),
+    ('mpm_set_static_rows', _i32, [_vp, _i64]),
+    ('mpm_compact_statics', _i32, [_vp, _vp]),
     ('mpm_get_state', _i32, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
     ('mpm_set_state', _i32, [_vp, _i32, _i64]),
     ('mpm_set_gravity', _i32, [_vp, _dp]),

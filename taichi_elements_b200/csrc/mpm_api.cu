@@ -25,6 +25,9 @@ struct mpm_ctx {
   Consts K;
   int dim = 0, nf = 0, cells = 0, no = 0, cb = 0, log_leaf = 0;
   uint32_t* state[2] = {nullptr, nullptr};
+  Statics stat{nullptr, nullptr, nullptr};   // static side arrays [3][cap]: colour, id, emitter by sid
+  int64_t n_static = 0;                       // rows of them in use
+  int nv = 0;                                 // virtual words of the read-back numbering (Fld::NV)
   size_t cap = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -201,6 +204,7 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
 
 extern "C" int mpm_abi_version(void) { return MPM_ABI_VERSION; }
 extern "C" int mpm_state_fields(int dim) { return dim == 3 ? Geo<3>::NF : (dim == 2 ? Geo<2>::NF : -1); }
+extern "C" int mpm_virtual_fields(int dim) { return dim == 3 ? Fld<3>::NV : (dim == 2 ? Fld<2>::NV : -1); }
 extern "C" size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks) {
   if ((dim != 2 && dim != 3) || capacity < 0 || max_blocks < 1) return 0;
   return carve(dim, capacity, max_blocks).total;
@@ -215,6 +219,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   ctx->P = *p;
   ctx->dim = p->dim;
   ctx->nf = mpm_state_fields(p->dim);
+  ctx->nv = p->dim == 3 ? Fld<3>::NV : Fld<2>::NV;
   ctx->cells = p->dim == 3 ? 64 : 256;
   ctx->no = p->dim == 3 ? 8 : 4;
   ctx->cb = p->dim == 3 ? 6 : 8;
@@ -291,9 +296,10 @@ extern "C" int mpm_destroy(mpm_ctx* ctx) {
 
 extern "C" const char* mpm_last_error(mpm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
-extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void* ws, size_t ws_bytes,
+extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, void* statics, int64_t capacity, void* ws, size_t ws_bytes,
                         int32_t max_blocks) {
-  if (!ctx || !s0 || !s1 || !ws || capacity < 1 || max_blocks < 1) return fail(ctx, MPM_E_INVALID, "mpm_bind: bad argument");
+  if (!ctx || !s0 || !s1 || !statics || !ws || capacity < 1 || max_blocks < 1) return fail(ctx, MPM_E_INVALID, "mpm_bind: bad argument");
+  if (capacity > (int64_t)TAG_SID + 1) return fail(ctx, MPM_E_INVALID, "mpm_bind: capacity must be <= 2^29 (static row index of the tag word)");
   if (capacity % 64 != 0) return fail(ctx, MPM_E_INVALID, "mpm_bind: capacity must be a multiple of 64");
   if (capacity >= (int64_t)1 << 31) return fail(ctx, MPM_E_INVALID, "mpm_bind: capacity must be < 2^31");
   Carve c = carve(ctx->dim, capacity, max_blocks);
@@ -301,6 +307,9 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, int64_t capacity, void
   CK(cudaSetDevice(ctx->P.device));
   ctx->state[0] = (uint32_t*)s0;
   ctx->state[1] = (uint32_t*)s1;
+  ctx->stat.color = (uint32_t*)statics;
+  ctx->stat.gid = (uint32_t*)statics + capacity;
+  ctx->stat.emit = (uint32_t*)statics + 2 * capacity;
   ctx->cap = (size_t)capacity;
   ctx->cell_zeroed = false; ctx->flags_zeroed = false;   // new workspace: nothing is cleared yet
   ctx->ws = ws;
@@ -351,8 +360,41 @@ extern "C" int mpm_set_state(mpm_ctx* ctx, int32_t cur, int64_t n) {
   }
   ctx->cur = cur;
   ctx->n = n;
+  if (n == 0) ctx->n_static = 0;
   ctx->bbox_valid = false;
   ctx->last_valid = false;
+  return MPM_OK;
+}
+extern "C" int mpm_get_static_rows(mpm_ctx* ctx, int64_t* n_static) {
+  if (!ctx || !n_static) return MPM_E_INVALID;
+  *n_static = ctx->n_static;
+  return MPM_OK;
+}
+extern "C" int mpm_set_static_rows(mpm_ctx* ctx, int64_t n_static) {
+  if (!ctx || n_static < 0 || (size_t)n_static > ctx->cap) return MPM_E_INVALID;
+  ctx->n_static = n_static;
+  return MPM_OK;
+}
+// Renumber the static rows by storage slot (sid = slot, n_static = n): the distributed solver calls it between
+// batches when departures have left too many holes.  Borrows the idle state set.
+extern "C" int mpm_compact_statics(mpm_ctx* ctx, void* stream) {
+  if (!ctx) return MPM_E_INVALID;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  if (ctx->in_batch || ctx->have_pending) return fail(ctx, MPM_E_INVALID, "mpm_compact_statics: inside a batch / pending g2p2g half");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)ctx->n;
+  if (n > 0) {
+    uint32_t* tmp = ctx->state[ctx->cur ^ 1];
+    const int blocks = gs_blocks(n, 256, ctx->sm_count);
+    for (int pass = 0; pass < 2; ++pass) {
+      if (ctx->dim == 3) k_compact_statics<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass);
+      else k_compact_statics<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+  }
+  ctx->n_static = n;
   return MPM_OK;
 }
 
@@ -390,6 +432,8 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   a.cap = ctx->cap;
   a.n0 = ctx->n;
   if (a.id_base < 0) a.id_base = ctx->n;
+  a.stat = ctx->stat; a.sid0 = ctx->n_static;
+  if ((size_t)(ctx->n_static + a.n) > ctx->cap) return fail(ctx, MPM_E_INVALID, "seed: static rows exceed the capacity (compact first)");
   int blocks = gs_blocks(a.n, 256, ctx->sm_count);
   // A large array of external positions is stored sorted by leaf block (ids keep the insertion order): the
   // first substep then reads block-local rows instead of gathering 26 words per particle at random.  The sort
@@ -409,6 +453,7 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   if (ctx->dim == 3) k_seed<3><<<blocks, 256, 0, s>>>(a); else k_seed<2><<<blocks, 256, 0, s>>>(a);
   CK(cudaGetLastError());
   ctx->n += a.n;
+  ctx->n_static += a.n;
   ctx->bbox_valid = false;
   ctx->last_valid = false;
   return MPM_OK;
@@ -454,16 +499,19 @@ extern "C" int mpm_seed_positions_slab(mpm_ctx* ctx, const float* x_dev, int64_t
   CK(cudaStreamSynchronize(s));
   if (kept_out) *kept_out = (int64_t)kept;
   if (kept == 0) return MPM_OK;
-  if ((size_t)(ctx->n + (int64_t)kept) > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_seed_positions_slab: capacity exceeded");
+  if ((size_t)(ctx->n + (int64_t)kept) > ctx->cap || (size_t)(ctx->n_static + (int64_t)kept) > ctx->cap)
+    return fail(ctx, MPM_E_INVALID, "mpm_seed_positions_slab: capacity exceeded");
   SeedArgs a{};
   a.n = (int64_t)kept; a.material = material; a.color = color; a.emitter = emitter; a.x = x_dev; a.mode = 0;
   a.id_base = id_base; a.order = dv.Current();
   fill3(a.vel, velocity, ctx->dim, 0.f);
   a.state = ctx->state[ctx->cur]; a.cap = ctx->cap; a.n0 = ctx->n;
+  a.stat = ctx->stat; a.sid0 = ctx->n_static;
   const int sb = gs_blocks(a.n, 256, ctx->sm_count);
   if (ctx->dim == 3) k_seed<3><<<sb, 256, 0, s>>>(a); else k_seed<2><<<sb, 256, 0, s>>>(a);
   CK(cudaGetLastError());
   ctx->n += a.n;
+  ctx->n_static += a.n;
   ctx->bbox_valid = false;
   ctx->last_valid = false;
   return MPM_OK;
@@ -500,8 +548,8 @@ extern "C" int mpm_export_local(mpm_ctx* ctx, void* out_dev, int64_t* count_out,
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->stage);
   CK(cudaMemsetAsync(cnt, 0, 8, s));
   const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count), half = ctx->P.grid_size / 2;
-  if (ctx->dim == 3) k_export_local<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
-  else k_export_local<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
+  if (ctx->dim == 3) k_export_local<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
+  else k_export_local<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
   CK(cudaGetLastError());
   unsigned long long c = 0;
   CK(cudaMemcpyAsync(&c, cnt, 8, cudaMemcpyDeviceToHost, s));
@@ -717,7 +765,7 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.pb_start = ctx->pb_start; a.pb_nbr = ctx->pb_nbr; a.grid = ctx->grid; a.st = ctx->d_status;
   a.pb_key = ctx->pb_key; a.cellstart = ctx->cur_cellstart;
   a.L = ctx->L; a.K = ctx->K; a.dt = dt;
-  a.slab = ctx->slab; a.cb = ctx->comm;
+  a.slab = ctx->slab; a.cb = ctx->comm; a.stat = ctx->stat;
   a.n_rows = (int)ctx->n;
   a.pf_mode = ctx->pf_mode;
   a.defer_svd = ctx->defer_svd;
@@ -928,7 +976,7 @@ static int enqueue_scatter_half(mpm_ctx* ctx, float dt, int cur, int commit_prev
 static int rebuild_pending(mpm_ctx* ctx, cudaStream_t s) {
   const bool d3 = ctx->dim == 3;
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n);
+  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n, (int)ctx->n_static);
   const int64_t n_keep = ctx->n;
   ctx->n = ctx->pending_n;
   int rc = d3 ? enqueue_scatter_half<3>(ctx, ctx->pending_dt, ctx->cur, 0, s)
@@ -967,7 +1015,7 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
       if (rc) continue;
       CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     }
-    k_batch_begin_keep<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, ctx->pending_npb, ctx->pending_ngb);
+    k_batch_begin_keep<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, ctx->pending_npb, ctx->pending_ngb, (int)ctx->n_static);
     const int cur0 = ctx->cur;
     int cur = cur0;
     const bool skipped_first = ctx->skip_gather;
@@ -1043,7 +1091,7 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     rc = update_layout(ctx);
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-    k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
+    k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
     const int cur0 = ctx->cur;
     ctx->keys_ready = false;
     ctx->cell_zeroed = false; ctx->flags_zeroed = false;
@@ -1120,7 +1168,7 @@ extern "C" int mpm_set_slab(mpm_ctx* ctx, int32_t enabled, int32_t lo_block, int
 
 extern "C" size_t mpm_comm_bytes(int32_t dim, int32_t kind, int32_t capacity) {
   if ((dim != 2 && dim != 3) || capacity < 0) return 0;
-  const size_t nf = (size_t)mpm_state_fields(dim), cells = dim == 3 ? 64 : 256;
+  const size_t nf = (size_t)mpm_virtual_fields(dim), cells = dim == 3 ? 64 : 256;   // a migrating row carries its static attributes
   if (kind == 0) return 4 * (COMM_HEADER + nf * (size_t)capacity);
   return 4 * (COMM_HEADER + (size_t)capacity + (size_t)capacity * cells * 4);
 }
@@ -1173,7 +1221,7 @@ extern "C" int mpm_batch_begin(mpm_ctx* ctx, void* stream) {
   if (rc) return rc;
   if (!ctx->dense) return fail(ctx, MPM_E_INVALID, "phase API needs the counting-sort path (box too large for the flag table)");
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n);
+  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
   ctx->in_batch = true;
   ctx->batch_cur0 = ctx->cur;
   ctx->batch_enq = 0;
@@ -1191,7 +1239,7 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
   REQUIRE_BATCH();
   if (!from_lo && !from_hi) return MPM_OK;
   const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
-  const int blocks = gs_blocks((int64_t)ctx->comm.mig_cap * ctx->nf, 256, ctx->sm_count);
+  const int blocks = gs_blocks((int64_t)ctx->comm.mig_cap * ctx->nv, 256, ctx->sm_count);
   // the last G2P emitted the coming substep's keys and flags: the appended rows need theirs too
   uint32_t* keys = ctx->keys_ready ? ctx->keys_a : nullptr;
   int nlin = 1;
@@ -1199,11 +1247,11 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
   if (ctx->dim == 3)
     CK(launch_chain(ctx->pdl, k_mig_unpack<3>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (uint32_t*)from_lo,
                     (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
-                    ctx->K.inv_dx, ctx->comm));
+                    ctx->K.inv_dx, ctx->comm, ctx->stat));
   else
     CK(launch_chain(ctx->pdl, k_mig_unpack<2>, blocks, 256, 0, s, ctx->state[cur], ctx->cap, (uint32_t*)from_lo,
                     (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status, keys, ctx->flags, nlin, ctx->L, ctx->slab,
-                    ctx->K.inv_dx, ctx->comm));
+                    ctx->K.inv_dx, ctx->comm, ctx->stat));
   ctx->launches += 1;
   if (!ctx->comm.fused) {   // (fused exchange: the last CTA of the unpack kernel commits)
     CK(launch_chain(ctx->pdl, k_mig_commit, 1, 1, 0, s, (uint32_t*)from_lo, (uint32_t*)from_hi, ctx->comm.mig_cap, ctx->d_status));
@@ -1296,6 +1344,7 @@ extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
   ctx->bbox_valid = false;
   if (!h.err) {
     ctx->n = h.n_cur;
+    ctx->n_static = h.n_static;
     if (h.n_cur > 0 && h.done > 0) {
       for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = h.bb_min[d]; ctx->bb_max[d] = h.bb_max[d]; }
       ctx->bbox_valid = true;
@@ -1434,12 +1483,15 @@ extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t
 
 // local rows [0, n) of one state word in storage order (no id un-permutation)
 extern "C" int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream) {
-  if (!ctx || field < 0 || field >= ctx->nf) return MPM_E_INVALID;
+  if (!ctx || field < 0 || field >= ctx->nv) return MPM_E_INVALID;
   if (ctx->n == 0) return MPM_OK;
   if (!dst_host) return MPM_E_INVALID;
   CK(cudaSetDevice(ctx->P.device));
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaMemcpyAsync(dst_host, ctx->state[ctx->cur] + (size_t)field * ctx->cap, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, s));
+  if (ctx->dim == 3) k_gather_raw<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage);
+  else k_gather_raw<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst_host, ctx->stage, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return MPM_OK;
 }
@@ -1477,12 +1529,11 @@ extern "C" int mpm_gather(mpm_ctx* ctx, int32_t field, int64_t begin, int64_t en
 
 extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords, int64_t begin, int64_t end,
                                void* dst_dev, void* stream) {
-  if (!ctx || first_field < 0 || nwords < 1 || first_field + nwords > ctx->nf || begin < 0 || end < begin || end > ctx->n)
+  if (!ctx || first_field < 0 || nwords < 1 || first_field + nwords > ctx->nv || begin < 0 || end < begin || end > ctx->n)
     return fail(ctx, MPM_E_INVALID, "mpm_gather_rows: bad range/field");
   if (end == begin) return MPM_OK;
   if (!dst_dev) return MPM_E_INVALID;
   CK(cudaSetDevice(ctx->P.device));
-  const int idf = ctx->dim == 3 ? Fld<3>::ID : Fld<2>::ID;
   // rows whose id is not present (ids that are not a permutation of [0, n): the distributed solver's
   // global ids) read as zero instead of uninitialised memory
   CK(cudaMemsetAsync(dst_dev, 0, (size_t)(end - begin) * nwords * 4, (cudaStream_t)stream));
@@ -1507,14 +1558,23 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
     const int lo = first_field >= jp ? jp : f_lo, hi = first_field >= jp ? jp + 1 : f_lo + dd;
     if (first_field < jp && first_field + nwords > f_lo + dd && first_field + nwords > jp)
       return fail(ctx, MPM_E_INVALID, "mpm_gather_rows: a range may not span F and Jp in g2p2g mode");
-    k_gather_rows_pending<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
-        ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->cap, first_field, nwords, idf, lo, hi,
-        ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+    if (ctx->dim == 3)
+      k_gather_rows_pending<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
+          ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->stat, first_field, nwords, lo, hi,
+          ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+    else
+      k_gather_rows_pending<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
+          ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->stat, first_field, nwords, lo, hi,
+          ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
     CK(cudaGetLastError());
     return MPM_OK;
   }
-  k_gather_rows<<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
-      ctx->state[ctx->cur], ctx->cap, first_field, nwords, idf, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+  if (ctx->dim == 3)
+    k_gather_rows<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
+        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+  else
+    k_gather_rows<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
+        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
   CK(cudaGetLastError());
   return MPM_OK;
 }
@@ -1550,9 +1610,9 @@ extern "C" int mpm_pack_particles(mpm_ctx* ctx, const float* lo_inv_host, uint32
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
   if (ctx->dim == 3)
-    k_pack_particles<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, pa, x_and_v_dev, color_dev);
+    k_pack_particles<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev);
   else
-    k_pack_particles<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, pa, x_and_v_dev, color_dev);
+    k_pack_particles<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev);
   CK(cudaGetLastError());
   return MPM_OK;
 }
@@ -1632,8 +1692,8 @@ extern "C" int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream
   int* out = (int*)ctx->state[ctx->cur ^ 1];   // the idle set is free between substeps
   const int half = ctx->P.grid_size / 2;
   int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
-  if (ctx->dim == 3) k_debug_binning<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, out);
-  else k_debug_binning<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, half, out);
+  if (ctx->dim == 3) k_debug_binning<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out);
+  else k_debug_binning<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(block_host, out, (size_t)ctx->n * ctx->dim * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

@@ -54,7 +54,7 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
     float4 xs[D];
 #pragma unroll
     for (int d = 0; d < D; ++d)
-      xs[d] = __ldg(reinterpret_cast<const float4*>(state + (size_t)(Fld<D>::X + d) * cap) + t);
+      xs[d] = __ldg(reinterpret_cast<const float4*>(state + word<D>(Fld<D>::X + d, 4u * t)));   // 4 particles of one tile row
     uint32_t out[4];
     uint32_t prev_lin = 0xFFFFFFFFu, prev_om = 0;
 #pragma unroll

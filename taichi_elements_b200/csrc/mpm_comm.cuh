@@ -124,26 +124,36 @@ template <int D>
 __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, uint32_t* __restrict__ from_lo,
                              uint32_t* __restrict__ from_hi, int mig_cap, Status* st,
                              uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, KeyLayout L, Slab slab,
-                             float inv_dx, CommBufs cb) {
+                             float inv_dx, CommBufs cb, Statics stat) {
   using G = Geo<D>;
-  constexpr int NF = Fld<D>::N;
+  using FL = Fld<D>;
+  constexpr int NW = FL::JP + 1;          // state words copied verbatim; the message's material / colour / id / emitter
+                                          // rows become the tag and a new row of the static side arrays
   pdl_enter();
   // fused exchange: the neighbours publish the epoch of the substep whose leavers these buffers hold
   if (cb.fused) cta_wait_epochs(from_lo ? cb.wait_mig[0] : nullptr, from_hi ? cb.wait_mig[1] : nullptr, cb.epoch, st);
   bool active = *(volatile int*)&st->err == 0;
   const int c0 = (active && from_lo) ? min((int)*(volatile uint32_t*)from_lo, mig_cap) : 0;
   const int c1 = (active && from_hi) ? min((int)*(volatile uint32_t*)from_hi, mig_cap) : 0;
-  const int base = st->n_cur;
-  if (active && (size_t)base + c0 + c1 > cap) {
+  const int base = st->n_cur, sbase = st->n_static;
+  if (active && ((size_t)base + c0 + c1 > cap || (size_t)sbase + c0 + c1 > cap)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, ERR_PARTICLE_CAPACITY);
     active = false;
   }
-  const int total = active ? (c0 + c1) * NF : 0;
+  const int total = active ? (c0 + c1) * NW : 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int f = i / (c0 + c1), r = i % (c0 + c1);
     const uint32_t v = r < c0 ? from_lo[COMM_HEADER + (size_t)f * mig_cap + r]
                               : from_hi[COMM_HEADER + (size_t)f * mig_cap + (r - c0)];
-    state[(size_t)f * cap + base + r] = v;
+    state[word<D>(f, (uint32_t)(base + r))] = v;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < (active ? c0 + c1 : 0); r += gridDim.x * blockDim.x) {
+    const uint32_t* m = r < c0 ? from_lo + COMM_HEADER + r : from_hi + COMM_HEADER + (r - c0);
+    const uint32_t sid = (uint32_t)(sbase + r);
+    state[word<D>(FL::TAG, (uint32_t)(base + r))] = make_tag(m[(size_t)FL::MAT * mig_cap], sid);
+    stat.color[sid] = m[(size_t)FL::COLOR * mig_cap];
+    stat.gid[sid] = m[(size_t)FL::ID * mig_cap];
+    stat.emit[sid] = m[(size_t)FL::EMIT * mig_cap];
   }
   const int nrows = (active && keys) ? c0 + c1 : 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
@@ -177,7 +187,7 @@ __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, uint32_t*
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(&st->unpack_done, 1) == (int)gridDim.x - 1) {
       st->unpack_done = 0;
-      if (active) st->n_cur = base + c0 + c1;
+      if (active) { st->n_cur = base + c0 + c1; st->n_static = sbase + c0 + c1; }
       if (from_lo) from_lo[0] = 0;
       if (from_hi) from_hi[0] = 0;
     }
@@ -189,6 +199,7 @@ __global__ void k_mig_commit(uint32_t* from_lo, uint32_t* from_hi, int mig_cap, 
   const int c0 = from_lo ? min((int)from_lo[0], mig_cap) : 0;
   const int c1 = from_hi ? min((int)from_hi[0], mig_cap) : 0;
   st->n_cur += c0 + c1;
+  st->n_static += c0 + c1;
   if (from_lo) from_lo[0] = 0;   // consumed: a second unpack of the same message appends nothing
   if (from_hi) from_hi[0] = 0;
 }

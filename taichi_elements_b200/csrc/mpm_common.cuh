@@ -15,18 +15,34 @@ template <int D> struct Geo;
 template <> struct Geo<3> {
   static constexpr int LEAF = 4, LOG_LEAF = 2, CELLS = 64, CB = 6;   // CB = cell bits in a key
   static constexpr int T = LEAF + 2, TN = T * T * T, NO = 8;         // staged tile, octants
-  static constexpr int NF = 2 * 3 + 2 * 9 + 5;
+  static constexpr int NF = 2 * 3 + 2 * 9 + 2;                       // physical words per particle (see Fld)
 };
 template <> struct Geo<2> {
   static constexpr int LEAF = 16, LOG_LEAF = 4, CELLS = 256, CB = 8;
   static constexpr int T = LEAF + 2, TN = T * T, NO = 4;
-  static constexpr int NF = 2 * 2 + 2 * 4 + 5;
+  static constexpr int NF = 2 * 2 + 2 * 4 + 2;
 };
 
-// Field (word) indices inside one state set, SoA with stride = capacity.
+// Word indices of one particle inside its tile (mpm_kernels.cuh: word()).  The substep moves every particle to its
+// sorted slot each time, so only what the physics needs travels: x v F C Jp and ONE tag word,
+//   tag = material << 29 | sid,
+// where sid indexes the static side arrays (colour, id, emitter), which never move.  MAT .. EMIT are the VIRTUAL
+// word numbers of the read-back ABI (include/mpm_b200.h: the reference's field order), resolved by vword().
 template <int D> struct Fld {
-  static constexpr int X = 0, V = D, F = 2 * D, C = 2 * D + D * D, JP = 2 * D + 2 * D * D,
-                       MAT = JP + 1, COLOR = JP + 2, ID = JP + 3, EMIT = JP + 4, N = JP + 5;
+  static constexpr int X = 0, V = D, F = 2 * D, C = 2 * D + D * D, JP = 2 * D + 2 * D * D, TAG = JP + 1, N = JP + 2;
+  static constexpr int MAT = JP + 1, COLOR = JP + 2, ID = JP + 3, EMIT = JP + 4, NV = JP + 5;
+};
+static constexpr int TAG_SHIFT = 29;
+static constexpr uint32_t TAG_SID = (1u << TAG_SHIFT) - 1u;
+__host__ __device__ inline uint32_t make_tag(uint32_t material, uint32_t sid) { return (material << TAG_SHIFT) | (sid & TAG_SID); }
+__host__ __device__ inline uint32_t tag_mat(uint32_t tag) { return tag >> TAG_SHIFT; }
+__host__ __device__ inline uint32_t tag_sid(uint32_t tag) { return tag & TAG_SID; }
+// Static per-particle attributes, indexed by sid (rows are appended, never moved by the substep; the distributed
+// solver compacts them between batches): packed colour, id (insertion index; global id with slabs), emitter id.
+struct Statics {
+  uint32_t* color;
+  uint32_t* gid;
+  uint32_t* emit;
 };
 
 static constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
@@ -68,6 +84,7 @@ struct Status {
   int halo_done;    // boundary blocks whose shared-column nodes have been sent (P2G)
   int g2p_done;     // CTAs of G2P that have finished (the last one publishes the migration message)
   int unpack_done;  // CTAs of k_mig_unpack that have finished (the last one commits the appended rows)
+  int n_static;     // rows of the static side arrays in use (arrivals append; see Statics)
 };
 
 // Slab decomposition along x (multi-GPU): this rank owns leaf-block columns

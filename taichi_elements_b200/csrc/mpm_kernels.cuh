@@ -14,17 +14,41 @@
 
 namespace mpm {
 
-__device__ __forceinline__ float ldf(const uint32_t* __restrict__ s, size_t cap, int f, uint32_t p) {
-  return __uint_as_float(__ldg(s + (size_t)f * cap + p));
+// Particle state layout: tiles of 32 particles, inside a tile one 128-byte row per state word:
+//   word(f, p) = ((p / 32) * NF + f) * 32 + p % 32.
+// A warp that reads word f of 32 consecutive particles touches one 128-byte line, as with a plain structure of arrays,
+// but all words of a particle sit at CONSTANT offsets (f * 128 B) from one address: a kernel that touches 26 words of
+// a particle needs one 64-bit address computation instead of 26 (the strided layout [f][capacity] of round 1 cost ~3
+// integer instructions per access and kept the register file full of row pointers).
+static constexpr int TILE = 32, TILE_LOG = 5;
+template <int NF> __host__ __device__ __forceinline__ size_t word_nf(int f, uint32_t p) {
+  return ((size_t)(p >> TILE_LOG) * NF + f) * TILE + (p & (TILE - 1));
 }
-__device__ __forceinline__ uint32_t ldu(const uint32_t* __restrict__ s, size_t cap, int f, uint32_t p) {
-  return __ldg(s + (size_t)f * cap + p);
+__host__ __device__ __forceinline__ size_t word_rt(int nf, int f, uint32_t p) {      // run-time field count
+  return ((size_t)(p >> TILE_LOG) * nf + f) * TILE + (p & (TILE - 1));
 }
-__device__ __forceinline__ void stf(uint32_t* __restrict__ s, size_t cap, int f, uint32_t p, float v) {
-  s[(size_t)f * cap + p] = __float_as_uint(v);
+template <int D> __host__ __device__ __forceinline__ size_t word(int f, uint32_t p) { return word_nf<Fld<D>::N>(f, p); }
+template <int D> __device__ __forceinline__ float ldf(const uint32_t* __restrict__ s, int f, uint32_t p) {
+  return __uint_as_float(__ldg(s + word<D>(f, p)));
 }
-__device__ __forceinline__ void stu(uint32_t* __restrict__ s, size_t cap, int f, uint32_t p, uint32_t v) {
-  s[(size_t)f * cap + p] = v;
+template <int D> __device__ __forceinline__ uint32_t ldu(const uint32_t* __restrict__ s, int f, uint32_t p) {
+  return __ldg(s + word<D>(f, p));
+}
+template <int D> __device__ __forceinline__ void stf(uint32_t* __restrict__ s, int f, uint32_t p, float v) {
+  s[word<D>(f, p)] = __float_as_uint(v);
+}
+template <int D> __device__ __forceinline__ void stu(uint32_t* __restrict__ s, int f, uint32_t p, uint32_t v) {
+  s[word<D>(f, p)] = v;
+}
+
+// virtual word `f` (read-back ABI numbering, Fld<D>::NV words) of the particle in storage slot s
+template <int D> __device__ __forceinline__ uint32_t vword(const uint32_t* __restrict__ state, const Statics& st, int f, uint32_t s) {
+  using FL = Fld<D>;
+  if (f <= FL::JP) return state[word<D>(f, s)];
+  const uint32_t tag = state[word<D>(FL::TAG, s)];
+  if (f == FL::MAT) return tag_mat(tag);
+  const uint32_t sid = tag_sid(tag);
+  return f == FL::COLOR ? st.color[sid] : (f == FL::ID ? st.gid[sid] : st.emit[sid]);
 }
 
 // base = int(floor(x * inv_dx - 0.5)), f32 multiply then f32 subtract, never
@@ -132,7 +156,7 @@ __global__ void k_reset(Status* st) {
   st->maxgv_bits = 0;
   for (int d = 0; d < 3; ++d) { st->bb_min[d] = INT_MAX; st->bb_max[d] = INT_MIN; }
 }
-__global__ void k_batch_begin(Status* st, int n) { st->n_cur = n; st->n_live = n; }
+__global__ void k_batch_begin(Status* st, int n, int n_static) { st->n_cur = n; st->n_live = n; st->n_static = n_static; }
 // first kernel of a substep whose keys came from the previous G2P: commit that substep, then
 // let the errors its key pass raised take effect
 __global__ void k_substep_begin(Status* st) {
@@ -162,7 +186,7 @@ __global__ void k_keys(const uint32_t* __restrict__ state, size_t cap, int n, fl
     bool bad = false;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      int g = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + L.half;
+      int g = base_index(ldf<D>(state, Fld<D>::X + d, p), inv_dx) + L.half;
       int rel = (g >> G::LOG_LEAF) - L.ob[d];
       if (rel < 0 || rel > L.eb[d] - 2) { bad = true; rel = min(max(rel, 0), L.eb[d] - 2); }
       lin = lin * (uint32_t)L.eb[d] + (uint32_t)rel;
@@ -183,7 +207,7 @@ __global__ void k_bbox(const uint32_t* __restrict__ state, size_t cap, int n, fl
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      int b = base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx);
+      int b = base_index(ldf<D>(state, Fld<D>::X + d, p), inv_dx);
       lo[d] = min(lo[d], b); hi[d] = max(hi[d], b);
     }
   }
@@ -384,6 +408,7 @@ template <int D> struct SubstepArgs {
   int pf_mode;    // next-block L2 prefetch: 0 off, 1 one prefetch per 128 B, 2 bulk range prefetch, 3 one per 32 B
   int defer_svd;  // k_p2g3: particles that need the SVD run in a second, compacted pass (MPM_DEFER_SVD)
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
+  Statics stat;   // static side arrays (G2P reads them for the particles it hands to a neighbour rank)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)
   CommBufs cb;    // multi-GPU: migration / halo send buffers
 };
@@ -427,8 +452,8 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
       int l[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        x[d] = ldf(a.src, cap, FL::X + d, p);
-        v[d] = ldf(a.src, cap, FL::V + d, p);
+        x[d] = ldf<D>(a.src, FL::X + d, p);
+        v[d] = ldf<D>(a.src, FL::V + d, p);
         int base = base_index(x[d], a.K.inv_dx);
         fx[d] = x[d] * a.K.inv_dx - (float)base;                 // :503
         l[d] = min(max(base + a.L.half - org[d], 0), G::LEAF - 1);
@@ -439,15 +464,15 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
       float F[D * D], C[D * D], aff[D * D], mass;
 #pragma unroll
       for (int i = 0; i < D * D; ++i) {
-        F[i] = ldf(a.src, cap, FL::F + i, p);
-        C[i] = ldf(a.src, cap, FL::C + i, p);
+        F[i] = ldf<D>(a.src, FL::F + i, p);
+        C[i] = ldf<D>(a.src, FL::C + i, p);
       }
-      float Jp = ldf(a.src, cap, FL::JP, p);
-      const int mat = (int)ldu(a.src, cap, FL::MAT, p);
+      float Jp = ldf<D>(a.src, FL::JP, p);
+      const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
       particle_update<D>(a.K, a.dt, mat, F, C, Jp, aff, mass);
 #pragma unroll
-      for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, F[i]);
-      stf(a.dst, cap, FL::JP, s, Jp);
+      for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
+      stf<D>(a.dst, FL::JP, s, Jp);
       float mv[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) mv[d] = mass * v[d];
@@ -716,8 +741,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     for (int d = 0; d < D; ++d) xn[d] = 0.0f;
     if (s < end) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) xn[d] = ldf(a.src, cap, FL::X + d, p1);
-      matn = ldu(a.src, cap, FL::MAT, p1);
+      for (int d = 0; d < D; ++d) xn[d] = ldf<D>(a.src, FL::X + d, p1);
+      matn = ldu<D>(a.src, FL::TAG, p1);
     }
     float4* tile = tile_buf[u];
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -732,22 +757,15 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     {   // next block's particle rows towards L2 while this one computes
       const int nb = nb_claim;
       if (nb < npb && a.pf_mode) {
+        // the rows G2P reads (x and the tag: two runs of 128-byte rows per tile) and perm
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
-        if (a.pf_mode == 2) {
-          if (tid < 8 && !(D == 2 && tid == 2)) {
-            const int f = tid < D ? FL::X + tid : (tid == 3 ? FL::MAT : (tid == 4 ? FL::COLOR : (tid == 5 ? FL::ID : FL::EMIT)));
-            prefetch_l2_range((tid == 7 ? a.perm : a.src + (size_t)f * cap) + ns, (uint32_t)(ne - ns) * 4u);
-          }
-        } else {
-          const int sh = a.pf_mode == 3 ? 3 : 5;           // words per prefetch: 8 (32 B) or 32 (128 B)
-          const int lines = (((ne - ns) + (1 << sh) - 1) >> sh) + 1;
-          for (int i = tid; i < 8 * lines; i += G2P_THREADS) {
-            const int k = i / lines, l = i % lines;
-            const int f = k < D ? FL::X + k : (k == 3 ? FL::MAT : (k == 4 ? FL::COLOR : (k == 5 ? FL::ID : FL::EMIT)));
-            if (D == 2 && k == 2) continue;
-            prefetch_l2((k == 7 ? a.perm : a.src + (size_t)f * cap) + ns + (l << sh));
-          }
+        const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
+        for (int i = tid; i < 2 * nt; i += G2P_THREADS) {
+          const uint32_t* tile0 = a.src + (size_t)(t0 + (i >> 1)) * FL::N * TILE;
+          if (i & 1) prefetch_l2_range(tile0 + FL::TAG * TILE, TILE * 4u);
+          else prefetch_l2_range(tile0 + FL::X * TILE, (uint32_t)D * TILE * 4u);
         }
+        if (tid == G2P_THREADS - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
       }
     }
     for (; s < end; s += G2P_THREADS) {
@@ -756,14 +774,12 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       int l[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) x[d] = xn[d];
-      const uint32_t mat = matn;
-      const uint32_t color = ldu(a.src, cap, FL::COLOR, p), pid = ldu(a.src, cap, FL::ID, p),
-                     emit = ldu(a.src, cap, FL::EMIT, p);
+      const uint32_t tag = matn, mat = tag_mat(tag);      // material | static row: the only immutable word that travels
       p1 = p2;
       if (s + G2P_THREADS < end) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) xn[d] = ldf(a.src, cap, FL::X + d, p1);
-        matn = ldu(a.src, cap, FL::MAT, p1);
+        for (int d = 0; d < D; ++d) xn[d] = ldf<D>(a.src, FL::X + d, p1);
+        matn = ldu<D>(a.src, FL::TAG, p1);
       }
       p2 = s + 2 * G2P_THREADS < end ? a.perm[s + 2 * G2P_THREADS] : 0u;
 #pragma unroll
@@ -859,10 +875,10 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         // The x + (-0) identity consumes each load INSIDE this rare branch: otherwise the stores after
         // the join wait on a scoreboard shared with the next particle's prefetched loads.
 #pragma unroll
-        for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(ldf(a.src, cap, FL::V + d, p), -0.0f);
+        for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(ldf<D>(a.src, FL::V + d, p), -0.0f);
         if (!a.K.g2p2g) {      // [g2p2g] C is a register value there: the gathered C is used (:385, 414)
 #pragma unroll
-          for (int i = 0; i < D * D; ++i) nC[i] = __fadd_rn(ldf(a.src, cap, FL::C + i, p), -0.0f);
+          for (int i = 0; i < D * D; ++i) nC[i] = __fadd_rn(ldf<D>(a.src, FL::C + i, p), -0.0f);
         }
       } else {
 #pragma unroll
@@ -872,8 +888,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       bool nbad = false;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        stf(a.dst, cap, FL::X + d, s, x[d]);
-        stf(a.dst, cap, FL::V + d, s, nv[d]);
+        stf<D>(a.dst, FL::X + d, s, x[d]);
+        stf<D>(a.dst, FL::V + d, s, nv[d]);
         vmax = fmaxf(vmax, fabsf(nv[d]));
         int nb = base_index(x[d], a.K.inv_dx);
         lo[d] = min(lo[d], nb); hi[d] = max(hi[d], nb);
@@ -912,7 +928,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         }
       }
 #pragma unroll
-      for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::C + i, s, nC[i]);
+      for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::C + i, s, nC[i]);
       if (a.slab.enabled) {
         // slab decomposition: the particle now belongs to a neighbour rank -> hand it over
         const int nbx = (base_index(x[0], a.K.inv_dx) + a.L.half) >> G::LOG_LEAF;
@@ -929,22 +945,20 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
             }
 #pragma unroll
             for (int i = 0; i < D * D; ++i) {
-              m[(FL::F + i) * mc] = a.dst[(size_t)(FL::F + i) * cap + s];   // written by P2G
+              m[(FL::F + i) * mc] = a.dst[word<D>(FL::F + i, s)];   // written by P2G
               m[(FL::C + i) * mc] = __float_as_uint(nC[i]);
             }
-            m[FL::JP * mc] = a.dst[(size_t)FL::JP * cap + s];
+            m[FL::JP * mc] = a.dst[word<D>(FL::JP, s)];
+            const uint32_t sid = tag_sid(tag);            // the message carries the static attributes along
             m[FL::MAT * mc] = mat;
-            m[FL::COLOR * mc] = color;
-            m[FL::ID * mc] = pid;
-            m[FL::EMIT * mc] = emit;
+            m[FL::COLOR * mc] = a.stat.color[sid];
+            m[FL::ID * mc] = a.stat.gid[sid];
+            m[FL::EMIT * mc] = a.stat.emit[sid];
             if (!a.cb.fused) __threadfence_system();   // peer path: the row may live in the neighbour's memory
           }
         }
       }
-      stu(a.dst, cap, FL::MAT, s, mat);
-      stu(a.dst, cap, FL::COLOR, s, color);
-      stu(a.dst, cap, FL::ID, s, pid);
-      stu(a.dst, cap, FL::EMIT, s, emit);
+      stu<D>(a.dst, FL::TAG, s, tag);
     }
     if (a.next_keys) {
       seen = __reduce_or_sync(0xffffffffu, seen);
@@ -1002,26 +1016,23 @@ __global__ void k_copy_advect(const uint32_t* __restrict__ src, uint32_t* __rest
   if (st->err) return;
   float vmax = 0.0f;
   for (int p = r0 + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const uint32_t mat = ldu(src, cap, FL::MAT, p);
+    const uint32_t tag = ldu<D>(src, FL::TAG, p), mat = tag_mat(tag);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const float v = ldf(src, cap, FL::V + d, p);
-      float x = ldf(src, cap, FL::X + d, p);
+      const float v = ldf<D>(src, FL::V + d, p);
+      float x = ldf<D>(src, FL::X + d, p);
       if (mat != (uint32_t)STATIONARY) x = __fadd_rn(x, __fmul_rn(dt, v));
-      stf(dst, cap, FL::X + d, p, x);
-      stf(dst, cap, FL::V + d, p, v);
+      stf<D>(dst, FL::X + d, p, x);
+      stf<D>(dst, FL::V + d, p, v);
       vmax = fmaxf(vmax, fabsf(v));
     }
 #pragma unroll
     for (int i = 0; i < D * D; ++i) {
-      stu(dst, cap, FL::F + i, p, ldu(src, cap, FL::F + i, p));
-      stf(dst, cap, FL::C + i, p, 0.0f);
+      stu<D>(dst, FL::F + i, p, ldu<D>(src, FL::F + i, p));
+      stf<D>(dst, FL::C + i, p, 0.0f);
     }
-    stu(dst, cap, FL::JP, p, ldu(src, cap, FL::JP, p));
-    stu(dst, cap, FL::MAT, p, mat);
-    stu(dst, cap, FL::COLOR, p, ldu(src, cap, FL::COLOR, p));
-    stu(dst, cap, FL::ID, p, ldu(src, cap, FL::ID, p));
-    stu(dst, cap, FL::EMIT, p, ldu(src, cap, FL::EMIT, p));
+    stu<D>(dst, FL::JP, p, ldu<D>(src, FL::JP, p));
+    stu<D>(dst, FL::TAG, p, tag);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -1034,8 +1045,8 @@ __global__ void k_half_commit(Status* st) {
   if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
 }
 // batch start in g2p2g mode: the pending scatter half's block structure stays valid
-__global__ void k_batch_begin_keep(Status* st, int n, int npb, int ngb) {
-  st->n_cur = n; st->n_live = n;
+__global__ void k_batch_begin_keep(Status* st, int n, int npb, int ngb, int n_static) {
+  st->n_cur = n; st->n_live = n; st->n_static = n_static;
   st->npb = npb; st->ngb = ngb;
   st->work_g2p = 0; st->maxv_bits = 0;
 }
@@ -1069,6 +1080,8 @@ struct SeedArgs {
   const uint32_t* order; // non-null (mode 0): row n0 + i takes input order[i] (inputs pre-sorted by leaf block)
   int64_t id_base;       // id of input 0 (the insertion index n0 on a single-device solver; global ids with slabs)
   float* x_out;          // non-null (modes 1, 2): positions only, [n][D] -- nothing is appended (mpm_seed_generate)
+  Statics stat;          // static side arrays; row n0 + i gets the static row sid0 + i
+  int64_t sid0;
 };
 
 // Sort key of an external position for block-sorted seeding: absolute leaf-block coordinates, 10 bits per
@@ -1146,19 +1159,20 @@ __global__ void k_seed(SeedArgs a) {
       continue;
     }
 #pragma unroll
-    for (int d = 0; d < D; ++d) { stf(a.state, a.cap, FL::X + d, p, x[d]); stf(a.state, a.cap, FL::V + d, p, v[d]); }
+    for (int d = 0; d < D; ++d) { stf<D>(a.state, FL::X + d, p, x[d]); stf<D>(a.state, FL::V + d, p, v[d]); }
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        stf(a.state, a.cap, FL::F + r * D + c, p, r == c ? 1.0f : 0.0f);
-        stf(a.state, a.cap, FL::C + r * D + c, p, 0.0f);
+        stf<D>(a.state, FL::F + r * D + c, p, r == c ? 1.0f : 0.0f);
+        stf<D>(a.state, FL::C + r * D + c, p, 0.0f);
       }
-    stf(a.state, a.cap, FL::JP, p, material == SAND ? 0.0f : 1.0f);   // :831-835
-    stu(a.state, a.cap, FL::MAT, p, (uint32_t)material);
-    stu(a.state, a.cap, FL::COLOR, p, (uint32_t)color);
-    stu(a.state, a.cap, FL::ID, p, (uint32_t)id);   // insertion index (block-sorted seeding: != row)
-    stu(a.state, a.cap, FL::EMIT, p, (uint32_t)a.emitter);
+    stf<D>(a.state, FL::JP, p, material == SAND ? 0.0f : 1.0f);   // :831-835
+    const uint32_t sid = (uint32_t)(a.sid0 + i);
+    stu<D>(a.state, FL::TAG, p, make_tag((uint32_t)material, sid));
+    a.stat.color[sid] = (uint32_t)color;
+    a.stat.gid[sid] = (uint32_t)id;             // insertion index (block-sorted seeding: != row)
+    a.stat.emit[sid] = (uint32_t)a.emitter;
   }
 }
 
@@ -1280,28 +1294,42 @@ __global__ void k_voxel_sample(VoxSampleArgs a) {
 }
 
 // read-back in insertion order: out[id - begin] = field[slot]
-__global__ void k_gather_field(const uint32_t* __restrict__ field, const uint32_t* __restrict__ ids, int n,
-                               int64_t begin, int64_t end, uint32_t* __restrict__ out) {
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    int64_t id = ids[s];
-    if (id >= begin && id < end) out[id - begin] = field[s];
-  }
-}
-
 // several consecutive state words of particles [begin, end) as rows out[id - begin][nwords]
-__global__ void k_gather_rows(const uint32_t* __restrict__ state, size_t cap, int first, int nwords, int idf,
+template <int D>
+__global__ void k_gather_rows(const uint32_t* __restrict__ state, Statics stat, int first, int nwords,
                               int n, int64_t begin, int64_t end, uint32_t* __restrict__ out) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    const int64_t id = state[(size_t)idf * cap + s];
+    const int64_t id = vword<D>(state, stat, Fld<D>::ID, s);
     if (id >= begin && id < end)
-      for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = state[(size_t)(first + w) * cap + s];
+      for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = vword<D>(state, stat, first + w, s);
+  }
+}
+// rows [0, n) of one (virtual) state word in storage order
+template <int D>
+__global__ void k_gather_raw(const uint32_t* __restrict__ state, Statics stat, int field, int n, uint32_t* __restrict__ out) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x)
+    out[s] = vword<D>(state, stat, field, s);
+}
+// Static rows renumbered by storage slot (distributed runs: leavers leave holes, arrivals append): pass 0 copies the
+// row of every live particle to tmp[3][n], pass 1 copies back and rewrites the tags (sid = slot).
+template <int D>
+__global__ void k_compact_statics(uint32_t* __restrict__ state, Statics stat, int n, uint32_t* __restrict__ tmp, int pass) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    if (pass == 0) {
+      const uint32_t sid = tag_sid(state[word<D>(Fld<D>::TAG, s)]);
+      tmp[s] = stat.color[sid]; tmp[(size_t)n + s] = stat.gid[sid]; tmp[2 * (size_t)n + s] = stat.emit[sid];
+    } else {
+      stat.color[s] = tmp[s]; stat.gid[s] = tmp[(size_t)n + s]; stat.emit[s] = tmp[2 * (size_t)n + s];
+      const size_t w = word<D>(Fld<D>::TAG, s);
+      state[w] = make_tag(tag_mat(state[w]), s);
+    }
   }
 }
 
 // particle_info() of one slab rank: rows [x[D] v[D] material color id] of the particles whose base block lies in
 // this rank's columns (rows already handed to a neighbour are skipped), compacted in storage order groups
 template <int D>
-__global__ void k_export_local(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, int half, Slab slab,
+__global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat, int n, float inv_dx, int half, Slab slab,
                                uint32_t* __restrict__ out, unsigned long long* __restrict__ count) {
   using G = Geo<D>;
   using FL = Fld<D>;
@@ -1311,7 +1339,7 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, size_t cap, i
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
     bool mine = s < (uint32_t)n;
     if (mine && slab.enabled) {
-      const int bx = (base_index(ldf(state, cap, FL::X, s), inv_dx) + half) >> G::LOG_LEAF;
+      const int bx = (base_index(ldf<D>(state, FL::X, s), inv_dx) + half) >> G::LOG_LEAF;
       mine = bx >= slab.lo && bx < slab.hi;
     }
     const unsigned m = __ballot_sync(0xffffffffu, mine);
@@ -1321,10 +1349,11 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, size_t cap, i
     if (!mine) continue;
     uint32_t* o = out + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * W;
 #pragma unroll
-    for (int d = 0; d < D; ++d) { o[d] = ldu(state, cap, FL::X + d, s); o[D + d] = ldu(state, cap, FL::V + d, s); }
-    o[2 * D] = ldu(state, cap, FL::MAT, s);
-    o[2 * D + 1] = ldu(state, cap, FL::COLOR, s);
-    o[2 * D + 2] = ldu(state, cap, FL::ID, s);
+    for (int d = 0; d < D; ++d) { o[d] = ldu<D>(state, FL::X + d, s); o[D + d] = ldu<D>(state, FL::V + d, s); }
+    const uint32_t tag = ldu<D>(state, FL::TAG, s);
+    o[2 * D] = tag_mat(tag);
+    o[2 * D + 1] = stat.color[tag_sid(tag)];
+    o[2 * D + 2] = stat.gid[tag_sid(tag)];
   }
 }
 
@@ -1350,7 +1379,7 @@ __global__ void k_ranges(const uint32_t* __restrict__ state, size_t cap, int n, 
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int f = 0; f < 2 * D; ++f) {
-      const float a = ldf(state, cap, f, s);
+      const float a = ldf<D>(state, f, s);
       lo[f] = fminf(lo[f], a); hi[f] = fmaxf(hi[f], a);
     }
   }
@@ -1373,21 +1402,21 @@ __global__ void k_ranges_decode(uint32_t* r, int nwords) {
 }
 struct PackArgs { float lo[2][3], inv[2][3]; };
 template <int D>
-__global__ void k_pack_particles(const uint32_t* __restrict__ state, size_t cap, int n, PackArgs pa,
+__global__ void k_pack_particles(const uint32_t* __restrict__ state, Statics stat, int n, PackArgs pa,
                                  uint32_t* __restrict__ xv, uint8_t* __restrict__ color) {
   using FL = Fld<D>;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    const uint32_t id = ldu(state, cap, FL::ID, s);
+    const uint32_t sid = tag_sid(ldu<D>(state, FL::TAG, s)), id = stat.gid[sid];
     if (id >= (uint32_t)n) continue;   // ids are a permutation of [0, n) on a single-device solver; never write outside
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       // ((a - lo) * (1 / (hi - lo)) * (2^bits - 1) + 0.499).astype(uint32), every step rounded to f32 (:50-55)
-      const float x = ldf(state, cap, FL::X + d, s), v = ldf(state, cap, FL::V + d, s);
+      const float x = ldf<D>(state, FL::X + d, s), v = ldf<D>(state, FL::V + d, s);
       const uint32_t xq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, pa.lo[0][d]), pa.inv[0][d]), 16777215.0f), 0.499f));
       const uint32_t vq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v, pa.lo[1][d]), pa.inv[1][d]), 255.0f), 0.499f));
       xv[(size_t)id * D + d] = (xq << 8) + vq;
     }
-    const uint32_t c = ldu(state, cap, FL::COLOR, s);
+    const uint32_t c = stat.color[sid];
     color[(size_t)id * 3 + 0] = (uint8_t)((c >> 16) & 255u);
     color[(size_t)id * 3 + 1] = (uint8_t)((c >> 8) & 255u);
     color[(size_t)id * 3 + 2] = (uint8_t)(c & 255u);
@@ -1397,33 +1426,34 @@ __global__ void k_pack_particles(const uint32_t* __restrict__ state, size_t cap,
 // g2p2g with a pending scatter half: F and Jp of the binned particles have already been
 // advanced by that half and live in the other set at their sorted slots (row s <- perm[s]);
 // everything else, and particles added since, is read from the live set.
+template <int D>
 __global__ void k_gather_rows_pending(const uint32_t* __restrict__ live, const uint32_t* __restrict__ other,
-                                      const uint32_t* __restrict__ perm, size_t cap, int first, int nwords, int idf,
+                                      const uint32_t* __restrict__ perm, Statics stat, int first, int nwords,
                                       int f_lo, int f_hi, int n_binned, int n, int64_t begin, int64_t end,
                                       uint32_t* __restrict__ out) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
     const bool binned = s < (uint32_t)n_binned;
     const uint32_t p = binned ? perm[s] : s;
-    const int64_t id = live[(size_t)idf * cap + p];
+    const int64_t id = vword<D>(live, stat, Fld<D>::ID, p);
     if (id < begin || id >= end) continue;
     for (int w = 0; w < nwords; ++w) {
       const int f = first + w;
       const bool adv = binned && f >= f_lo && f < f_hi;     // F words and Jp are contiguous
-      out[(size_t)(id - begin) * nwords + w] = adv ? other[(size_t)f * cap + s] : live[(size_t)f * cap + p];
+      out[(size_t)(id - begin) * nwords + w] = adv ? other[word<D>(f, s)] : vword<D>(live, stat, f, p);
     }
   }
 }
 
 template <int D>
-__global__ void k_debug_binning(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, int half,
+__global__ void k_debug_binning(const uint32_t* __restrict__ state, Statics stat, int n, float inv_dx, int half,
                                 int* __restrict__ out) {
   using G = Geo<D>;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
-    uint32_t id = ldu(state, cap, Fld<D>::ID, p);
+    uint32_t id = stat.gid[tag_sid(ldu<D>(state, Fld<D>::TAG, p))];
     if (id >= (uint32_t)n) continue;
 #pragma unroll
     for (int d = 0; d < D; ++d)
-      out[(size_t)id * D + d] = (base_index(ldf(state, cap, Fld<D>::X + d, p), inv_dx) + half) >> G::LOG_LEAF;
+      out[(size_t)id * D + d] = (base_index(ldf<D>(state, Fld<D>::X + d, p), inv_dx) + half) >> G::LOG_LEAF;
   }
 }
 

@@ -121,21 +121,21 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, MINB) k_p2g_cell(SubstepAr
         float x[D], v[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          x[d] = ldf(a.src, cap, FL::X + d, p);
-          v[d] = ldf(a.src, cap, FL::V + d, p);
+          x[d] = ldf<D>(a.src, FL::X + d, p);
+          v[d] = ldf<D>(a.src, FL::V + d, p);
         }
         float F[D * D], C[D * D], aff[D * D], mass;
 #pragma unroll
         for (int i = 0; i < D * D; ++i) {
-          F[i] = ldf(a.src, cap, FL::F + i, p);
-          C[i] = ldf(a.src, cap, FL::C + i, p);
+          F[i] = ldf<D>(a.src, FL::F + i, p);
+          C[i] = ldf<D>(a.src, FL::C + i, p);
         }
-        float Jp = ldf(a.src, cap, FL::JP, p);
-        const int mat = (int)ldu(a.src, cap, FL::MAT, p);
+        float Jp = ldf<D>(a.src, FL::JP, p);
+        const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
         particle_update<D>(a.K, a.dt, mat, F, C, Jp, aff, mass);
 #pragma unroll
-        for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, F[i]);
-        stf(a.dst, cap, FL::JP, s, Jp);
+        for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
+        stf<D>(a.dst, FL::JP, s, Jp);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const int base = base_index(x[d], a.K.inv_dx);
@@ -154,12 +154,10 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, MINB) k_p2g_cell(SubstepAr
         const int nb = s_next;
         if (nb < npb) {
           const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
-          const int lines = ((ne - ns) * 4 + 127) / 128 + 1;
-          for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
-            const int f = i / lines, l = i % lines;
-            const uint32_t* ptr = (f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + l * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-          }
+          const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
+          for (int i = tid; i < nt; i += T)
+            prefetch_l2_range(a.src + (size_t)(t0 + i) * FL::N * TILE, (uint32_t)(FL::TAG + 1) * TILE * 4u);
+          if (tid == T - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
         }
       }
       // ---- phase 2: per-(cell, slice) register accumulation

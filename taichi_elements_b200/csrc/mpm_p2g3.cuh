@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
   __shared__ int s_b, s_next, s_ticket, s_ticket_q;
   __shared__ int s_hist[32];
   __shared__ unsigned short s_queue[(P2G3::T / 32) * ((CHUNK + P2G3::T - 1) / P2G3::T) * 32];   // per warp: deferred particles (chunk-relative index | material << 12)
+  __shared__ int s_wn[P2G3::T / 32];             // entries in each warp's queue
   static_assert(CHUNK <= 4096, "queue entries hold a 12-bit index");
   pdl_enter();
   const int tid = threadIdx.x, lane = tid & 31;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
               k0 = sl == 0 ? 1.125f : (sl == 1 ? -0.25f : 0.125f);
 
   if (tid == 0) { s_b = atomicAdd(&a.st->work_p2g, 1); s_ticket = 0; }
+  if (tid < P2G3::T / 32) s_wn[tid] = 0;
   __syncthreads();
   int qpos = s_b;                                           // position in the work queue
   int b = qpos < npb ? p2g3_block_of(qpos, npb, n_bhi) : npb;
@@ -153,21 +155,21 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
         float x[D], v[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          x[d] = ldf(a.src, cap, FL::X + d, p);
-          v[d] = ldf(a.src, cap, FL::V + d, p);
+          x[d] = ldf<D>(a.src, FL::X + d, p);
+          v[d] = ldf<D>(a.src, FL::V + d, p);
         }
         float F[D * D], C[D * D], aff[D * D], mass;
 #pragma unroll
         for (int i = 0; i < D * D; ++i) {
-          F[i] = ldf(a.src, cap, FL::F + i, p);
-          C[i] = ldf(a.src, cap, FL::C + i, p);
+          F[i] = ldf<D>(a.src, FL::F + i, p);
+          C[i] = ldf<D>(a.src, FL::C + i, p);
         }
-        float Jp = ldf(a.src, cap, FL::JP, p);
-        const int mat = (int)ldu(a.src, cap, FL::MAT, p);
+        float Jp = ldf<D>(a.src, FL::JP, p);
+        const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
         particle_update<D>(a.K, a.dt, mat, F, C, Jp, aff, mass);
 #pragma unroll
-        for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, F[i]);
-        stf(a.dst, cap, FL::JP, s, Jp);
+        for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
+        stf<D>(a.dst, FL::JP, s, Jp);
         float fx[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
@@ -190,60 +192,56 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
 #pragma unroll
       for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
       unsigned short* wq = s_queue + (tid >> 5) * (NIT * 32);
-      int nq = 0;
+      int* wn = &s_wn[tid >> 5];
 #pragma unroll 1
-      for (int q = tid; q < ((cn + 31) & ~31); q += T) {
-        const bool live = q < cn;
+      for (int q = tid; q < cn; q += T) {
         const int s = start + c0 + q;
         const uint32_t p = pq[0];
 #pragma unroll
         for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
-        bool done = true;
-        int mat = 0;
-        if (live) {
-          float x[D], v[D];
+        float x[D], v[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) {
-            x[d] = ldf(a.src, cap, FL::X + d, p);
-            v[d] = ldf(a.src, cap, FL::V + d, p);
-          }
-          float F[D * D], C[D * D], aff[D * D], mass;
-#pragma unroll
-          for (int i = 0; i < D * D; ++i) {
-            F[i] = ldf(a.src, cap, FL::F + i, p);
-            C[i] = ldf(a.src, cap, FL::C + i, p);
-          }
-          float Jp = ldf(a.src, cap, FL::JP, p);
-          mat = (int)ldu(a.src, cap, FL::MAT, p);
-          float Fn[D * D];
-          trial_F<D>(a.K, a.dt, mat, F, C, Jp, Fn);
-          done = particle_update_fast<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
-          float fx[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
-          const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
-          if (done) {
-#pragma unroll
-            for (int i = 0; i < D * D; ++i) stf(a.dst, cap, FL::F + i, s, Fn[i]);
-            stf(a.dst, cap, FL::JP, s, Jp);
-            const float dx = a.K.dx;                                     // dpos = (o - fx) * dx
-            pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
-            pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
-            pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
-            pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
-          } else {
-            pay[q * PS + (0 ^ sw)] = make_float4(Fn[0], Fn[1], Fn[2], Fn[3]);
-            pay[q * PS + (1 ^ sw)] = make_float4(Fn[4], Fn[5], Fn[6], Fn[7]);
-            pay[q * PS + (2 ^ sw)] = make_float4(Fn[8], Jp, v[0], v[1]);
-            pay[q * PS + (3 ^ sw)] = make_float4(v[2], fx[0], fx[1], fx[2]);
-          }
+        for (int d = 0; d < D; ++d) {
+          x[d] = ldf<D>(a.src, FL::X + d, p);
+          v[d] = ldf<D>(a.src, FL::V + d, p);
         }
-        // append to this WARP's queue of deferred particles (the count is warp-uniform: no atomics)
-        const unsigned dm = __ballot_sync(0xffffffffu, !done);
-        if (!done) wq[nq + __popc(dm & ((1u << lane) - 1u))] = (unsigned short)(q | (mat << 12));
-        nq += __popc(dm);
+        float F[D * D], C[D * D], aff[D * D], mass;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) {
+          F[i] = ldf<D>(a.src, FL::F + i, p);
+          C[i] = ldf<D>(a.src, FL::C + i, p);
+        }
+        float Jp = ldf<D>(a.src, FL::JP, p);
+        const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
+        float Fn[D * D];
+        trial_F<D>(a.K, a.dt, mat, F, C, Jp, Fn);
+        const bool done = particle_update_fast<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
+        if (done) {
+#pragma unroll
+          for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, Fn[i]);
+          stf<D>(a.dst, FL::JP, s, Jp);
+        }
+        float fx[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
+        const float dx = a.K.dx;                                       // dpos = (o - fx) * dx
+        const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
+        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
+        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
+        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
+        if (!done) {                                                   // rare: park the inputs of the SVD path instead
+          pay[q * PS + (0 ^ sw)] = make_float4(Fn[0], Fn[1], Fn[2], Fn[3]);
+          pay[q * PS + (1 ^ sw)] = make_float4(Fn[4], Fn[5], Fn[6], Fn[7]);
+          pay[q * PS + (2 ^ sw)] = make_float4(Fn[8], Jp, v[0], v[1]);
+          pay[q * PS + (3 ^ sw)] = make_float4(v[2], fx[0], fx[1], fx[2]);
+          wq[atomicAdd(wn, 1)] = (unsigned short)(q | (mat << 12));
+        }
       }
       __syncwarp();                                                     // this warp's queue and stashes are visible
+      const int nq = *wn;
+      __syncwarp();
+      if (lane == 0) *wn = 0;
 #pragma unroll 1
       for (int i = lane; i < nq; i += 32) {
         const unsigned e = wq[i];
@@ -258,11 +256,11 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
         const float v[D] = {s2.z, s2.w, s3.x}, fx[D] = {s3.y, s3.z, s3.w};
         float C[D * D], aff[D * D], mass;
 #pragma unroll
-        for (int k = 0; k < D * D; ++k) C[k] = ldf(a.src, cap, FL::C + k, p);
+        for (int k = 0; k < D * D; ++k) C[k] = ldf<D>(a.src, FL::C + k, p);
         particle_update_svd<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
 #pragma unroll
-        for (int k = 0; k < D * D; ++k) stf(a.dst, cap, FL::F + k, s, Fn[k]);
-        stf(a.dst, cap, FL::JP, s, Jp);
+        for (int k = 0; k < D * D; ++k) stf<D>(a.dst, FL::F + k, s, Fn[k]);
+        stf<D>(a.dst, FL::JP, s, Jp);
         const float dx = a.K.dx;
         pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
         pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
@@ -276,18 +274,12 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
       if (c0 == 0 && a.pf_mode) {
         const int nb = s_next;
         if (nb < npb) {
+          // every word P2G reads (x .. material) is in the first FL::TAG + 1 rows of the block's tiles
           const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
-          if (a.pf_mode == 2) {
-            if (tid < FL::MAT + 2)
-              prefetch_l2_range((tid <= FL::MAT ? a.src + (size_t)tid * cap : a.perm) + ns, (uint32_t)(ne - ns) * 4u);
-          } else {
-            const int sh = a.pf_mode == 3 ? 3 : 5;         // words per prefetch: 8 (32 B) or 32 (128 B)
-            const int lines = (((ne - ns) + (1 << sh) - 1) >> sh) + 1;
-            for (int i = tid; i < (FL::MAT + 2) * lines; i += T) {
-              const int f = i / lines, l = i % lines;
-              prefetch_l2((f <= FL::MAT ? a.src + (size_t)f * cap : a.perm) + ns + (l << sh));
-            }
-          }
+          const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
+          for (int i = tid; i < nt; i += T)
+            prefetch_l2_range(a.src + (size_t)(t0 + i) * FL::N * TILE, (uint32_t)(FL::TAG + 1) * TILE * 4u);
+          if (tid == T - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
         }
       }
       // ---- phase 2: (cell, slice) register accumulation (:577-584), packed pairs

@@ -314,10 +314,17 @@ def _make_distributed_solver():
             return list(lo), list(hi)
 
         def _batch_begin(self, glo, ghi):
-            need = self._n + 2 * self._mig_cap          # rows for the particles that may arrive
+            lib, ctx = self._lib, self._ctx
+            # static rows (colour, id, emitter by sid): departures leave holes, arrivals append -- renumber them by
+            # storage slot once the holes exceed one message capacity (a cheap pass between batches)
+            ns = ctypes.c_int64()
+            lib.mpm_get_static_rows(ctx, ctypes.byref(ns))
+            if ns.value - self._n > self._mig_cap:
+                self._check(lib.mpm_compact_statics(ctx, self._stream()), 'mpm_compact_statics')
+                ns.value = self._n
+            need = max(self._n, ns.value) + 2 * self._mig_cap     # rows for the particles that may arrive
             if need > self._cap:
                 self._rebind(capacity=max(need, int(self._cap * 1.25)))
-            lib, ctx = self._lib, self._ctx
             self._check(lib.mpm_set_layout_box(ctx, 1, (ctypes.c_int32 * 3)(*glo), (ctypes.c_int32 * 3)(*ghi)),
                         'mpm_set_layout_box')
             self._check(lib.mpm_batch_begin(ctx, self._stream()), 'mpm_batch_begin')
@@ -512,8 +519,9 @@ def _make_distributed_solver():
             """This rank's live particles: dict of arrays in storage order, with global ids.
             Rows of particles that have left the slab since the last substep are excluded."""
             n = self._n
-            out = np.empty((self._nf, n), np.int32)
-            for f in range(self._nf):
+            nv = self._lib.mpm_virtual_fields(self.dim)      # x v F C Jp material color id emitter
+            out = np.empty((nv, n), np.int32)
+            for f in range(nv):
                 if n:
                     self._check(
                         self._lib.mpm_download_raw(self._ctx, f, out[f].ctypes.data_as(ctypes.c_void_p),

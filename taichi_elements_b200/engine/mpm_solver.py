@@ -198,10 +198,11 @@ class MPMSolver:
         if rc != 0:
             raise _lib.MPMError(f'mpm_create failed ({rc})')
         self._ctx = ctx
-        self._nf = self._lib.mpm_state_fields(self.dim)
+        self._nf = self._lib.mpm_state_fields(self.dim)          # physical words per particle (x v F C Jp tag)
         self._cap = 0
         self._max_blocks = 0
         self._state = None
+        self._static = None
         self._ws = None
         self._n = 0
         self._rebind(capacity=1 << 14, max_blocks=1 << 10)
@@ -219,7 +220,7 @@ class MPMSolver:
         if use_emitter_id:
             self.emitter_ids = _Field(self, jp + 4, (), np.int32)
         self.n_particles = _Scalar(lambda: self._n)
-        self.particle = _ParticleNode(self._nf * 4)
+        self.particle = _ParticleNode((self._nf + 3) * 4)     # bytes per particle: one state set + the static row
 
         self.grid_postprocess = []
         if self.dim == 2:
@@ -260,12 +261,19 @@ class MPMSolver:
         mb = self._max_blocks if max_blocks is None else int(max_blocks)
         with torch.cuda.device(self._device):
             if cap != self._cap:
-                new_state = torch.empty((2, self._nf, cap), dtype=torch.int32, device=self._device)
+                # one set = tiles of 32 particles x nf words x 32 lanes (include/mpm_b200.h): rows are tile-major,
+                # so the live particles are a prefix of the buffer
+                new_state = torch.empty((2, cap // 32, self._nf, 32), dtype=torch.int32, device=self._device)
+                new_static = torch.empty((3, cap), dtype=torch.int32, device=self._device)   # colour, id, emitter by sid
                 if self._n > 0:
                     cur = ctypes.c_int32()
                     self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
-                    new_state[0, :, :self._n] = self._state[cur.value, :, :self._n]
-                self._state = new_state
+                    tiles = (self._n + 31) // 32
+                    new_state[0, :tiles] = self._state[cur.value, :tiles]
+                    ns = ctypes.c_int64()
+                    self._lib.mpm_get_static_rows(self._ctx, ctypes.byref(ns))
+                    new_static[:, :ns.value] = self._static[:, :ns.value]
+                self._state, self._static = new_state, new_static
                 cur_set = 0
             else:
                 cur = ctypes.c_int32()
@@ -277,8 +285,8 @@ class MPMSolver:
             torch.cuda.synchronize(self._device)
         self._cap, self._max_blocks = cap, mb
         self._check(
-            self._lib.mpm_bind(self._ctx, self._state[0].data_ptr(), self._state[1].data_ptr(), cap,
-                               self._ws.data_ptr(), nbytes, mb), 'mpm_bind')
+            self._lib.mpm_bind(self._ctx, self._state[0].data_ptr(), self._state[1].data_ptr(),
+                               self._static.data_ptr(), cap, self._ws.data_ptr(), nbytes, mb), 'mpm_bind')
         self._check(self._lib.mpm_set_state(self._ctx, cur_set, self._n), 'mpm_set_state')
 
     def _reserve(self, new_particles):
@@ -648,13 +656,19 @@ class MPMSolver:
                 np.asarray(F, np.float32).reshape(n, d * d).T, np.asarray(C, np.float32).reshape(n, d * d).T,
                 np.asarray(Jp, np.float32)[None]]
         fl = np.ascontiguousarray(np.concatenate(rows, axis=0)).view(np.int32)
-        ints = np.stack([np.asarray(material, np.int32), np.asarray(color, np.int32),
-                         np.arange(n, dtype=np.int32), np.zeros(n, np.int32)])
-        words = torch.from_numpy(np.ascontiguousarray(np.concatenate([fl, ints], axis=0))).to(self._device)
-        self._state[0, :, :n] = words
+        tag = ((np.asarray(material, np.int64) << 29) | np.arange(n, dtype=np.int64)).astype(np.uint32).view(np.int32)
+        words = np.ascontiguousarray(np.concatenate([fl, tag[None]], axis=0))       # (nf, n): x v F C Jp tag
+        statics = np.stack([np.asarray(color, np.int32), np.arange(n, dtype=np.int32), np.zeros(n, np.int32)])
+        tiles = (n + 31) // 32
+        padded = np.zeros((self._nf, tiles * 32), np.int32)
+        padded[:, :n] = words
+        tiled = np.ascontiguousarray(padded.reshape(self._nf, tiles, 32).transpose(1, 0, 2))   # (tiles, nf, 32)
+        self._state[0, :tiles] = torch.from_numpy(tiled).to(self._device)
+        self._static[:, :n] = torch.from_numpy(statics).to(self._device)
         torch.cuda.synchronize(self._device)
         self._n = n
         self._check(self._lib.mpm_set_state(self._ctx, 0, n), 'mpm_set_state')
+        self._check(self._lib.mpm_set_static_rows(self._ctx, n), 'mpm_set_static_rows')
 
     def debug_binning(self):
         out = np.empty((self._n, self.dim), np.int32)

@@ -30,7 +30,8 @@ def test_header_symbols_exported():
 def test_sizes_and_argument_checks():
     from taichi_elements_b200 import _lib
     lib = _lib.load()
-    assert lib.mpm_state_fields(3) == 29 and lib.mpm_state_fields(2) == 17 and lib.mpm_state_fields(4) == -1
+    assert lib.mpm_state_fields(3) == 26 and lib.mpm_state_fields(2) == 14 and lib.mpm_state_fields(4) == -1
+    assert lib.mpm_virtual_fields(3) == 29 and lib.mpm_virtual_fields(2) == 17      # the reference's field order
     a = lib.mpm_workspace_bytes(3, 1 << 20, 1 << 12)
     b = lib.mpm_workspace_bytes(3, 1 << 21, 1 << 12)
     c = lib.mpm_workspace_bytes(3, 1 << 20, 1 << 13)
