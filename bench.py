@@ -559,6 +559,15 @@ def main():
                         'frac_of_nominal_8TBs': b_alg_step / (ms_per_step * 1e-3) / 1e9 / 8000.0},
         }
     else:
+        # per-rank phase times (separate pass with CUDA events on each rank's stream): "sort+structure" includes the
+        # wait for the neighbours' migration message, "grid_op" the wait for their halo -- the skew between ranks
+        ph = phase_times(mpm, dt, args.steps)
+        tp = torch.tensor([ph['sort+structure'], ph['p2g'], ph['grid_op'], ph['g2p'], float(mpm.n_particles[None])],
+                          dtype=torch.float64, device=dev)
+        allp = [torch.empty_like(tp) for _ in range(world)]
+        dist.all_gather(allp, tp)
+        per_rank = [{'sort+structure': round(float(t[0]), 4), 'p2g': round(float(t[1]), 4), 'grid_op': round(float(t[2]), 4),
+                     'g2p': round(float(t[3]), 4), 'particles': int(t[4])} for t in allp]
         # whole job: sum over ranks of the algorithmic bytes / max-over-ranks time, against N x peak
         b_job = allsum(b_alg_step)
         achieved = b_job / (ms_per_step * 1e-3) / 1e9
@@ -566,6 +575,7 @@ def main():
             'bound': 'hbm', 'kernel': 'whole substep, all ranks (per-kernel events are a single-GPU pass)',
             'achieved': achieved, 'peak': peak * world, 'unit': 'GB/s', 'frac': achieved / (peak * world),
             'traffic': None, 'peak_source': peak_src + f' x {world} GPUs', 'algorithmic_bytes_per_launch': b_job,
+            'kernel_ms_per_rank': per_rank,
         }
 
     # ---------------- end to end through the public API, host buffers ----------------

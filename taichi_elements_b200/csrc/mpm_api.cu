@@ -17,6 +17,7 @@
 #include "mpm_comm.cuh"
 #include "mpm_p2g.cuh"
 #include "mpm_p2g3.cuh"
+#include "mpm_g2p2g.cuh"
 
 using namespace mpm;
 
@@ -54,6 +55,7 @@ struct mpm_ctx {
   // peer path (NVLink writes into the neighbour's buffers)
   uint32_t* peer_region = nullptr;     // cudaMalloc'ed by mpm_peer_alloc: flags + the four receive buffers
   size_t peer_mig_words = 0, peer_halo_words = 0, peer_plane_words = 0;   // plane: one of the 3 rotating halo planes of a side
+  int fused_fast = 1;                  // use_g2p2g, 3D: cell-owner fused kernel (MPM_G2P2G=simple: general kernel)
   int defer_svd = 0;                   // MPM_DEFER_SVD=0: SVD inline in the first pass of k_p2g3
   int fused_halo = 1;                  // MPM_FUSED_HALO=0: legacy pack / wait / add kernels on the peer path
   void* peer_open[2] = {nullptr, nullptr};
@@ -61,10 +63,21 @@ struct mpm_ctx {
   bool ext_box = false;          // layout box supplied by the host (global box of all ranks)
   int box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
   // state of the batch being enqueued (phase API)
-  // g2p2g mode: a scatter half (bin + P2G + grid op) awaits its gather half
-  bool have_pending = false, pending_rebuild = false, skip_gather = false;
-  float pending_dt = 0.f;
-  int pending_n = 0, pending_npb = 0, pending_ngb = 0;
+  // Block structure and grid exist twice (use_g2p2g: the fused kernel reads last substep's OUTPUT grid through its
+  // block table while it scatters into the other one; the split path only uses set 0).  `sel` = the set that the
+  // pointers flags / fscan / grid / pb_start / pb_key / pb_nbr currently refer to.
+  int* flags2[2] = {nullptr, nullptr};
+  int* fscan2[2] = {nullptr, nullptr};
+  float4* grid2[2] = {nullptr, nullptr};
+  int* pb_start2[2] = {nullptr, nullptr};
+  uint32_t* pb_key2[2] = {nullptr, nullptr};
+  int* pb_nbr2[2] = {nullptr, nullptr};
+  int sel = 0;
+  // use_g2p2g: the input grid of the next fused substep = set `sel` as left by the last completed substep
+  bool fused_prev = false;       // such a grid exists (false before the first substep and after clear_particles)
+  int64_t fused_n_old = 0;       // rows that existed then: rows beyond them skip the gather (:396-399)
+  KeyLayout fused_L{};           // key layout of its block table
+  int fused_nlin = 0, fused_npb = 0, fused_ngb = 0;
   bool keys_ready = false;     // the previous G2P of this batch already produced keys + flags
   int fuse_keys = 1;
   int sort_seed = 1;            // (MPM_SORT_SEED) block-sorted storage of large add_particles arrays
@@ -103,6 +116,8 @@ struct mpm_ctx {
   int launches = 0;
   int done_last = 0;
   bool profiling = false;
+  cudaEvent_t* cur_ev = nullptr;   // phase API: the five events of the substep being enqueued (profiling), or null
+  int prof_enq = 0;                // substeps of the open batch that carry events
   std::vector<cudaEvent_t> ev;   // 5 per profiled substep
   float ms[4] = {0, 0, 0, 0};
   std::string err;
@@ -146,6 +161,7 @@ static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, in
 struct Carve {
   size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
       off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, off_scan_desc, total,
+      off_pb_start2, off_pb_nbr2, off_grid2, off_pb_key2, off_flags2, off_fscan2,
       cub_bytes, scan_tiles;
   int64_t table_cap;
 };
@@ -196,6 +212,13 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_pb_key = take((size_t)max_blocks * 4);
   c.off_flags = take((size_t)c.table_cap * 4);
   c.off_fscan = take((size_t)c.table_cap * 4);
+  // second set of block structure + grid (use_g2p2g ping-pong)
+  c.off_pb_start2 = take((size_t)(max_blocks + 2) * 4);
+  c.off_pb_nbr2 = take((size_t)max_blocks * no * 4);
+  c.off_grid2 = take((size_t)max_blocks * cells * sizeof(float4));
+  c.off_pb_key2 = take((size_t)max_blocks * 4);
+  c.off_flags2 = take((size_t)c.table_cap * 4);
+  c.off_fscan2 = take((size_t)c.table_cap * 4);
   c.off_cellcount = take(((size_t)max_blocks * cells + 1) * 4);
   c.off_cellstart = take(((size_t)max_blocks * cells + 1) * 4);
   c.total = o;
@@ -271,6 +294,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
   if (const char* v = getenv("MPM_FUSED_HALO")) ctx->fused_halo = atoi(v);
   if (const char* v = getenv("MPM_DEFER_SVD")) ctx->defer_svd = atoi(v);
+  if (const char* v = getenv("MPM_G2P2G")) ctx->fused_fast = strcmp(v, "simple") != 0;
   if (const char* v = getenv("MPM_SCAN")) ctx->own_scan = strcmp(v, "cub") != 0;
   {
     int occ = 1;
@@ -296,6 +320,12 @@ extern "C" int mpm_destroy(mpm_ctx* ctx) {
 
 extern "C" const char* mpm_last_error(mpm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
+static void select_set(mpm_ctx* ctx, int q) {
+  ctx->sel = q;
+  ctx->flags = ctx->flags2[q]; ctx->fscan = ctx->fscan2[q]; ctx->grid = ctx->grid2[q];
+  ctx->pb_start = ctx->pb_start2[q]; ctx->pb_key = ctx->pb_key2[q]; ctx->pb_nbr = ctx->pb_nbr2[q];
+}
+
 extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, void* statics, int64_t capacity, void* ws, size_t ws_bytes,
                         int32_t max_blocks) {
   if (!ctx || !s0 || !s1 || !statics || !ws || capacity < 1 || max_blocks < 1) return fail(ctx, MPM_E_INVALID, "mpm_bind: bad argument");
@@ -305,6 +335,13 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, void* statics, int64_t
   Carve c = carve(ctx->dim, capacity, max_blocks);
   if (ws_bytes < c.total) return fail(ctx, MPM_E_INVALID, "mpm_bind: workspace too small");
   CK(cudaSetDevice(ctx->P.device));
+  // use_g2p2g: the input grid of the next substep and its block structure live in the OLD workspace (which the
+  // caller keeps alive until this call returns): remember where, they are copied over below
+  const bool migrate = ctx->K.g2p2g && ctx->fused_prev && ctx->ws && ctx->ws != ws;
+  int* o_flags = ctx->flags2[ctx->sel]; int* o_fscan = ctx->fscan2[ctx->sel]; float4* o_grid = ctx->grid2[ctx->sel];
+  int* o_pbs = ctx->pb_start2[ctx->sel]; uint32_t* o_pbk = ctx->pb_key2[ctx->sel]; int* o_pbn = ctx->pb_nbr2[ctx->sel];
+  if (migrate && (ctx->fused_npb > max_blocks || ctx->fused_ngb > max_blocks || 2 * (int64_t)ctx->fused_nlin + 1 > c.table_cap))
+    return fail(ctx, MPM_E_INVALID, "mpm_bind: the new workspace cannot hold the pending g2p2g grid");
   ctx->state[0] = (uint32_t*)s0;
   ctx->state[1] = (uint32_t*)s1;
   ctx->stat.color = (uint32_t*)statics;
@@ -342,7 +379,26 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, void* statics, int64_t
   ctx->table_cap = c.table_cap;
   ctx->ct_dirty = true;
   ctx->last_valid = false;
-  if (ctx->have_pending) ctx->pending_rebuild = true;   // the pending g2p2g half lived in the old workspace
+  ctx->pb_start2[0] = ctx->pb_start; ctx->pb_nbr2[0] = ctx->pb_nbr; ctx->grid2[0] = ctx->grid;
+  ctx->pb_key2[0] = ctx->pb_key; ctx->flags2[0] = ctx->flags; ctx->fscan2[0] = ctx->fscan;
+  ctx->pb_start2[1] = (int*)(b + c.off_pb_start2); ctx->pb_nbr2[1] = (int*)(b + c.off_pb_nbr2);
+  ctx->grid2[1] = (float4*)(b + c.off_grid2); ctx->pb_key2[1] = (uint32_t*)(b + c.off_pb_key2);
+  ctx->flags2[1] = (int*)(b + c.off_flags2); ctx->fscan2[1] = (int*)(b + c.off_fscan2);
+  if (migrate) {
+    const int q = ctx->sel, no = ctx->no;
+    const size_t nt = 2 * (size_t)ctx->fused_nlin + 1;
+    CK(cudaMemcpy(ctx->flags2[q], o_flags, nt * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->fscan2[q], o_fscan, nt * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->grid2[q], o_grid, (size_t)ctx->fused_ngb * ctx->cells * sizeof(float4), cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->pb_start2[q], o_pbs, ((size_t)ctx->fused_npb + 1) * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->pb_key2[q], o_pbk, (size_t)ctx->fused_npb * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->pb_nbr2[q], o_pbn, (size_t)ctx->fused_npb * no * 4, cudaMemcpyDeviceToDevice));
+  } else if (ctx->ws != nullptr && ctx->fused_prev && ctx->K.g2p2g && ctx->ws == ws) {
+    // same workspace re-bound: nothing moved
+  } else {
+    ctx->fused_prev = false;
+  }
+  select_set(ctx, ctx->K.g2p2g ? ctx->sel : 0);
   return MPM_OK;
 }
 
@@ -354,10 +410,7 @@ extern "C" int mpm_get_state(mpm_ctx* ctx, int32_t* cur, int64_t* n) {
 }
 extern "C" int mpm_set_state(mpm_ctx* ctx, int32_t cur, int64_t n) {
   if (!ctx || (cur != 0 && cur != 1) || n < 0 || (size_t)n > ctx->cap) return fail(ctx, MPM_E_INVALID, "mpm_set_state: bad argument");
-  if (ctx->have_pending && n < ctx->pending_n) {
-    ctx->have_pending = false;   // particles were replaced or cleared: start over (all rows count as new)
-    ctx->skip_gather = false;
-  }
+  if (n < ctx->n || n < ctx->fused_n_old) ctx->fused_prev = false;   // cleared or replaced: the next fused substep starts over
   ctx->cur = cur;
   ctx->n = n;
   if (n == 0) ctx->n_static = 0;
@@ -380,7 +433,7 @@ extern "C" int mpm_set_static_rows(mpm_ctx* ctx, int64_t n_static) {
 extern "C" int mpm_compact_statics(mpm_ctx* ctx, void* stream) {
   if (!ctx) return MPM_E_INVALID;
   if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
-  if (ctx->in_batch || ctx->have_pending) return fail(ctx, MPM_E_INVALID, "mpm_compact_statics: inside a batch / pending g2p2g half");
+  if (ctx->in_batch) return fail(ctx, MPM_E_INVALID, "mpm_compact_statics: inside a batch");
   CK(cudaSetDevice(ctx->P.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)ctx->n;
@@ -437,7 +490,7 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   int blocks = gs_blocks(a.n, 256, ctx->sm_count);
   // A large array of external positions is stored sorted by leaf block (ids keep the insertion order): the
   // first substep then reads block-local rows instead of gathering 26 words per particle at random.  The sort
-  // borrows the binning scratch, which is free between batches except for g2p2g's pending permutation; the
+  // borrows the binning scratch, which is free between batches; the
   // distributed solver writes its global ids by row and keeps the input order.
   if (a.mode == 0 && ctx->sort_seed && a.n >= (1 << 15) && !ctx->K.g2p2g && !ctx->slab.enabled && !ctx->in_batch &&
       ctx->P.grid_size == 4096 && (size_t)a.n <= ctx->cap) {
@@ -799,7 +852,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
   const int sm = ctx->sm_count;
   Status* st = ctx->d_status;
   const uint32_t* src = ctx->state[cur];
-  if (prof) cudaEventRecord(ev[0], s);
+  if (prof && !ctx->in_batch) cudaEventRecord(ev[0], s);   // (phase API: recorded before the unpack)
   const uint32_t* keys = nullptr;
   const uint32_t* perm = nullptr;
   const int* cellstart = nullptr;
@@ -941,63 +994,70 @@ static int enqueue_grid_g2p(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, cud
   return MPM_OK;
 }
 
-// ---- g2p2g order (engine/mpm_solver.py:773-787): a substep is the GATHER half of the split
-// substep whose scatter half ran last (same particle sets, same binning), then a new scatter
-// half at the advected positions.  `cur` = live set before the call.
+// ---- use_g2p2g (engine/mpm_solver.py:773-787): key pass, binning of the advected positions, ONE fused kernel,
+// grid op -- see mpm_g2p2g.cuh.  Every substep switches to the other set of block structure + grid; the set it
+// leaves behind is the next substep's input.
 template <int D>
-static int enqueue_gather_half(mpm_ctx* ctx, float dt, int cur, cudaStream_t s) {
-  const int n = (int)ctx->n;
-  const int r0 = ctx->have_pending ? ctx->pending_n : 0;
-  if (ctx->have_pending) {
-    SubstepArgs<D> a = make_args<D>(ctx, dt, cur);
-    launch_g2p<D>(ctx, a, s);
-    ctx->launches += 1;
-  }
-  if (r0 < n) {
-    k_copy_advect<D><<<gs_blocks(n - r0, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[cur], ctx->state[cur ^ 1], ctx->cap, r0, n, dt,
-                                                                       ctx->K.inv_dx, ctx->d_status);
-    ctx->launches += 1;
-  }
-  k_half_commit<<<1, 1, 0, s>>>(ctx->d_status);
-  ctx->launches += 1;
-  CK(cudaGetLastError());
-  return MPM_OK;
-}
-template <int D>
-static int enqueue_scatter_half(mpm_ctx* ctx, float dt, int cur, int commit_prev, cudaStream_t s) {
-  int rc = enqueue_bin_p2g<D>(ctx, dt, cur, commit_prev, s, nullptr);
-  if (rc) return rc;
-  return enqueue_grid_op<D>(ctx, dt, s);
-}
-
-// The workspace was re-bound while a scatter half was pending: redo it (same rows, same dt) so that
-// its block structure, grid and advanced F/Jp exist again; it is a pure function of the live set.
-// Expects a valid key layout.  Returns MPM_OK, MPM_E_BLOCK_CAPACITY, or MPM_E_INVALID (retry layout).
-static int rebuild_pending(mpm_ctx* ctx, cudaStream_t s) {
-  const bool d3 = ctx->dim == 3;
-  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-  k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, ctx->pending_n, (int)ctx->n_static);
-  const int64_t n_keep = ctx->n;
-  ctx->n = ctx->pending_n;
-  int rc = d3 ? enqueue_scatter_half<3>(ctx, ctx->pending_dt, ctx->cur, 0, s)
-              : enqueue_scatter_half<2>(ctx, ctx->pending_dt, ctx->cur, 0, s);
-  ctx->n = n_keep;
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  if (ctx->h_status->err) {
-    ctx->bbox_valid = false;
-    ctx->layout_valid = false;
-    if (ctx->h_status->err & ERR_BLOCK_CAPACITY) {
-      ctx->last.need_blocks = ctx->h_status->need_blocks;
-      ctx->err = "active leaf blocks exceed the bound capacity (rebuilding the pending g2p2g half)";
-      return MPM_E_BLOCK_CAPACITY;
+static int enqueue_fused_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s, bool have_prev, int64_t n_old,
+                                 int npb_host) {
+  using G = Geo<D>;
+  const int n = (int)ctx->n, sm = ctx->sm_count;
+  Status* st = ctx->d_status;
+  const int q_in = ctx->sel, q_out = ctx->sel ^ 1;
+  int nlin = 1;
+  for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+  FusedArgs<D> fa{};
+  fa.s = make_args<D>(ctx, dt, cur);                       // (set q_in: last substep's particle blocks)
+  fa.grid_in = have_prev ? ctx->grid2[q_in] : nullptr;
+  fa.tin = GridTable{ctx->flags2[q_in], ctx->fscan2[q_in], ctx->fused_nlin, ctx->fused_L};
+  fa.n_old = have_prev ? (int)n_old : 0;
+  fa.keys = ctx->keys_a; fa.flags = ctx->flags2[q_out]; fa.nlin = nlin;
+  // ---- key pass
+  CK(cudaMemsetAsync(ctx->flags2[q_out], 0, (size_t)(2 * nlin + 1) * 4, s));
+  if (have_prev && ctx->fused_npb > 0)   // (npb_host < 0: the block count of the substep enqueued just before is on the device)
+    k_g2p2g_keys<D><<<std::min(ctx->fused_npb, sm * 16), 128, 0, s>>>(fa, npb_host);
+  if (fa.n_old < n) k_g2p2g_keys_tail<D><<<gs_blocks(n - fa.n_old, 256, sm), 256, 0, s>>>(fa, fa.n_old, n);
+  ctx->launches += 2;
+  // ---- binning of the advected positions into set q_out (counting sort, mpm_bin.cuh)
+  select_set(ctx, q_out);
+  const int ncell = ctx->max_blocks * G::CELLS + 1;
+  CK(cudaMemsetAsync(ctx->cellcount, 0, (size_t)ncell * 4, s));
+  { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, false, s); if (rc) return rc; }
+  CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
+                  ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
+  { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s, ctx->fscan + nlin, G::CELLS); if (rc) return rc; }
+  CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
+                  ctx->fscan, ctx->cellstart, ctx->vals_b, st));
+  CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
+                  ctx->flags, ctx->fscan, nlin, ctx->L, ctx->pb_key, ctx->cellstart, ctx->pb_start, ctx->pb_nbr,
+                  ctx->gb_key, ctx->max_blocks, st, ctx->slab));
+  CK(launch_chain(ctx->pdl, k_clear_grid<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s,
+                  ctx->grid, (const Status*)st, (int*)nullptr, 0, (int*)nullptr, 0, 0, (float4*)nullptr, (float4*)nullptr, 0));
+  ctx->launches += 6;
+  // ---- the fused kernel over the NEW blocks, then the grid op on the output grid
+  ctx->cur_keys = ctx->keys_a; ctx->cur_perm = ctx->vals_b; ctx->cur_cellstart = ctx->cellstart;
+  ctx->last_keys = ctx->keys_a;
+  fa.s = make_args<D>(ctx, dt, cur);                       // (set q_out)
+  bool fast = false;
+  if constexpr (D == 3) {
+    if (ctx->fused_fast) {     // cell-owner scatter (mpm_p2g3.cuh); MPM_G2P2G=simple selects the general kernel
+      static LaunchCache lc;
+      constexpr size_t smem = p2g3_smem_bytes<640>();
+      const int grid = cached_grid(lc, ctx, k_p2g3<640, 3, false, false, true>, P2G3::T, smem);
+      CK(launch_chain(ctx->pdl, k_p2g3<640, 3, false, false, true>, grid, P2G3::T, smem, s, fa));
+      fast = true;
     }
-    return MPM_E_INVALID;
   }
-  ctx->pending_npb = ctx->h_status->npb;
-  ctx->pending_ngb = ctx->h_status->ngb;
-  ctx->pending_rebuild = false;
+  if (!fast) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p2g<D>, 256, 0);
+    CK(launch_chain(ctx->pdl, k_g2p2g<D>, sm * std::max(occ, 1), 256, 0, s, fa));
+  }
+  int rc = enqueue_grid_op<D>(ctx, dt, s);
+  if (rc) return rc;
+  CK(launch_chain(ctx->pdl, k_fused_commit, 1, 1, 0, s, st));
+  ctx->launches += 2;
+  CK(cudaGetLastError());
   return MPM_OK;
 }
 
@@ -1008,47 +1068,50 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
     if (rc) return rc;
     rc = update_layout(ctx);
     if (rc) return rc;
+    if (!ctx->dense) return fail(ctx, MPM_E_INVALID, "use_g2p2g needs the dense block table (particle box too large)");
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-    if (ctx->have_pending && ctx->pending_rebuild) {
-      rc = rebuild_pending(ctx, s);
-      if (rc == MPM_E_BLOCK_CAPACITY) return rc;
-      if (rc) continue;
-      CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
-    }
-    k_batch_begin_keep<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, ctx->pending_npb, ctx->pending_ngb, (int)ctx->n_static);
-    const int cur0 = ctx->cur;
-    int cur = cur0;
-    const bool skipped_first = ctx->skip_gather;
+    k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
+    const int cur0 = ctx->cur, sel0 = ctx->sel;
+    const bool prev0 = ctx->fused_prev;
+    const int64_t nold0 = ctx->fused_n_old;
+    const KeyLayout L0 = ctx->fused_L;
+    const int nlin0 = ctx->fused_nlin, npb0 = ctx->fused_npb;
+    int nlin = 1;
+    for (int d = 0; d < ctx->dim; ++d) nlin *= ctx->L.eb[d];
+    // enqueue optimistically: substep i reads what substep i - 1 wrote; a substep that refuses to run (capacity,
+    // box) makes every later kernel a no-op and the host bookkeeping is rewound to the last completed one
     for (int i = 0; i < count; ++i) {
-      if (!(i == 0 && ctx->skip_gather)) {
-        rc = d3 ? enqueue_gather_half<3>(ctx, dt, cur, s) : enqueue_gather_half<2>(ctx, dt, cur, s);
-        if (rc) return rc;
-        cur ^= 1;
+      const bool have_prev = i > 0 || prev0;
+      if (i > 0) {
+        // structure of the substep just enqueued: its block count only exists on the device (Status::npb)
+        ctx->fused_L = ctx->L; ctx->fused_nlin = nlin; ctx->fused_npb = ctx->max_blocks; ctx->fused_n_old = ctx->n;
       }
-      // from here on every row is binned: the pending description covers all n rows
-      ctx->have_pending = true; ctx->pending_n = (int)ctx->n; ctx->pending_dt = dt;
-      rc = d3 ? enqueue_scatter_half<3>(ctx, dt, cur, i > 0, s) : enqueue_scatter_half<2>(ctx, dt, cur, i > 0, s);
+      rc = d3 ? enqueue_fused_substep<3>(ctx, dt, cur0 ^ (i & 1), s, have_prev, i > 0 ? ctx->n : nold0, i > 0 ? -1 : npb0)
+              : enqueue_fused_substep<2>(ctx, dt, cur0 ^ (i & 1), s, have_prev, i > 0 ? ctx->n : nold0, i > 0 ? -1 : npb0);
       if (rc) return rc;
     }
-    k_end<<<1, 1, 0, s>>>(ctx->d_status);
-    ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const Status& h = *ctx->h_status;
-    ctx->cur = cur0 ^ (h.half & 1);
+    ctx->cur = cur0 ^ (h.done & 1);
+    select_set(ctx, sel0 ^ (h.done & 1));
     count -= h.done;
     ctx->done_last += h.done;
-    ctx->skip_gather = false;
-    ctx->bbox_valid = false;            // the box of the advected positions is re-measured next batch
-    if (h.done > 0 || !h.err) { ctx->last = h; ctx->lastL = ctx->L; ctx->last_valid = (h.err == 0); }
+    ctx->bbox_valid = false;
+    if (h.done > 0) {
+      ctx->last = h; ctx->lastL = ctx->L; ctx->last_valid = (h.err == 0);
+      ctx->fused_prev = true; ctx->fused_L = ctx->L; ctx->fused_nlin = nlin; ctx->fused_n_old = ctx->n;
+      // (after an error the status block still describes the last COMPLETED substep only if it failed before
+      // k_bin_finish rewrote npb / ngb, which is where capacity and box errors are raised)
+      ctx->fused_npb = h.npb; ctx->fused_ngb = h.ngb;
+    } else {
+      ctx->fused_prev = prev0; ctx->fused_L = L0; ctx->fused_nlin = nlin0; ctx->fused_npb = npb0; ctx->fused_n_old = nold0;
+    }
     if (!h.err) {
-      ctx->pending_npb = h.npb; ctx->pending_ngb = h.ngb;
+      for (int d = 0; d < 3; ++d) { ctx->bb_min[d] = h.bb_min[d]; ctx->bb_max[d] = h.bb_max[d]; }
+      ctx->bbox_valid = true;
       return MPM_OK;
     }
-    // a scatter half refused to run; its gather half (if it ran) is done and must not be repeated
-    const int halves = h.half + (skipped_first ? 1 : 0);
-    ctx->skip_gather = halves > h.done;
-    ctx->have_pending = false;
     ctx->layout_valid = false;
     if (h.err & ERR_BLOCK_CAPACITY) {
       ctx->last.need_blocks = h.need_blocks;
@@ -1057,6 +1120,7 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
       ctx->err = buf;
       return MPM_E_BLOCK_CAPACITY;
     }
+    // ERR_BBOX: the advected positions left the sticky box; rebuild it around them and go on
   }
   return fail(ctx, MPM_E_INVALID, "g2p2g substep could not establish a key layout");
 }
@@ -1223,6 +1287,7 @@ extern "C" int mpm_batch_begin(mpm_ctx* ctx, void* stream) {
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
   k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
   ctx->in_batch = true;
+  ctx->prof_enq = 0;
   ctx->batch_cur0 = ctx->cur;
   ctx->batch_enq = 0;
   ctx->keys_ready = false; ctx->cell_zeroed = false; ctx->flags_zeroed = false;
@@ -1264,8 +1329,8 @@ extern "C" int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo, const void* f
 extern "C" int mpm_phase_p2g(mpm_ctx* ctx, double dt, void* stream) {
   REQUIRE_BATCH();
   const int cur = ctx->batch_cur0 ^ (ctx->batch_enq & 1);
-  return ctx->dim == 3 ? enqueue_bin_p2g<3>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, nullptr)
-                       : enqueue_bin_p2g<2>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, nullptr);
+  return ctx->dim == 3 ? enqueue_bin_p2g<3>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, ctx->cur_ev)
+                       : enqueue_bin_p2g<2>(ctx, (float)dt, cur, ctx->batch_enq > 0, s, ctx->cur_ev);
 }
 
 extern "C" int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream) {
@@ -1317,8 +1382,8 @@ extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
   // the key pass of the next substep of this batch rides on G2P (its layout box is fixed for the batch);
   // if no substep follows the keys are simply not used
   const bool fuse = ctx->fuse_keys && ctx->dense && !ctx->K.g2p2g;
-  int rc = ctx->dim == 3 ? enqueue_grid_g2p<3>(ctx, (float)dt, cur, s, nullptr, fuse)
-                         : enqueue_grid_g2p<2>(ctx, (float)dt, cur, s, nullptr, fuse);
+  int rc = ctx->dim == 3 ? enqueue_grid_g2p<3>(ctx, (float)dt, cur, s, ctx->cur_ev, fuse)
+                         : enqueue_grid_g2p<2>(ctx, (float)dt, cur, s, ctx->cur_ev, fuse);
   if (rc) return rc;
   ctx->batch_enq += 1;
   return MPM_OK;
@@ -1334,6 +1399,15 @@ extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
   CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const Status& h = *ctx->h_status;
+  if (ctx->prof_enq > 0 && !h.err) {   // per-phase device time, averaged over the batch
+    for (int i = 0; i < 4; ++i) ctx->ms[i] = 0.f;
+    for (int k = 0; k < ctx->prof_enq; ++k)
+      for (int i = 0; i < 4; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->ev[5 * k + i], ctx->ev[5 * k + i + 1]);
+        ctx->ms[i] += t / ctx->prof_enq;
+      }
+  }
   ctx->cur = ctx->batch_cur0 ^ (h.done & 1);
   ctx->done_last = h.done;
   if (h.done > 0) {
@@ -1443,13 +1517,25 @@ extern "C" int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t
   const bool fused = ctx->fused_halo && ctx->dim == 3 && ctx->p2g_ver == 3 && ctx->p2g_variant == 1 && ctx->dense &&
                      ctx->peer_plane_words && (int64_t)ctx->L.eb[1] * ctx->L.eb[2] <= ctx->comm.plane_blocks;
   if (fused) {
+    // per-phase CUDA events (mpm_set_profiling): "sort" then includes the wait for the neighbours' migration
+    // message, "grid" the wait for their halo
+    const bool prof = ctx->profiling && !deliver_only && ctx->prof_enq + n_iter <= 4096;
+    if (prof)
+      while ((int)ctx->ev.size() < 5 * (ctx->prof_enq + n_iter)) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->ev.push_back(e);
+      }
     for (int i = 0; i < n_iter; ++i) {
       ctx->comm.fused = 1;
       ctx->comm.epoch = ctx->epoch;
+      ctx->cur_ev = prof ? ctx->ev.data() + 5 * (ctx->prof_enq++) : nullptr;
+      if (ctx->cur_ev) cudaEventRecord(ctx->cur_ev[0], s);      // (re-recorded by the binning: the unpack wait counts as "sort")
       int rc = mpm_phase_unpack(ctx, mig_from[0], mig_from[1], stream);
       if (!rc && !deliver_only) rc = mpm_phase_p2g(ctx, dt, stream);
       if (!rc && !deliver_only) rc = mpm_phase_g2p(ctx, dt, stream);
       ctx->comm.fused = 0;
+      ctx->cur_ev = nullptr;
       if (rc) return rc;
       if (!deliver_only) ctx->epoch += 1;
     }
@@ -1537,38 +1623,6 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
   // rows whose id is not present (ids that are not a permutation of [0, n): the distributed solver's
   // global ids) read as zero instead of uninitialised memory
   CK(cudaMemsetAsync(dst_dev, 0, (size_t)(end - begin) * nwords * 4, (cudaStream_t)stream));
-  if (ctx->K.g2p2g && ctx->have_pending) {
-    // F and Jp were already advanced by the pending scatter half (see k_gather_rows_pending)
-    cudaStream_t s = (cudaStream_t)stream;
-    if (ctx->pending_rebuild) {
-      int rc = upload_colliders(ctx, s);
-      for (int attempt = 0; !rc && attempt < 3; ++attempt) {
-        rc = refresh_bbox(ctx, s);
-        if (!rc) rc = update_layout(ctx);
-        if (rc) break;
-        rc = rebuild_pending(ctx, s);
-        if (rc != MPM_E_INVALID) break;
-        rc = MPM_OK;
-      }
-      if (rc) return rc;
-    }
-    const int f_lo = ctx->dim == 3 ? Fld<3>::F : Fld<2>::F, dd = ctx->dim * ctx->dim;
-    const int jp = ctx->dim == 3 ? Fld<3>::JP : Fld<2>::JP;
-    // F occupies [f_lo, f_lo + dd), C the next dd words, then Jp: two advanced ranges
-    const int lo = first_field >= jp ? jp : f_lo, hi = first_field >= jp ? jp + 1 : f_lo + dd;
-    if (first_field < jp && first_field + nwords > f_lo + dd && first_field + nwords > jp)
-      return fail(ctx, MPM_E_INVALID, "mpm_gather_rows: a range may not span F and Jp in g2p2g mode");
-    if (ctx->dim == 3)
-      k_gather_rows_pending<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
-          ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->stat, first_field, nwords, lo, hi,
-          ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
-    else
-      k_gather_rows_pending<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(
-          ctx->state[ctx->cur], ctx->state[ctx->cur ^ 1], ctx->cur_perm, ctx->stat, first_field, nwords, lo, hi,
-          ctx->pending_n, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
-    CK(cudaGetLastError());
-    return MPM_OK;
-  }
   if (ctx->dim == 3)
     k_gather_rows<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
         ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev);

@@ -1006,51 +1006,6 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 }
 
 
-// g2p2g: particles that are not in the pending binning (added since, or all of them on the
-// first substep) skip the gather (engine/mpm_solver.py:396-399): v kept, C = 0, advected
-// unless STATIONARY; the row is copied to the same row of the other set.
-template <int D>
-__global__ void k_copy_advect(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t cap, int r0, int n,
-                              float dt, float inv_dx, Status* st) {
-  using FL = Fld<D>;
-  if (st->err) return;
-  float vmax = 0.0f;
-  for (int p = r0 + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const uint32_t tag = ldu<D>(src, FL::TAG, p), mat = tag_mat(tag);
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float v = ldf<D>(src, FL::V + d, p);
-      float x = ldf<D>(src, FL::X + d, p);
-      if (mat != (uint32_t)STATIONARY) x = __fadd_rn(x, __fmul_rn(dt, v));
-      stf<D>(dst, FL::X + d, p, x);
-      stf<D>(dst, FL::V + d, p, v);
-      vmax = fmaxf(vmax, fabsf(v));
-    }
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) {
-      stu<D>(dst, FL::F + i, p, ldu<D>(src, FL::F + i, p));
-      stf<D>(dst, FL::C + i, p, 0.0f);
-    }
-    stu<D>(dst, FL::JP, p, ldu<D>(src, FL::JP, p));
-    stu<D>(dst, FL::TAG, p, tag);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(&st->maxv_bits, __float_as_uint(vmax));
-}
-// end of the gather half of a g2p2g substep
-__global__ void k_half_commit(Status* st) {
-  if (st->err) return;
-  st->half += 1;
-  if (st->maxv_bits > st->maxv_all) st->maxv_all = st->maxv_bits;
-}
-// batch start in g2p2g mode: the pending scatter half's block structure stays valid
-__global__ void k_batch_begin_keep(Status* st, int n, int npb, int ngb, int n_static) {
-  st->n_cur = n; st->n_live = n; st->n_static = n_static;
-  st->npb = npb; st->ngb = ngb;
-  st->work_g2p = 0; st->maxv_bits = 0;
-}
-
 // ------------------------------------------------------------------ seeding
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -1420,27 +1375,6 @@ __global__ void k_pack_particles(const uint32_t* __restrict__ state, Statics sta
     color[(size_t)id * 3 + 0] = (uint8_t)((c >> 16) & 255u);
     color[(size_t)id * 3 + 1] = (uint8_t)((c >> 8) & 255u);
     color[(size_t)id * 3 + 2] = (uint8_t)(c & 255u);
-  }
-}
-
-// g2p2g with a pending scatter half: F and Jp of the binned particles have already been
-// advanced by that half and live in the other set at their sorted slots (row s <- perm[s]);
-// everything else, and particles added since, is read from the live set.
-template <int D>
-__global__ void k_gather_rows_pending(const uint32_t* __restrict__ live, const uint32_t* __restrict__ other,
-                                      const uint32_t* __restrict__ perm, Statics stat, int first, int nwords,
-                                      int f_lo, int f_hi, int n_binned, int n, int64_t begin, int64_t end,
-                                      uint32_t* __restrict__ out) {
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    const bool binned = s < (uint32_t)n_binned;
-    const uint32_t p = binned ? perm[s] : s;
-    const int64_t id = vword<D>(live, stat, Fld<D>::ID, p);
-    if (id < begin || id >= end) continue;
-    for (int w = 0; w < nwords; ++w) {
-      const int f = first + w;
-      const bool adv = binned && f >= f_lo && f < f_hi;     // F words and Jp are contiguous
-      out[(size_t)(id - begin) * nwords + w] = adv ? other[word<D>(f, s)] : vword<D>(live, stat, f, p);
-    }
   }
 }
 

@@ -20,7 +20,9 @@
 //     out of scatter work, off the critical path (double-buffered)
 // Barriers per block: 6, of which only two can see unbalanced arrivals.
 #pragma once
-#include "mpm_kernels.cuh"
+#include <type_traits>
+
+#include "mpm_fused.cuh"
 
 namespace mpm {
 
@@ -79,9 +81,16 @@ __device__ __forceinline__ void p2g3_publish_halo(const CommBufs& cb) {
 }
 
 // FUSED: the multi-GPU variant (fused halo); the single-device kernel carries none of its state.
-template <int CHUNK, int MINB, bool FUSED, bool DEFER>
-__global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
+__device__ __forceinline__ const SubstepArgs<3>& p2g3_args(const SubstepArgs<3>& a) { return a; }
+__device__ __forceinline__ const SubstepArgs<3>& p2g3_args(const FusedArgs<3>& a) { return a.s; }
+
+// G2P2G: the use_g2p2g fused kernel (mpm_g2p2g.cuh): the constitutive phase first gathers v and C from the INPUT grid
+// at the old position (an 8^3 node tile around the block, staged once per block) and advects; C stays in registers.
+template <int CHUNK, int MINB, bool FUSED, bool DEFER, bool G2P2G = false>
+__global__ void __launch_bounds__(P2G3::T, MINB)
+k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg) {
   constexpr int D = 3;
+  const SubstepArgs<3>& a = p2g3_args(arg);
   using G = Geo<3>;
   using FL = Fld<3>;
   constexpr int T = P2G3::T, CH = CHUNK, PS = P2G3::PS;
@@ -92,6 +101,9 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
   __shared__ int s_nbr[G::NO];
   __shared__ int s_b, s_next, s_ticket, s_ticket_q;
   __shared__ int s_hist[32];
+  __shared__ float4 s_gin[G2P2G ? 512 : 1];   // use_g2p2g: velocities of the INPUT grid, 8^3 nodes around the block
+  float vmax = 0.0f;                            // use_g2p2g: compute_max_velocity and the next bounding box
+  int bb_lo[3] = {INT_MAX, INT_MAX, INT_MAX}, bb_hi[3] = {INT_MIN, INT_MIN, INT_MIN};
   __shared__ unsigned short s_queue[(P2G3::T / 32) * ((CHUNK + P2G3::T - 1) / P2G3::T) * 32];   // per warp: deferred particles (chunk-relative index | material << 12)
   __shared__ int s_wn[P2G3::T / 32];             // entries in each warp's queue
   static_assert(CHUNK <= 4096, "queue entries hold a 12-bit index");
@@ -131,6 +143,24 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
     const int cnt = end - start;
     if (tid < G::NO) s_nbr[tid] = a.pb_nbr[b * G::NO + tid];
     const bool boundary = fused && qpos < n_bnd;            // fused halo: this block's tile touches a shared column
+    int org[3] = {0, 0, 0};                                 // use_g2p2g: absolute cell (offset by half) of the block origin
+    if constexpr (G2P2G) {
+      int rel[3];
+      key_to_rel<3>(a.L, a.pb_key[b], rel);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
+      for (int n = tid; n < 512; n += T) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (arg.grid_in) {
+          const int c[3] = {org[0] - 1 + (n >> 6), org[1] - 1 + ((n >> 3) & 7), org[2] - 1 + (n & 7)};
+          const int babs[3] = {c[0] >> 2, c[1] >> 2, c[2] >> 2};
+          const int slot = table_slot<3>(arg.tin, babs);
+          if (slot >= 0) g = arg.grid_in[(size_t)slot * G::CELLS + (((c[0] & 3) << 4) | ((c[1] & 3) << 2) | (c[2] & 3))];
+        }
+        s_gin[n] = g;
+      }
+      __syncthreads();
+    }
     const int* cs = s_cs[u];
     const int cell = s_order[u][tid / P2G3::SL];
     const int c_lo = cs[cell], c_hi = cs[cell + 1];
@@ -140,7 +170,73 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
     for (int c0 = 0; c0 < cnt; c0 += CH) {
       const int cn = min(CH, cnt - c0);
       const bool last = c0 + CH >= cnt;
-      if constexpr (!DEFER) {
+      if constexpr (G2P2G) {
+      // ---- phase 1 (use_g2p2g): G2P half at the old position, advection, P2G half at the new one (ref :376-483)
+      constexpr int NIT = (CH + T - 1) / T;
+      uint32_t pq[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
+#pragma unroll 1
+      for (int q = tid; q < cn; q += T) {
+        const int s = start + c0 + q;
+        const uint32_t p = pq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
+        float x[D], v[D], fx[D], C[D * D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          x[d] = ldf<D>(a.src, FL::X + d, p);
+          v[d] = ldf<D>(a.src, FL::V + d, p);
+        }
+        float F[D * D], aff[D * D], mass;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) F[i] = ldf<D>(a.src, FL::F + i, p);
+        float Jp = ldf<D>(a.src, FL::JP, p);
+        const uint32_t tag = ldu<D>(a.src, FL::TAG, p), mat = tag_mat(tag);
+        if ((int)p < arg.n_old) {
+          int l[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const int base = base_index(x[d], a.K.inv_dx);
+            fx[d] = __fsub_rn(__fmul_rn(x[d], a.K.inv_dx), (float)base);
+            l[d] = min(max(base + a.L.half - (org[d] - 1), 0), 5);
+          }
+          float nv[D];
+          gather_vC<D, true>(s_gin, 8, l, fx, a.K.four_inv_dx, nv, C);
+          if (mat != (uint32_t)STATIONARY) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = nv[d];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < D * D; ++i) C[i] = 0.0f;                                 // :396-399
+        }
+        if (mat != (uint32_t)STATIONARY) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, v[d]));  // :401-403
+        }
+        particle_update<D>(a.K, a.dt, (int)mat, F, C, Jp, aff, mass);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          stf<D>(a.dst, FL::X + d, s, x[d]);
+          stf<D>(a.dst, FL::V + d, s, v[d]);
+          vmax = fmaxf(vmax, fabsf(v[d]));
+          const int nb = base_index(x[d], a.K.inv_dx);
+          bb_lo[d] = min(bb_lo[d], nb); bb_hi[d] = max(bb_hi[d], nb);
+          fx[d] = x[d] * a.K.inv_dx - (float)nb;                                       // :409
+        }
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
+        stf<D>(a.dst, FL::JP, s, Jp);
+        stu<D>(a.dst, FL::TAG, s, tag);
+        const float dx = a.K.dx;
+        const int sw = (q >> 1) & 3;
+        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
+        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
+        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
+        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
+      }
+      } else if constexpr (!DEFER) {
       // ---- phase 1 (single pass): constitutive update (engine/mpm_solver.py:506-574), payload to shared memory
       constexpr int NIT = (CH + T - 1) / T;
       uint32_t pq[NIT];
@@ -419,6 +515,24 @@ __global__ void __launch_bounds__(P2G3::T, MINB) k_p2g3(SubstepArgs<3> a) {
         }
       }
       if (fused && last) qpos = q_next;
+    }
+  }
+  if constexpr (G2P2G) {      // compute_max_velocity (:726-735) and the next bounding box, once per CTA lifetime
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        bb_lo[d] = min(bb_lo[d], __shfl_xor_sync(0xffffffffu, bb_lo[d], o));
+        bb_hi[d] = max(bb_hi[d], __shfl_xor_sync(0xffffffffu, bb_hi[d], o));
+      }
+    }
+    if (lane == 0) {
+      if (vmax != vmax) vmax = __int_as_float(0x7f800000);
+      atomicMax(&a.st->maxv_bits, __float_as_uint(vmax));
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (bb_lo[d] <= bb_hi[d]) { atomicMin(&a.st->bb_min[d], bb_lo[d]); atomicMax(&a.st->bb_max[d], bb_hi[d]); }
     }
   }
 }

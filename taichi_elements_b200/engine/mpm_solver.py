@@ -280,6 +280,9 @@ class MPMSolver:
                 self._lib.mpm_get_state(self._ctx, ctypes.byref(cur), None)
                 cur_set = cur.value
             nbytes = self._lib.mpm_workspace_bytes(self.dim, cap, mb)
+            # use_g2p2g keeps the last substep's output grid and block table in the workspace: the old one must stay
+            # alive until mpm_bind has copied them over; otherwise it is released first (less peak memory)
+            old_ws = self._ws if self.use_g2p2g else None
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
             torch.cuda.synchronize(self._device)
@@ -287,6 +290,7 @@ class MPMSolver:
         self._check(
             self._lib.mpm_bind(self._ctx, self._state[0].data_ptr(), self._state[1].data_ptr(),
                                self._static.data_ptr(), cap, self._ws.data_ptr(), nbytes, mb), 'mpm_bind')
+        del old_ws
         self._check(self._lib.mpm_set_state(self._ctx, cur_set, self._n), 'mpm_set_state')
 
     def _reserve(self, new_particles):
