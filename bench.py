@@ -166,10 +166,11 @@ def substep_dt(w, default_dt):
     return w.get('dt', default_dt)
 
 
-# Relative cost of a particle-substep by material (WATER, ELASTIC, SNOW, SAND), measured on one B200 with the whole
-# configs[3] scene made of ONE material (MPM_BENCH_MATERIAL=k, profiles/README.md): the strong-scaling cuts give every
-# rank the same COST, not the same count (with equal counts the ranks that hold snow and sand set the pace).
-MATERIAL_COST = (1.0, 1.09, 1.21, 1.18)
+# Relative cost of a particle-substep by material (WATER, ELASTIC, SNOW, SAND) in the timed window of this scene, from
+# the per-rank phase times of a 4-GPU run with one material per rank (roofline.kernel_ms_per_rank: busy time per
+# particle 80 / 93 / 117 / 113 ps; profiles/README.md): the strong-scaling cuts give every rank the same COST, not
+# the same count (with equal counts the ranks that hold snow and sand set the pace).  The cuts are static.
+MATERIAL_COST = (1.0, 1.16, 1.46, 1.40)
 
 
 def rank_chunks(w, rank, world):

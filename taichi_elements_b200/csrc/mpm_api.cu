@@ -750,8 +750,8 @@ static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t 
   constexpr size_t smem = p2g3_smem_bytes<CH>();
   if (a.cb.fused) {          // multi-GPU: halo inside the kernel (mpm_comm.cuh)
     static LaunchCache lcf;
-    const int grid = cached_grid(lcf, ctx, k_p2g3<CH, MB, true, true>, P2G3::T, smem);
-    launch_chain(ctx->pdl, k_p2g3<CH, MB, true, true>, grid, P2G3::T, smem, s, a);
+    const int grid = cached_grid(lcf, ctx, k_p2g3<CH, MB, true, false>, P2G3::T, smem);
+    launch_chain(ctx->pdl, k_p2g3<CH, MB, true, false>, grid, P2G3::T, smem, s, a);
     return;
   }
   if (!ctx->defer_svd) {     // MPM_DEFER_SVD=0: single-pass constitutive phase (comparison)
@@ -931,10 +931,10 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     float4 *zp0 = nullptr, *zp1 = nullptr;
     int nzp = 0;
     if (ctx->comm.fused) {
-      const size_t off = (size_t)((ctx->comm.epoch + 1u) % 3u) * ctx->comm.plane_blocks * G::CELLS;
+      const size_t off = (size_t)((ctx->comm.epoch + 1u) % 3u) * ctx->comm.plane_blocks * HALO_SLAB;
       if (ctx->comm.plane_in[0]) zp0 = ctx->comm.plane_in[0] + off;
       if (ctx->comm.plane_in[1]) zp1 = ctx->comm.plane_in[1] + off;
-      nzp = D == 3 ? ctx->L.eb[1] * ctx->L.eb[2] * G::CELLS : 0;
+      nzp = D == 3 ? ctx->L.eb[1] * ctx->L.eb[2] * HALO_SLAB : 0;
     }
     CK(launch_chain(ctx->pdl, k_clear_grid<D>, gs_blocks((int64_t)ctx->max_blocks * G::CELLS, 256, sm), 256, 0, s,
                     ctx->grid, (const Status*)st, z1, n1, z2, n2, (int)G::CELLS, zp0, zp1, nzp));
@@ -1451,7 +1451,7 @@ extern "C" int mpm_peer_alloc(mpm_ctx* ctx, int32_t mig_cap, int32_t halo_cap) {
   if (ctx->peer_region) return fail(ctx, MPM_E_INVALID, "mpm_peer_alloc: already allocated");
   ctx->peer_mig_words = mpm_comm_bytes(ctx->dim, 0, mig_cap) / 4;
   ctx->peer_halo_words = mpm_comm_bytes(ctx->dim, 1, halo_cap) / 4;
-  ctx->peer_plane_words = ctx->dim == 3 ? (size_t)halo_cap * 64 * 4 : 0;
+  ctx->peer_plane_words = ctx->dim == 3 ? (size_t)halo_cap * HALO_SLAB * 4 : 0;
   const size_t words = 16 + 2 * ctx->peer_mig_words + 2 * ctx->peer_halo_words + 6 * ctx->peer_plane_words;
   // the one allocation this library owns: it has to be a whole cudaMalloc block to be exported over CUDA IPC
   CK(cudaMalloc((void**)&ctx->peer_region, words * 4));

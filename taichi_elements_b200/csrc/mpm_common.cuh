@@ -96,16 +96,19 @@ struct Slab {
 //   migration: header | field-major rows  [field][mig_cap]
 //   halo:      header | keys [halo_cap] | node records [halo_cap][CELLS] float4
 static constexpr int COMM_HEADER = 16;
+static constexpr int HALO_SLAB = 2 * 6 * 6;   // node records one boundary block sends (3D)
 struct CommBufs {
   uint32_t* mig[2];        // where leavers to the -x / +x rank are written: a local send buffer (NCCL
   uint32_t* halo[2];       //   path) or the neighbour's receive buffer mapped over NVLink (peer path)
   int mig_cap, halo_cap;
   uint32_t* flag_mig[2];   // peer path: the neighbour's "data ready" epoch words to release-store
   uint32_t* flag_halo[2];
-  // fused halo (peer path, 3D): the shared grid column travels inside P2G as vector reductions into a dense
-  // plane in the NEIGHBOUR's memory, indexed by the (y, z) block coordinates of the common key layout; three
-  // planes per side rotate with the substep epoch (one being filled, one being read, one being cleared)
-  float4* plane_out[2];    // neighbour's planes for what I send to the -x / +x side (3 * plane_blocks * 64 records)
+  // fused halo (peer path, 3D): the nodes of the grid column at a cut that both ranks scatter into are its first TWO
+  // cell layers.  Every boundary particle block stores its partial sums of them -- a slab of 2 x 6 x 6 node records
+  // of its tile -- with plain vector stores into a slot of a dense plane in the NEIGHBOUR's memory, indexed by the
+  // block's (y, z) coordinates in the common key layout (no remote atomics); the neighbour's grid op adds the <= 4
+  // slabs that overlap a node.  Three planes per side rotate with the substep epoch (filled / read / cleared).
+  float4* plane_out[2];    // neighbour's planes for what I send to the -x / +x side (3 * plane_blocks * HALO_SLAB)
   float4* plane_in[2];     // my planes, filled by the -x / +x neighbour
   const uint32_t* wait_mig[2];    // my epoch words, written by the neighbours
   const uint32_t* wait_halo[2];

@@ -540,7 +540,7 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
   const float4* pl_hi = nullptr;
   if (cb.fused) {
     cta_wait_epochs(cb.wait_halo[0], cb.wait_halo[1], cb.epoch + 1u, st);
-    const size_t off = (size_t)(cb.epoch % 3u) * cb.plane_blocks * G::CELLS;
+    const size_t off = (size_t)(cb.epoch % 3u) * cb.plane_blocks * HALO_SLAB;
     if (cb.plane_in[0]) pl_lo = cb.plane_in[0] + off;
     if (cb.plane_in[1]) pl_hi = cb.plane_in[1] + off;
   }
@@ -565,9 +565,18 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
       if (cb.fused) {
         const int col = rel[0] + L.ob[0];
         const float4* pl = col == slab.lo ? pl_lo : (col == slab.hi ? pl_hi : nullptr);
-        if (pl) {
-          const float4 h = pl[(size_t)(rel[1] * L.eb[2] + rel[2]) * G::CELLS + cell];
-          v[0] += h.x; v[1] += h.y; v[2] += h.z; m += h.w;
+        const int cx = cell >> 4, cy = (cell >> 2) & 3, cz = cell & 3;
+        if (pl && cx <= 1) {
+          // the neighbour's particle blocks (y - dy, z - dz) whose tiles cover this node: tile node (cy + 4 dy, cz + 4 dz)
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dz = 0; dz < 2; ++dz) {
+              if ((dy && cy > 1) || (dz && cz > 1) || rel[1] - dy < 0 || rel[2] - dz < 0) continue;
+              const float4 h = pl[(size_t)((rel[1] - dy) * L.eb[2] + (rel[2] - dz)) * HALO_SLAB + cx * 36 + (cy + 4 * dy) * 6 +
+                                  (cz + 4 * dz)];
+              v[0] += h.x; v[1] += h.y; v[2] += h.z; m += h.w;
+            }
         }
       }
     }

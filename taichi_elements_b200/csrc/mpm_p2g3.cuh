@@ -490,14 +490,13 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
             const int slot = s_nbr[oct];
             if (slot >= 0) red_add_v4(a.grid + (size_t)slot * G::CELLS + cellg, val);
             if (boundary) {
-              // a node of a grid column shared with a neighbour rank: the same partial sum also goes into that
-              // neighbour's halo plane (peer memory over NVLink); its grid op adds the plane to its own sums
-              const int col = hb_x + (oct & 1);
-              const int side = col == a.slab.hi ? 1 : (col == a.slab.lo ? 0 : -1);
+              // a node in the first two cell layers of a grid column shared with a neighbour rank: this block's
+              // partial sum also goes into its slot of that neighbour's halo plane (a plain store into peer memory
+              // over NVLink -- the slot belongs to this block alone); the neighbour's grid op adds the slabs
+              const int side = (hb_x == a.slab.hi - 1 && nx >= 4) ? 1 : ((hb_x == a.slab.lo && nx <= 1) ? 0 : -1);
               if (side >= 0 && a.cb.plane_out[side]) {
-                const int py = hb_y + ((oct >> 1) & 1), pz = hb_z + ((oct >> 2) & 1);
-                float4* plane = a.cb.plane_out[side] + (size_t)(a.cb.epoch % 3u) * a.cb.plane_blocks * G::CELLS;
-                red_add_v4(plane + (size_t)(py * a.L.eb[2] + pz) * G::CELLS + cellg, val);
+                float4* plane = a.cb.plane_out[side] + (size_t)(a.cb.epoch % 3u) * a.cb.plane_blocks * HALO_SLAB;
+                plane[(size_t)(hb_y * a.L.eb[2] + hb_z) * HALO_SLAB + (nx & 3) * 36 + ny * 6 + nz] = val;
               }
             }
           }
