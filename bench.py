@@ -96,7 +96,7 @@ def multimat(name, z_cells=232, chunks_per_material=4, y_cells=120.27, side_wall
 def brick(name, world=1, cells=(248, 252, 250)):
     """configs[4] / SURVEY 8(d) cfg 5: res 512 unbounded, one brick per GPU (248 x 252 x 250 cells x 8 = 124 992 000
     particles), WATER below SAND, bricks tiled along x (cuts on leaf-block boundaries carry halo and migration),
-    neighbouring bricks approach each other at +-0.25 m/s, all fall at 1 m/s onto a slip floor 2 cells below."""
+    all fall at 1 m/s onto a slip floor 2 cells below (every brick does the same work as the single one at N = 1)."""
     res, dx = 512, 1.0 / 512
     cx, cy, cz = cells
     x0 = -cx * world // 2
@@ -104,7 +104,7 @@ def brick(name, world=1, cells=(248, 252, 250)):
     y0 = 2.0
     chunks = []
     for r in range(world):
-        vel = (0.25 if r % 2 == 0 else -0.25, -1.0, 0.0)
+        vel = (0.0, -1.0, 0.0)
         for h, mat in enumerate((WATER, SAND)):
             lo = (x0 + cx * r + 0.5, y0 + h * cy / 2, -cz / 2 + 0.5)
             hi = (x0 + cx * (r + 1) + 0.5, y0 + (h + 1) * cy / 2, cz / 2 + 0.5)

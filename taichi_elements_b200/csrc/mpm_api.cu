@@ -41,13 +41,14 @@ struct mpm_ctx {
   unsigned long long* scan_desc = nullptr;   // tile descriptors of k_scan_excl
   size_t scan_tiles = 0;
   uint32_t scan_epoch = 0;
-  int own_scan = 1, scan_grid = 0;
+  int own_scan = 1, scan_grid = 0, scan2_force = 0;   // MPM_SCAN=two: always the two-level bucket scan (tests)
   size_t cub_bytes = 0;
   int* pb_start = nullptr;
   uint32_t* pb_mask = nullptr;
   int* pb_nbr = nullptr;
   uint32_t *cand_a = nullptr, *cand_b = nullptr, *gb_key = nullptr, *pb_key = nullptr;
   int *flags = nullptr, *fscan = nullptr, *cellcount = nullptr, *cellstart = nullptr;
+  int *blocksum = nullptr, *blockstart = nullptr;   // two-level bucket scan (large block counts)
   int64_t table_cap = 0;
   bool dense = false;   // counting-sort path usable for the current layout
   Slab slab{0, INT_MIN, INT_MAX};
@@ -56,7 +57,6 @@ struct mpm_ctx {
   uint32_t* peer_region = nullptr;     // cudaMalloc'ed by mpm_peer_alloc: flags + the four receive buffers
   size_t peer_mig_words = 0, peer_halo_words = 0, peer_plane_words = 0;   // plane: one of the 3 rotating halo planes of a side
   int fused_fast = 1;                  // use_g2p2g, 3D: cell-owner fused kernel (MPM_G2P2G=simple: general kernel)
-  int defer_svd = 0;                   // MPM_DEFER_SVD=0: SVD inline in the first pass of k_p2g3
   int fused_halo = 1;                  // MPM_FUSED_HALO=0: legacy pack / wait / add kernels on the peer path
   void* peer_open[2] = {nullptr, nullptr};
   uint32_t epoch = 0;                  // substeps completed since mpm_peer_alloc (same on every rank)
@@ -161,7 +161,7 @@ static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, in
 struct Carve {
   size_t off_status, off_ct, off_scratch, off_cub, off_pb_start, off_pb_mask, off_pb_nbr, off_cand_a,
       off_cand_b, off_gb_key, off_grid, off_pb_key, off_flags, off_fscan, off_cellcount, off_cellstart, off_scan_desc, total,
-      off_pb_start2, off_pb_nbr2, off_grid2, off_pb_key2, off_flags2, off_fscan2,
+      off_pb_start2, off_pb_nbr2, off_grid2, off_pb_key2, off_flags2, off_fscan2, off_blocksum, off_blockstart,
       cub_bytes, scan_tiles;
   int64_t table_cap;
 };
@@ -219,6 +219,8 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
   c.off_pb_key2 = take((size_t)max_blocks * 4);
   c.off_flags2 = take((size_t)c.table_cap * 4);
   c.off_fscan2 = take((size_t)c.table_cap * 4);
+  c.off_blocksum = take((size_t)(max_blocks + 2) * 4);
+  c.off_blockstart = take((size_t)(max_blocks + 2) * 4);
   c.off_cellcount = take(((size_t)max_blocks * cells + 1) * 4);
   c.off_cellstart = take(((size_t)max_blocks * cells + 1) * 4);
   c.total = o;
@@ -293,9 +295,8 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
   if (const char* v = getenv("MPM_FUSED_HALO")) ctx->fused_halo = atoi(v);
-  if (const char* v = getenv("MPM_DEFER_SVD")) ctx->defer_svd = atoi(v);
   if (const char* v = getenv("MPM_G2P2G")) ctx->fused_fast = strcmp(v, "simple") != 0;
-  if (const char* v = getenv("MPM_SCAN")) ctx->own_scan = strcmp(v, "cub") != 0;
+  if (const char* v = getenv("MPM_SCAN")) { ctx->own_scan = strcmp(v, "cub") != 0; ctx->scan2_force = strcmp(v, "two") == 0; }
   {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_excl<true>, SCAN_T, 0);
@@ -374,6 +375,8 @@ extern "C" int mpm_bind(mpm_ctx* ctx, void* s0, void* s1, void* statics, int64_t
   ctx->pb_key = (uint32_t*)(b + c.off_pb_key);
   ctx->flags = (int*)(b + c.off_flags);
   ctx->fscan = (int*)(b + c.off_fscan);
+  ctx->blocksum = (int*)(b + c.off_blocksum);
+  ctx->blockstart = (int*)(b + c.off_blockstart);
   ctx->cellcount = (int*)(b + c.off_cellcount);
   ctx->cellstart = (int*)(b + c.off_cellstart);
   ctx->table_cap = c.table_cap;
@@ -750,19 +753,13 @@ static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t 
   constexpr size_t smem = p2g3_smem_bytes<CH>();
   if (a.cb.fused) {          // multi-GPU: halo inside the kernel (mpm_comm.cuh)
     static LaunchCache lcf;
-    const int grid = cached_grid(lcf, ctx, k_p2g3<CH, MB, true, false>, P2G3::T, smem);
-    launch_chain(ctx->pdl, k_p2g3<CH, MB, true, false>, grid, P2G3::T, smem, s, a);
-    return;
-  }
-  if (!ctx->defer_svd) {     // MPM_DEFER_SVD=0: single-pass constitutive phase (comparison)
-    static LaunchCache lcn;
-    const int grid = cached_grid(lcn, ctx, k_p2g3<CH, MB, false, false>, P2G3::T, smem);
-    launch_chain(ctx->pdl, k_p2g3<CH, MB, false, false>, grid, P2G3::T, smem, s, a);
+    const int grid = cached_grid(lcf, ctx, k_p2g3<CH, MB, true>, P2G3::T, smem);
+    launch_chain(ctx->pdl, k_p2g3<CH, MB, true>, grid, P2G3::T, smem, s, a);
     return;
   }
   static LaunchCache lc;
-  const int grid = cached_grid(lc, ctx, k_p2g3<CH, MB, false, true>, P2G3::T, smem);
-  launch_chain(ctx->pdl, k_p2g3<CH, MB, false, true>, grid, P2G3::T, smem, s, a);
+  const int grid = cached_grid(lc, ctx, k_p2g3<CH, MB, false>, P2G3::T, smem);
+  launch_chain(ctx->pdl, k_p2g3<CH, MB, false>, grid, P2G3::T, smem, s, a);
 }
 template <int D>
 static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
@@ -821,7 +818,6 @@ static SubstepArgs<D> make_args(mpm_ctx* ctx, float dt, int cur) {
   a.slab = ctx->slab; a.cb = ctx->comm; a.stat = ctx->stat;
   a.n_rows = (int)ctx->n;
   a.pf_mode = ctx->pf_mode;
-  a.defer_svd = ctx->defer_svd;
   return a;
 }
 
@@ -840,6 +836,24 @@ static int enqueue_scan(mpm_ctx* ctx, const int* in, int* out, int n, bool commi
   if (commit) CK(launch_chain(ctx->pdl, k_substep_begin, 1, 1, 0, s, ctx->d_status));
   size_t tb = ctx->cub_bytes;
   CK(cub::DeviceScan::ExclusiveSum(ctx->cub_temp, tb, in, out, n, s));
+  return MPM_OK;
+}
+
+// bucket starts from the per-cell counts of the npb = fscan[nlin] existing particle blocks
+template <int D>
+static int enqueue_cell_scan(mpm_ctx* ctx, int nlin, cudaStream_t s) {
+  using G = Geo<D>;
+  const int ncell = ctx->max_blocks * G::CELLS + 1;
+  if (!ctx->own_scan || (ncell <= 256 * SCAN_TILE && !ctx->scan2_force))   // one look-back chain (or MPM_SCAN=cub)
+    return enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s, ctx->fscan + nlin, G::CELLS);
+  const int blocks = gs_blocks((int64_t)ctx->max_blocks * 32, 256, ctx->sm_count);
+  CK(launch_chain(ctx->pdl, k_cell_sums<D>, blocks, 256, 0, s, (const int*)ctx->cellcount, (const int*)(ctx->fscan + nlin),
+                  ctx->blocksum, (const Status*)ctx->d_status));
+  int rc = enqueue_scan(ctx, ctx->blocksum, ctx->blockstart, ctx->max_blocks + 1, false, s, ctx->fscan + nlin, 1);
+  if (rc) return rc;
+  CK(launch_chain(ctx->pdl, k_cell_starts<D>, blocks, 256, 0, s, (const int*)ctx->cellcount, (const int*)(ctx->fscan + nlin),
+                  (const int*)ctx->blockstart, ctx->cellstart, (const Status*)ctx->d_status));
+  ctx->launches += 2;
   return MPM_OK;
 }
 
@@ -876,7 +890,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
                     ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
     // (only the cells of the npb = fscan[nlin] existing blocks: the table is sized by capacity)
-    { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s, ctx->fscan + nlin, G::CELLS); if (rc) return rc; }
+    { int rc = enqueue_cell_scan<D>(ctx, nlin, s); if (rc) return rc; }
     CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
                     ctx->fscan, ctx->cellstart, ctx->vals_b, st));
     CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
@@ -1025,7 +1039,7 @@ static int enqueue_fused_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s
   { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, false, s); if (rc) return rc; }
   CK(launch_chain(ctx->pdl, k_bin_rank<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->fscan,
                   ctx->cellcount, ctx->vals_a, ctx->pb_key, ctx->max_blocks, st));
-  { int rc = enqueue_scan(ctx, ctx->cellcount, ctx->cellstart, ncell, false, s, ctx->fscan + nlin, G::CELLS); if (rc) return rc; }
+  { int rc = enqueue_cell_scan<D>(ctx, nlin, s); if (rc) return rc; }
   CK(launch_chain(ctx->pdl, k_bin_scatter<D>, gs_blocks((n + 3) / 4, 256, sm), 256, 0, s, ctx->keys_a, ctx->vals_a,
                   ctx->fscan, ctx->cellstart, ctx->vals_b, st));
   CK(launch_chain(ctx->pdl, k_bin_finish<D>, gs_blocks((int64_t)ctx->max_blocks * G::NO, 256, sm), 256, 0, s,
@@ -1043,8 +1057,8 @@ static int enqueue_fused_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s
     if (ctx->fused_fast) {     // cell-owner scatter (mpm_p2g3.cuh); MPM_G2P2G=simple selects the general kernel
       static LaunchCache lc;
       constexpr size_t smem = p2g3_smem_bytes<640>();
-      const int grid = cached_grid(lc, ctx, k_p2g3<640, 3, false, false, true>, P2G3::T, smem);
-      CK(launch_chain(ctx->pdl, k_p2g3<640, 3, false, false, true>, grid, P2G3::T, smem, s, fa));
+      const int grid = cached_grid(lc, ctx, k_p2g3<640, 3, false, true>, P2G3::T, smem);
+      CK(launch_chain(ctx->pdl, k_p2g3<640, 3, false, true>, grid, P2G3::T, smem, s, fa));
       fast = true;
     }
   }

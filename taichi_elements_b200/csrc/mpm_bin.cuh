@@ -264,6 +264,51 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
   }
 }
 
+// Bucket starts for tables too long for one look-back chain (> 256 tiles: the prefix of k_scan_excl travels one
+// 32-tile window per hop): two levels, all own kernels.  k_cell_sums: particles per particle block (one warp per
+// block); k_scan_excl over those <= max_blocks sums; k_cell_starts: exclusive scan inside each block + its offset.
+template <int D>
+__global__ void k_cell_sums(const int* __restrict__ cellcount, const int* __restrict__ npb_dev, int* __restrict__ blocksum,
+                            const Status* st) {
+  using G = Geo<D>;
+  pdl_enter();
+  if (st->err) return;
+  const int npb = *npb_dev, lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b <= npb; b += nwarp) {
+    int s = 0;
+    if (b < npb)
+      for (int c = lane; c < G::CELLS; c += 32) s += cellcount[(size_t)b * G::CELLS + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) blocksum[b] = s;                     // (entry npb = 0: the scan's last output is the total)
+  }
+}
+template <int D>
+__global__ void k_cell_starts(const int* __restrict__ cellcount, const int* __restrict__ npb_dev,
+                              const int* __restrict__ blockstart, int* __restrict__ cellstart, const Status* st) {
+  using G = Geo<D>;
+  pdl_enter();
+  if (st->err) return;
+  const int npb = *npb_dev, lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b <= npb; b += nwarp) {
+    int run = blockstart[b];
+    if (b == npb) { if (lane == 0) cellstart[(size_t)npb * G::CELLS] = run; continue; }
+    for (int c0 = 0; c0 < G::CELLS; c0 += 32) {
+      const int v = cellcount[(size_t)b * G::CELLS + c0 + lane];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      cellstart[(size_t)b * G::CELLS + c0 + lane] = run + incl - v;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
 template <int D>
 __global__ void k_bin_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
                               const int* __restrict__ fscan, const int* __restrict__ cellstart,

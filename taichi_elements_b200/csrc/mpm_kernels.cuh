@@ -406,7 +406,6 @@ template <int D> struct SubstepArgs {
   int* next_flags;      //   (same key layout, see mpm_bin.cuh); saves the k_bin_keys pass
   int next_nlin;
   int pf_mode;    // next-block L2 prefetch: 0 off, 1 one prefetch per 128 B, 2 bulk range prefetch, 3 one per 32 B
-  int defer_svd;  // k_p2g3: particles that need the SVD run in a second, compacted pass (MPM_DEFER_SVD)
   int n_rows;     // g2p2g: rows of the live set (rows >= pb_start[npb] were added after the binning)
   Statics stat;   // static side arrays (G2P reads them for the particles it hands to a neighbour rank)
   Slab slab;      // multi-GPU: this rank's block columns (mpm_comm.cuh)

@@ -86,7 +86,7 @@ __device__ __forceinline__ const SubstepArgs<3>& p2g3_args(const FusedArgs<3>& a
 
 // G2P2G: the use_g2p2g fused kernel (mpm_g2p2g.cuh): the constitutive phase first gathers v and C from the INPUT grid
 // at the old position (an 8^3 node tile around the block, staged once per block) and advects; C stays in registers.
-template <int CHUNK, int MINB, bool FUSED, bool DEFER, bool G2P2G = false>
+template <int CHUNK, int MINB, bool FUSED, bool G2P2G = false>
 __global__ void __launch_bounds__(P2G3::T, MINB)
 k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg) {
   constexpr int D = 3;
@@ -104,9 +104,6 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
   __shared__ float4 s_gin[G2P2G ? 512 : 1];   // use_g2p2g: velocities of the INPUT grid, 8^3 nodes around the block
   float vmax = 0.0f;                            // use_g2p2g: compute_max_velocity and the next bounding box
   int bb_lo[3] = {INT_MAX, INT_MAX, INT_MAX}, bb_hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-  __shared__ unsigned short s_queue[(P2G3::T / 32) * ((CHUNK + P2G3::T - 1) / P2G3::T) * 32];   // per warp: deferred particles (chunk-relative index | material << 12)
-  __shared__ int s_wn[P2G3::T / 32];             // entries in each warp's queue
-  static_assert(CHUNK <= 4096, "queue entries hold a 12-bit index");
   pdl_enter();
   const int tid = threadIdx.x, lane = tid & 31;
   constexpr bool fused = FUSED;
@@ -126,7 +123,6 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
               k0 = sl == 0 ? 1.125f : (sl == 1 ? -0.25f : 0.125f);
 
   if (tid == 0) { s_b = atomicAdd(&a.st->work_p2g, 1); s_ticket = 0; }
-  if (tid < P2G3::T / 32) s_wn[tid] = 0;
   __syncthreads();
   int qpos = s_b;                                           // position in the work queue
   int b = qpos < npb ? p2g3_block_of(qpos, npb, n_bhi) : npb;
@@ -236,7 +232,7 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
         pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
       }
-      } else if constexpr (!DEFER) {
+      } else {
       // ---- phase 1 (single pass): constitutive update (engine/mpm_solver.py:506-574), payload to shared memory
       constexpr int NIT = (CH + T - 1) / T;
       uint32_t pq[NIT];
@@ -271,93 +267,6 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
         const float dx = a.K.dx;                                       // dpos = (o - fx) * dx
         const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
-        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
-        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
-        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
-        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
-      }
-      } else {
-      // ---- phase 1: constitutive update (engine/mpm_solver.py:506-574), payload to shared memory.
-      // Pass a: every particle; the cases that need no SVD (water, elastic, snow inside its clamp interval,
-      // expanding sand: mpm_math.cuh) finish here.  The others park their trial F, Jp, v and fx in their own
-      // (still unused) payload slot and join their WARP's queue; pass b runs that queue COMPACTED (a warp owns ~107 of
-      // the 640 particles of a chunk), so the lanes are all on the ~1500-instruction SVD path instead of a few lanes
-      // dragging 32 through it in every iteration -- with no CTA barrier between the passes.
-      constexpr int NIT = (CH + T - 1) / T;
-      uint32_t pq[NIT];
-#pragma unroll
-      for (int k = 0; k < NIT; ++k) pq[k] = (tid + k * T < cn) ? a.perm[start + c0 + tid + k * T] : 0u;
-      unsigned short* wq = s_queue + (tid >> 5) * (NIT * 32);
-      int* wn = &s_wn[tid >> 5];
-#pragma unroll 1
-      for (int q = tid; q < cn; q += T) {
-        const int s = start + c0 + q;
-        const uint32_t p = pq[0];
-#pragma unroll
-        for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
-        float x[D], v[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          x[d] = ldf<D>(a.src, FL::X + d, p);
-          v[d] = ldf<D>(a.src, FL::V + d, p);
-        }
-        float F[D * D], C[D * D], aff[D * D], mass;
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) {
-          F[i] = ldf<D>(a.src, FL::F + i, p);
-          C[i] = ldf<D>(a.src, FL::C + i, p);
-        }
-        float Jp = ldf<D>(a.src, FL::JP, p);
-        const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
-        float Fn[D * D];
-        trial_F<D>(a.K, a.dt, mat, F, C, Jp, Fn);
-        const bool done = particle_update_fast<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
-        if (done) {
-#pragma unroll
-          for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, Fn[i]);
-          stf<D>(a.dst, FL::JP, s, Jp);
-        }
-        float fx[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
-        const float dx = a.K.dx;                                       // dpos = (o - fx) * dx
-        const int sw = (q >> 1) & 3;                                  // 16-byte columns rotated: conflict-free STS.128
-        pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
-        pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
-        pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);
-        pay[q * PS + (3 ^ sw)] = make_float4(aff[2] * dx, aff[5] * dx, aff[8] * dx, fx[2]);
-        if (!done) {                                                   // rare: park the inputs of the SVD path instead
-          pay[q * PS + (0 ^ sw)] = make_float4(Fn[0], Fn[1], Fn[2], Fn[3]);
-          pay[q * PS + (1 ^ sw)] = make_float4(Fn[4], Fn[5], Fn[6], Fn[7]);
-          pay[q * PS + (2 ^ sw)] = make_float4(Fn[8], Jp, v[0], v[1]);
-          pay[q * PS + (3 ^ sw)] = make_float4(v[2], fx[0], fx[1], fx[2]);
-          wq[atomicAdd(wn, 1)] = (unsigned short)(q | (mat << 12));
-        }
-      }
-      __syncwarp();                                                     // this warp's queue and stashes are visible
-      const int nq = *wn;
-      __syncwarp();
-      if (lane == 0) *wn = 0;
-#pragma unroll 1
-      for (int i = lane; i < nq; i += 32) {
-        const unsigned e = wq[i];
-        const int q = (int)(e & 0xfffu), mat = (int)(e >> 12);
-        const int s = start + c0 + q;
-        const uint32_t p = a.perm[s];
-        const int sw = (q >> 1) & 3;
-        const float4 s0 = pay[q * PS + (0 ^ sw)], s1 = pay[q * PS + (1 ^ sw)], s2 = pay[q * PS + (2 ^ sw)],
-                     s3 = pay[q * PS + (3 ^ sw)];
-        float Fn[D * D] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x};
-        float Jp = s2.y;
-        const float v[D] = {s2.z, s2.w, s3.x}, fx[D] = {s3.y, s3.z, s3.w};
-        float C[D * D], aff[D * D], mass;
-#pragma unroll
-        for (int k = 0; k < D * D; ++k) C[k] = ldf<D>(a.src, FL::C + k, p);
-        particle_update_svd<D>(a.K, a.dt, mat, Fn, C, Jp, aff, mass);
-#pragma unroll
-        for (int k = 0; k < D * D; ++k) stf<D>(a.dst, FL::F + k, s, Fn[k]);
-        stf<D>(a.dst, FL::JP, s, Jp);
-        const float dx = a.K.dx;
         pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
         pay[q * PS + (1 ^ sw)] = make_float4(aff[0] * dx, aff[3] * dx, aff[6] * dx, fx[0]);
         pay[q * PS + (2 ^ sw)] = make_float4(aff[1] * dx, aff[4] * dx, aff[7] * dx, fx[1]);

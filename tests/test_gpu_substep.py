@@ -150,7 +150,7 @@ def test_kernel_variants_agree():
     block structure, same physics."""
     base = _run_variant({}, 'default')
     for tag, env in (('radix', {'MPM_SORT': 'radix'}), ('p2g2', {'MPM_P2G_VER': '2'}),
-                     ('atomic', {'MPM_P2G': 'atomic'})):
+                     ('atomic', {'MPM_P2G': 'atomic'}), ('scan2', {'MPM_SCAN': 'two'}), ('scancub', {'MPM_SCAN': 'cub'})):
         alt = _run_variant(env, tag)
         assert np.array_equal(base['pb'], alt['pb']) and np.array_equal(base['gb'], alt['gb'])
         assert np.array_equal(base['cnt'], alt['cnt'])

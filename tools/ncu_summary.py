@@ -16,9 +16,9 @@ KEYS = [
     'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
 ]
-rows = list(csv.reader(open(sys.argv[1])))
+rows = list(csv.reader(open(sys.argv[1]))) if '--traffic' not in sys.argv else [[], []]
 h, units = rows[0], rows[1]
-kn = h.index('Kernel Name')
+kn = h.index('Kernel Name') if h else 0
 seen = set()
 for r in rows[2:]:
     name = r[kn]
@@ -40,3 +40,28 @@ for r in rows[2:]:
                 pass
     stalls.sort(reverse=True)
     print('\nTop stalls (warps per issue-active cycle): ' + ', '.join(f'{n} {v:.2f}' for v, n in stalls[:6]) + '\n')
+
+
+def traffic_entry(csv_path, workload, source, out_path):
+    """profiles/traffic.json: dram bytes per launch of each captured kernel (bench.py's roofline.traffic).
+    NOTE: captured on `workload`; bench.py scales it to its own particle count when the scene is the same."""
+    import json
+    import os
+    rows = list(csv.reader(open(csv_path)))
+    h = rows[0]
+    kn, ir, iw = h.index('Kernel Name'), h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
+    units = rows[1]
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    data = json.load(open(out_path)) if os.path.exists(out_path) else {}
+    entry = data.setdefault(workload, {})
+    for r in rows[2:]:
+        name = r[kn].split('<')[0].replace('void ', '').replace('mpm::', '')
+        if name in entry:
+            continue
+        entry[name] = {'dram_bytes': float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]], 'source': source}
+    json.dump(data, open(out_path, 'w'), indent=1)
+
+
+if '--traffic' in sys.argv:
+    i = sys.argv.index('--traffic')
+    traffic_entry(sys.argv[1], sys.argv[i + 1], sys.argv[i + 2], sys.argv[i + 3])
