@@ -65,7 +65,8 @@ typedef struct mpm_params {
   int32_t padding;         /* :52 */
   int32_t support_plasticity;
   int32_t device;          /* CUDA device ordinal */
-  int32_t flags;           /* bit 0: use_g2p2g (:57), bit 1: quant (F clamp in g2p2g, :99, 415-416) */
+  int32_t flags;           /* bit 0: use_g2p2g (:57), bit 1: quant (F clamp in g2p2g, :99, 415-416; with bit 0 in 3D also
+                            * the bit-packed storage, see mpm_ctx_state_fields) */
   double dx, inv_dx;       /* :82-83 */
   double p_vol, p_mass;    /* :85-87 */
   double mu_0, lambda_0;   /* :203-205 */
@@ -108,6 +109,11 @@ int mpm_abi_version(void);
 int mpm_state_fields(int dim);
 /* words of the read-back numbering (2*dim + 2*dim*dim + 5) */
 int mpm_virtual_fields(int dim);
+/* physical words per particle of THIS context: mpm_state_fields(dim), or 11 with the bit-packed storage of quant=True
+ * (flags bits 0 and 1, dim 3; engine/mpm_solver.py:106-114, 216-247):  xq[2] vq[2] Fq[5] Jp tag
+ *   x  3 x 21-bit signed fixed point, range +-2.0; v  3 x 19-bit fractions sharing a 7-bit exponent;
+ *   F  9 x 16-bit signed fixed point, range +-4.1 (csrc/mpm_quant.cuh).  C does not exist in that mode. */
+int mpm_ctx_state_fields(mpm_ctx* ctx);
 /* bytes the workspace must have for `capacity` particles and `max_blocks` leaf blocks */
 size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks);
 

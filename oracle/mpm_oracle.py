@@ -192,6 +192,10 @@ class OracleMPM:
         self.grid_m = None
         self.grid_v = None
 
+    def _packed(self):
+        """Bit-packed x / v / F storage: quant=True in 3D (:106-114, 216-247); only built for the g2p2g mode here."""
+        return bool(self.quant and self.use_g2p2g and self.dim == 3)
+
     @property
     def n_particles(self):
         return self.x.shape[0]
@@ -216,6 +220,9 @@ class OracleMPM:
         self.material = np.concatenate(
             [self.material, np.full(n, material, np.int32)])
         self.color = np.concatenate([self.color, np.full(n, color, np.int32)])
+        if self._packed():
+            from .quant_oracle import round_v, round_x
+            self.x, self.v = round_x(self.x), round_v(self.v)
 
     def add_sphere_collider(self, center, radius, surface=SURFACE_STICKY):
         self.colliders.append(Collider('sphere', center=list(center),
@@ -315,6 +322,9 @@ class OracleMPM:
         F = _mm((I[None] + dt * C).astype(f32), F)                # :513
         if g2p2g and self.quant:                                  # [g2p2g] :415-416
             F = np.maximum(f32(-self.F_bound), np.minimum(f32(self.F_bound), F)).astype(f32)
+            if self._packed():                                    # self.F[p] = new_F rounds to the 16-bit grid (:416)
+                from .quant_oracle import round_F
+                F = round_F(F, self.F_bound)
         h = np.ones(n, f32)                                       # :515-521
         if self.support_plasticity:
             with np.errstate(over='ignore'):
@@ -560,9 +570,16 @@ class OracleMPM:
         new_v[~old] = self.v[~old]
         mov = self.material != MATERIAL_STATIONARY                # :401-403
         self.v = np.where(mov[:, None], new_v, self.v).astype(f32)
+        if self._packed():                                        # quantised fields (:106-114): a store rounds
+            from .quant_oracle import round_v, round_x, round_F
+            self.v = round_v(self.v)
         self.x = np.where(mov[:, None], self.x + dtf * self.v, self.x).astype(f32)
+        if self._packed():
+            self.x = round_x(self.x)
         self.C = C                                                # a register value in the reference (:385)
         self.p2g(dt, g2p2g=True)
+        if self._packed():
+            self.F = round_F(self.F, self.F_bound)                # the final store of F (:445, 466)
         self.last_time_final_particles = n                        # :485
         self.grid_op(dt, self.t)
         self.t += float(dt)

@@ -70,6 +70,7 @@ SYMBOLS = [
     ('mpm_destroy', _i32, [_vp]),
     ('mpm_last_error', ctypes.c_char_p, [_vp]),
     ('mpm_virtual_fields', _i32, [_i32]),
+    ('mpm_ctx_state_fields', _i32, [_vp]),
     ('mpm_bind', _i32, [_vp, _vp, _vp, _vp, _i64, _vp, ctypes.c_size_t, _i32]),
     ('mpm_get_static_rows', _i32, [_vp, ctypes.POINTER(_i64)]),
     ('mpm_set_static_rows', _i32, [_vp, _i64]),

@@ -29,6 +29,7 @@ struct mpm_ctx {
   Statics stat{nullptr, nullptr, nullptr};   // static side arrays [3][cap]: colour, id, emitter by sid
   int64_t n_static = 0;                       // rows of them in use
   int nv = 0;                                 // virtual words of the read-back numbering (Fld::NV)
+  int quant = 0;                              // packed x / v / F storage (quant=True with use_g2p2g, 3D; mpm_quant.cuh)
   size_t cap = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -229,6 +230,7 @@ static Carve carve(int dim, int64_t cap, int32_t max_blocks) {
 
 extern "C" int mpm_abi_version(void) { return MPM_ABI_VERSION; }
 extern "C" int mpm_state_fields(int dim) { return dim == 3 ? Geo<3>::NF : (dim == 2 ? Geo<2>::NF : -1); }
+extern "C" int mpm_ctx_state_fields(mpm_ctx* ctx) { return ctx ? ctx->nf : -1; }
 extern "C" int mpm_virtual_fields(int dim) { return dim == 3 ? Fld<3>::NV : (dim == 2 ? Fld<2>::NV : -1); }
 extern "C" size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks) {
   if ((dim != 2 && dim != 3) || capacity < 0 || max_blocks < 1) return 0;
@@ -243,7 +245,8 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   mpm_ctx* ctx = new mpm_ctx();
   ctx->P = *p;
   ctx->dim = p->dim;
-  ctx->nf = mpm_state_fields(p->dim);
+  ctx->quant = ((p->flags & 2) && (p->flags & 1) && p->dim == 3) ? 1 : 0;
+  ctx->nf = ctx->quant ? FldQ3::N : mpm_state_fields(p->dim);
   ctx->nv = p->dim == 3 ? Fld<3>::NV : Fld<2>::NV;
   ctx->cells = p->dim == 3 ? 64 : 256;
   ctx->no = p->dim == 3 ? 8 : 4;
@@ -444,8 +447,8 @@ extern "C" int mpm_compact_statics(mpm_ctx* ctx, void* stream) {
     uint32_t* tmp = ctx->state[ctx->cur ^ 1];
     const int blocks = gs_blocks(n, 256, ctx->sm_count);
     for (int pass = 0; pass < 2; ++pass) {
-      if (ctx->dim == 3) k_compact_statics<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass);
-      else k_compact_statics<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass);
+      if (ctx->dim == 3) k_compact_statics<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass, ctx->quant);
+      else k_compact_statics<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, n, tmp, pass, 0);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
@@ -488,7 +491,7 @@ static int seed_common(mpm_ctx* ctx, SeedArgs& a, void* stream) {
   a.cap = ctx->cap;
   a.n0 = ctx->n;
   if (a.id_base < 0) a.id_base = ctx->n;
-  a.stat = ctx->stat; a.sid0 = ctx->n_static;
+  a.stat = ctx->stat; a.sid0 = ctx->n_static; a.quant = ctx->quant;
   if ((size_t)(ctx->n_static + a.n) > ctx->cap) return fail(ctx, MPM_E_INVALID, "seed: static rows exceed the capacity (compact first)");
   int blocks = gs_blocks(a.n, 256, ctx->sm_count);
   // A large array of external positions is stored sorted by leaf block (ids keep the insertion order): the
@@ -604,8 +607,8 @@ extern "C" int mpm_export_local(mpm_ctx* ctx, void* out_dev, int64_t* count_out,
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->stage);
   CK(cudaMemsetAsync(cnt, 0, 8, s));
   const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count), half = ctx->P.grid_size / 2;
-  if (ctx->dim == 3) k_export_local<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
-  else k_export_local<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt);
+  if (ctx->dim == 3) k_export_local<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt, ctx->quant);
+  else k_export_local<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab, (uint32_t*)out_dev, cnt, 0);
   CK(cudaGetLastError());
   unsigned long long c = 0;
   CK(cudaMemcpyAsync(&c, cnt, 8, cudaMemcpyDeviceToHost, s));
@@ -656,8 +659,8 @@ static int refresh_bbox(mpm_ctx* ctx, cudaStream_t s) {
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
   k_reset<<<1, 1, 0, s>>>(ctx->d_status);
   int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
-  if (ctx->dim == 3) k_bbox<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status);
-  else k_bbox<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status);
+  if (ctx->dim == 3) k_bbox<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status, ctx->quant);
+  else k_bbox<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, ctx->K.inv_dx, ctx->d_status, 0);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1028,9 +1031,23 @@ static int enqueue_fused_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s
   fa.keys = ctx->keys_a; fa.flags = ctx->flags2[q_out]; fa.nlin = nlin;
   // ---- key pass
   CK(cudaMemsetAsync(ctx->flags2[q_out], 0, (size_t)(2 * nlin + 1) * 4, s));
-  if (have_prev && ctx->fused_npb > 0)   // (npb_host < 0: the block count of the substep enqueued just before is on the device)
-    k_g2p2g_keys<D><<<std::min(ctx->fused_npb, sm * 16), 128, 0, s>>>(fa, npb_host);
-  if (fa.n_old < n) k_g2p2g_keys_tail<D><<<gs_blocks(n - fa.n_old, 256, sm), 256, 0, s>>>(fa, fa.n_old, n);
+  const bool packed = D == 3 && ctx->quant;
+  if (have_prev && ctx->fused_npb > 0) {   // (npb_host < 0: the block count of the substep enqueued just before is on the device)
+    if constexpr (D == 3) {
+      if (packed) k_g2p2g_keys<3, true><<<std::min(ctx->fused_npb, sm * 16), 128, 0, s>>>(fa, npb_host);
+      else k_g2p2g_keys<3, false><<<std::min(ctx->fused_npb, sm * 16), 128, 0, s>>>(fa, npb_host);
+    } else {
+      k_g2p2g_keys<D, false><<<std::min(ctx->fused_npb, sm * 16), 128, 0, s>>>(fa, npb_host);
+    }
+  }
+  if (fa.n_old < n) {
+    if constexpr (D == 3) {
+      if (packed) k_g2p2g_keys_tail<3, true><<<gs_blocks(n - fa.n_old, 256, sm), 256, 0, s>>>(fa, fa.n_old, n);
+      else k_g2p2g_keys_tail<3, false><<<gs_blocks(n - fa.n_old, 256, sm), 256, 0, s>>>(fa, fa.n_old, n);
+    } else {
+      k_g2p2g_keys_tail<D, false><<<gs_blocks(n - fa.n_old, 256, sm), 256, 0, s>>>(fa, fa.n_old, n);
+    }
+  }
   ctx->launches += 2;
   // ---- binning of the advected positions into set q_out (counting sort, mpm_bin.cuh)
   select_set(ctx, q_out);
@@ -1054,9 +1071,14 @@ static int enqueue_fused_substep(mpm_ctx* ctx, float dt, int cur, cudaStream_t s
   fa.s = make_args<D>(ctx, dt, cur);                       // (set q_out)
   bool fast = false;
   if constexpr (D == 3) {
-    if (ctx->fused_fast) {     // cell-owner scatter (mpm_p2g3.cuh); MPM_G2P2G=simple selects the general kernel
+    constexpr size_t smem = p2g3_smem_bytes<640>();
+    if (packed) {              // packed storage: the cell-owner kernel on the quantised accessors
+      static LaunchCache lcq;
+      const int grid = cached_grid(lcq, ctx, k_p2g3<640, 3, false, true, true>, P2G3::T, smem);
+      CK(launch_chain(ctx->pdl, k_p2g3<640, 3, false, true, true>, grid, P2G3::T, smem, s, fa));
+      fast = true;
+    } else if (ctx->fused_fast) {     // cell-owner scatter (mpm_p2g3.cuh); MPM_G2P2G=simple selects the general kernel
       static LaunchCache lc;
-      constexpr size_t smem = p2g3_smem_bytes<640>();
       const int grid = cached_grid(lc, ctx, k_p2g3<640, 3, false, true>, P2G3::T, smem);
       CK(launch_chain(ctx->pdl, k_p2g3<640, 3, false, true>, grid, P2G3::T, smem, s, fa));
       fast = true;
@@ -1588,8 +1610,8 @@ extern "C" int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, voi
   if (!dst_host) return MPM_E_INVALID;
   CK(cudaSetDevice(ctx->P.device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (ctx->dim == 3) k_gather_raw<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage);
-  else k_gather_raw<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage);
+  if (ctx->dim == 3) k_gather_raw<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage, ctx->quant);
+  else k_gather_raw<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, field, (int)ctx->n, ctx->stage, 0);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst_host, ctx->stage, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1639,10 +1661,10 @@ extern "C" int mpm_gather_rows(mpm_ctx* ctx, int32_t first_field, int32_t nwords
   CK(cudaMemsetAsync(dst_dev, 0, (size_t)(end - begin) * nwords * 4, (cudaStream_t)stream));
   if (ctx->dim == 3)
     k_gather_rows<3><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
-        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev, ctx->quant);
   else
     k_gather_rows<2><<<gs_blocks(ctx->n, 256, ctx->sm_count), 256, 0, (cudaStream_t)stream>>>(
-        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev);
+        ctx->state[ctx->cur], ctx->stat, first_field, nwords, (int)ctx->n, begin, end, (uint32_t*)dst_dev, 0);
   CK(cudaGetLastError());
   return MPM_OK;
 }
@@ -1657,8 +1679,8 @@ extern "C" int mpm_particle_ranges(mpm_ctx* ctx, float* ranges_dev, void* stream
   const int nw = 4 * ctx->dim;
   k_ranges_init<<<1, 32, 0, s>>>(r, nw);
   const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
-  if (ctx->dim == 3) k_ranges<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r);
-  else k_ranges<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r);
+  if (ctx->dim == 3) k_ranges<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r, ctx->quant);
+  else k_ranges<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, (int)ctx->n, r, 0);
   k_ranges_decode<<<1, 32, 0, s>>>(r, nw);
   CK(cudaGetLastError());
   return MPM_OK;
@@ -1678,9 +1700,9 @@ extern "C" int mpm_pack_particles(mpm_ctx* ctx, const float* lo_inv_host, uint32
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
   if (ctx->dim == 3)
-    k_pack_particles<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev);
+    k_pack_particles<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev, ctx->quant);
   else
-    k_pack_particles<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev);
+    k_pack_particles<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, pa, x_and_v_dev, color_dev, 0);
   CK(cudaGetLastError());
   return MPM_OK;
 }
@@ -1760,8 +1782,8 @@ extern "C" int mpm_debug_binning(mpm_ctx* ctx, int32_t* block_host, void* stream
   int* out = (int*)ctx->state[ctx->cur ^ 1];   // the idle set is free between substeps
   const int half = ctx->P.grid_size / 2;
   int blocks = gs_blocks(ctx->n, 256, ctx->sm_count);
-  if (ctx->dim == 3) k_debug_binning<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out);
-  else k_debug_binning<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out);
+  if (ctx->dim == 3) k_debug_binning<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out, ctx->quant);
+  else k_debug_binning<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, out, 0);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(block_host, out, (size_t)ctx->n * ctx->dim * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

@@ -55,10 +55,10 @@ __device__ __forceinline__ uint32_t key_and_flags(const float* x, float inv_dx, 
 }
 
 // ---- key pass over LAST substep's particle blocks (storage order = that substep's sorted order, perm = identity)
-template <int D>
+template <int D, bool Q>
 __global__ void __launch_bounds__(128) k_g2p2g_keys(FusedArgs<D> a, int npb_old) {
   using G = Geo<D>;
-  using FL = Fld<D>;
+  using P = PStore<D, Q>;
   __shared__ float4 tile[G::TN];
   pdl_enter();
   if (a.s.st->err) return;
@@ -84,36 +84,40 @@ __global__ void __launch_bounds__(128) k_g2p2g_keys(FusedArgs<D> a, int npb_old)
     for (int s = start + tid; s < end; s += blockDim.x) {
       float x[D], fx[D], nv[D];
       int l[D];
+      P::load_x(a.s.src, s, x);
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        x[d] = ldf<D>(a.s.src, FL::X + d, s);
         const int base = base_index(x[d], a.s.K.inv_dx);
         fx[d] = __fsub_rn(__fmul_rn(x[d], a.s.K.inv_dx), (float)base);
         l[d] = min(max(base + a.tin.L.half - org[d], 0), G::LEAF - 1);
       }
-      const uint32_t mat = tag_mat(ldu<D>(a.s.src, FL::TAG, s));
+      const uint32_t mat = tag_mat(__ldg(a.s.src + P::w(P::TAG, s)));
       gather_vC<D, false>(tile, G::T, l, fx, a.s.K.four_inv_dx, nv, nullptr);
       if (mat != (uint32_t)STATIONARY) {
+        P::round_v(nv);                                                                   // (packed storage: a store rounds)
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.s.dt, nv[d]));     // :401-403
+        P::round_x(x);
       }
       a.keys[s] = key_and_flags<D>(x, a.s.K.inv_dx, a.s.L, a.flags, a.nlin, a.s.st);
     }
   }
 }
 // rows added since the last substep (all rows on the first one): no gather, x' = x + dt v with the seeded v (:396-399)
-template <int D>
+template <int D, bool Q>
 __global__ void k_g2p2g_keys_tail(FusedArgs<D> a, int r0, int n) {
-  using FL = Fld<D>;
+  using P = PStore<D, Q>;
   pdl_enter();
   if (a.s.st->err) return;
   for (int s = r0 + blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-    float x[D];
-    const uint32_t mat = tag_mat(ldu<D>(a.s.src, FL::TAG, s));
+    float x[D], v[D];
+    const uint32_t mat = tag_mat(__ldg(a.s.src + P::w(P::TAG, s)));
+    P::load_x(a.s.src, s, x);
+    P::load_v(a.s.src, s, v);
+    if (mat != (uint32_t)STATIONARY) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      x[d] = ldf<D>(a.s.src, FL::X + d, s);
-      if (mat != (uint32_t)STATIONARY) x[d] = __fadd_rn(x[d], __fmul_rn(a.s.dt, ldf<D>(a.s.src, FL::V + d, s)));
+      for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.s.dt, v[d]));
+      P::round_x(x);
     }
     a.keys[s] = key_and_flags<D>(x, a.s.K.inv_dx, a.s.L, a.flags, a.nlin, a.s.st);
   }

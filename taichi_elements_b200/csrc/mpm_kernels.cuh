@@ -11,6 +11,7 @@
 // (:344-361, 487-616, 618-687, 694-735).
 #pragma once
 #include "mpm_common.cuh"
+#include "mpm_quant.cuh"
 
 namespace mpm {
 
@@ -41,9 +42,113 @@ template <int D> __device__ __forceinline__ void stu(uint32_t* __restrict__ s, i
   s[word<D>(f, p)] = v;
 }
 
-// virtual word `f` (read-back ABI numbering, Fld<D>::NV words) of the particle in storage slot s
-template <int D> __device__ __forceinline__ uint32_t vword(const uint32_t* __restrict__ state, const Statics& st, int f, uint32_t s) {
+// ---- particle storage accessors.  Q = false: the f32 words of Fld<D>.  Q = true (quant=True with use_g2p2g, 3D):
+// bit-packed words  xq[2] vq[2] Fq[5] Jp tag  = 11 words (44 B per set instead of 104; mpm_quant.cuh, ref :216-247);
+// C does not exist in that mode (a register value of the fused kernel, ref :102-103).
+struct FldQ3 { static constexpr int X = 0, V = 2, F = 4, JP = 9, TAG = 10, N = 11; };
+template <int D, bool Q> struct PStore;
+template <int D> struct PStore<D, false> {
   using FL = Fld<D>;
+  static constexpr int N = FL::N, JP = FL::JP, TAG = FL::TAG;
+  static __device__ __forceinline__ size_t w(int f, uint32_t p) { return word<D>(f, p); }
+  static __device__ __forceinline__ void load_x(const uint32_t* __restrict__ s, uint32_t p, float* x) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = ldf<D>(s, FL::X + d, p);
+  }
+  static __device__ __forceinline__ void load_v(const uint32_t* __restrict__ s, uint32_t p, float* v) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = ldf<D>(s, FL::V + d, p);
+  }
+  static __device__ __forceinline__ void load_F(const uint32_t* __restrict__ s, uint32_t p, float* F) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) F[i] = ldf<D>(s, FL::F + i, p);
+  }
+  static __device__ __forceinline__ void store_x(uint32_t* __restrict__ s, uint32_t p, const float* x) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) stf<D>(s, FL::X + d, p, x[d]);
+  }
+  static __device__ __forceinline__ void store_v(uint32_t* __restrict__ s, uint32_t p, const float* v) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) stf<D>(s, FL::V + d, p, v[d]);
+  }
+  static __device__ __forceinline__ void store_F(uint32_t* __restrict__ s, uint32_t p, const float* F) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) stf<D>(s, FL::F + i, p, F[i]);
+  }
+  // what a store keeps (the fused kernel reads x and v back after storing them, ref :401-409)
+  static __device__ __forceinline__ void round_x(float*) {}
+  static __device__ __forceinline__ void round_v(float*) {}
+};
+template <> struct PStore<3, true> {
+  static constexpr int N = FldQ3::N, JP = FldQ3::JP, TAG = FldQ3::TAG;
+  static __device__ __forceinline__ size_t w(int f, uint32_t p) { return word_nf<FldQ3::N>(f, p); }
+  static __device__ __forceinline__ void load_x(const uint32_t* __restrict__ s, uint32_t p, float* x) {
+    const uint32_t q[2] = {__ldg(s + w(FldQ3::X, p)), __ldg(s + w(FldQ3::X + 1, p))};
+    decode_x3(q, x);
+  }
+  static __device__ __forceinline__ void load_v(const uint32_t* __restrict__ s, uint32_t p, float* v) {
+    const uint32_t q[2] = {__ldg(s + w(FldQ3::V, p)), __ldg(s + w(FldQ3::V + 1, p))};
+    decode_v3(q, v);
+  }
+  static __device__ __forceinline__ void load_F(const uint32_t* __restrict__ s, uint32_t p, float* F) {
+    uint32_t q[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) q[i] = __ldg(s + w(FldQ3::F + i, p));
+    decode_F9(q, F);
+  }
+  static __device__ __forceinline__ void store_x(uint32_t* __restrict__ s, uint32_t p, const float* x) {
+    uint32_t q[2];
+    encode_x3(x, q);
+    s[w(FldQ3::X, p)] = q[0]; s[w(FldQ3::X + 1, p)] = q[1];
+  }
+  static __device__ __forceinline__ void store_v(uint32_t* __restrict__ s, uint32_t p, const float* v) {
+    uint32_t q[2];
+    encode_v3(v, q);
+    s[w(FldQ3::V, p)] = q[0]; s[w(FldQ3::V + 1, p)] = q[1];
+  }
+  static __device__ __forceinline__ void store_F(uint32_t* __restrict__ s, uint32_t p, const float* F) {
+    uint32_t q[5];
+    encode_F9(F, q);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s[w(FldQ3::F + i, p)] = q[i];
+  }
+  static __device__ __forceinline__ void round_x(float* x) { round_x3(x); }
+  static __device__ __forceinline__ void round_v(float* v) { round_v3(v); }
+};
+// run-time selection for the utility kernels (seeding, boxes, read-back): quant != 0 only exists in 3D
+template <int D> __device__ __forceinline__ void load_x_rt(const uint32_t* __restrict__ s, int quant, uint32_t p, float* x) {
+  if constexpr (D == 3) { if (quant) { PStore<3, true>::load_x(s, p, x); return; } }
+  PStore<D, false>::load_x(s, p, x);
+}
+template <int D> __device__ __forceinline__ void load_v_rt(const uint32_t* __restrict__ s, int quant, uint32_t p, float* v) {
+  if constexpr (D == 3) { if (quant) { PStore<3, true>::load_v(s, p, v); return; } }
+  PStore<D, false>::load_v(s, p, v);
+}
+template <int D> __device__ __forceinline__ uint32_t load_tag_rt(const uint32_t* __restrict__ s, int quant, uint32_t p) {
+  if constexpr (D == 3) { if (quant) return __ldg(s + PStore<3, true>::w(FldQ3::TAG, p)); }
+  return ldu<D>(s, Fld<D>::TAG, p);
+}
+
+// virtual word `f` (read-back ABI numbering, Fld<D>::NV words) of the particle in storage slot s
+template <int D> __device__ __forceinline__ uint32_t vword(const uint32_t* __restrict__ state, const Statics& st, int f, uint32_t s,
+                                                          int quant = 0) {
+  using FL = Fld<D>;
+  if constexpr (D == 3) {
+    if (quant) {             // packed storage: decode the group the word belongs to (C does not exist: zeros)
+      if (f < FL::F) {
+        float t[3];
+        if (f < FL::V) PStore<3, true>::load_x(state, s, t); else PStore<3, true>::load_v(state, s, t);
+        return __float_as_uint(t[f < FL::V ? f : f - FL::V]);
+      }
+      if (f < FL::C) { float F[9]; PStore<3, true>::load_F(state, s, F); return __float_as_uint(F[f - FL::F]); }
+      if (f < FL::JP) return 0u;
+      if (f == FL::JP) return state[PStore<3, true>::w(FldQ3::JP, s)];
+      const uint32_t tq = state[PStore<3, true>::w(FldQ3::TAG, s)];
+      if (f == FL::MAT) return tag_mat(tq);
+      const uint32_t sq = tag_sid(tq);
+      return f == FL::COLOR ? st.color[sq] : (f == FL::ID ? st.gid[sq] : st.emit[sq]);
+    }
+  }
   if (f <= FL::JP) return state[word<D>(f, s)];
   const uint32_t tag = state[word<D>(FL::TAG, s)];
   if (f == FL::MAT) return tag_mat(tag);
@@ -200,14 +305,16 @@ __global__ void k_keys(const uint32_t* __restrict__ state, size_t cap, int n, fl
 
 // particle bounding box in global signed base-cell coordinates
 template <int D>
-__global__ void k_bbox(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, Status* st) {
+__global__ void k_bbox(const uint32_t* __restrict__ state, size_t cap, int n, float inv_dx, Status* st, int quant) {
   int lo[D], hi[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) { lo[d] = INT_MAX; hi[d] = INT_MIN; }
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
+    float xx[D];
+    load_x_rt<D>(state, quant, p, xx);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      int b = base_index(ldf<D>(state, Fld<D>::X + d, p), inv_dx);
+      int b = base_index(xx[d], inv_dx);
       lo[d] = min(lo[d], b); hi[d] = max(hi[d], b);
     }
   }
@@ -1045,6 +1152,7 @@ struct SeedArgs {
   float* x_out;          // non-null (modes 1, 2): positions only, [n][D] -- nothing is appended (mpm_seed_generate)
   Statics stat;          // static side arrays; row n0 + i gets the static row sid0 + i
   int64_t sid0;
+  int quant;             // packed storage (3D)
 };
 
 // Sort key of an external position for block-sorted seeding: absolute leaf-block coordinates, 10 bits per
@@ -1120,6 +1228,19 @@ __global__ void k_seed(SeedArgs a) {
 #pragma unroll
       for (int d = 0; d < D; ++d) a.x_out[i * D + d] = x[d];
       continue;
+    }
+    const uint32_t sidq = (uint32_t)(a.sid0 + i);
+    if constexpr (D == 3) {
+      if (a.quant) {                                           // packed storage: x, v, F = I, Jp, tag
+        const float Fi[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+        PStore<3, true>::store_x(a.state, p, x);
+        PStore<3, true>::store_v(a.state, p, v);
+        PStore<3, true>::store_F(a.state, p, Fi);
+        a.state[PStore<3, true>::w(FldQ3::JP, p)] = __float_as_uint(material == SAND ? 0.0f : 1.0f);
+        a.state[PStore<3, true>::w(FldQ3::TAG, p)] = make_tag((uint32_t)material, sidq);
+        a.stat.color[sidq] = (uint32_t)color; a.stat.gid[sidq] = (uint32_t)id; a.stat.emit[sidq] = (uint32_t)a.emitter;
+        continue;
+      }
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) { stf<D>(a.state, FL::X + d, p, x[d]); stf<D>(a.state, FL::V + d, p, v[d]); }
@@ -1260,30 +1381,33 @@ __global__ void k_voxel_sample(VoxSampleArgs a) {
 // several consecutive state words of particles [begin, end) as rows out[id - begin][nwords]
 template <int D>
 __global__ void k_gather_rows(const uint32_t* __restrict__ state, Statics stat, int first, int nwords,
-                              int n, int64_t begin, int64_t end, uint32_t* __restrict__ out) {
+                              int n, int64_t begin, int64_t end, uint32_t* __restrict__ out, int quant) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    const int64_t id = vword<D>(state, stat, Fld<D>::ID, s);
+    const int64_t id = vword<D>(state, stat, Fld<D>::ID, s, quant);
     if (id >= begin && id < end)
-      for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = vword<D>(state, stat, first + w, s);
+      for (int w = 0; w < nwords; ++w) out[(size_t)(id - begin) * nwords + w] = vword<D>(state, stat, first + w, s, quant);
   }
 }
 // rows [0, n) of one (virtual) state word in storage order
 template <int D>
-__global__ void k_gather_raw(const uint32_t* __restrict__ state, Statics stat, int field, int n, uint32_t* __restrict__ out) {
+__global__ void k_gather_raw(const uint32_t* __restrict__ state, Statics stat, int field, int n, uint32_t* __restrict__ out,
+                             int quant) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x)
-    out[s] = vword<D>(state, stat, field, s);
+    out[s] = vword<D>(state, stat, field, s, quant);
 }
 // Static rows renumbered by storage slot (distributed runs: leavers leave holes, arrivals append): pass 0 copies the
 // row of every live particle to tmp[3][n], pass 1 copies back and rewrites the tags (sid = slot).
 template <int D>
-__global__ void k_compact_statics(uint32_t* __restrict__ state, Statics stat, int n, uint32_t* __restrict__ tmp, int pass) {
+__global__ void k_compact_statics(uint32_t* __restrict__ state, Statics stat, int n, uint32_t* __restrict__ tmp, int pass,
+                                  int quant) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
     if (pass == 0) {
-      const uint32_t sid = tag_sid(state[word<D>(Fld<D>::TAG, s)]);
+      const uint32_t sid = tag_sid(load_tag_rt<D>(state, quant, s));
       tmp[s] = stat.color[sid]; tmp[(size_t)n + s] = stat.gid[sid]; tmp[2 * (size_t)n + s] = stat.emit[sid];
     } else {
       stat.color[s] = tmp[s]; stat.gid[s] = tmp[(size_t)n + s]; stat.emit[s] = tmp[2 * (size_t)n + s];
-      const size_t w = word<D>(Fld<D>::TAG, s);
+      size_t w = word<D>(Fld<D>::TAG, s);
+      if constexpr (D == 3) { if (quant) w = PStore<3, true>::w(FldQ3::TAG, s); }
       state[w] = make_tag(tag_mat(state[w]), s);
     }
   }
@@ -1293,7 +1417,7 @@ __global__ void k_compact_statics(uint32_t* __restrict__ state, Statics stat, in
 // this rank's columns (rows already handed to a neighbour are skipped), compacted in storage order groups
 template <int D>
 __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat, int n, float inv_dx, int half, Slab slab,
-                               uint32_t* __restrict__ out, unsigned long long* __restrict__ count) {
+                               uint32_t* __restrict__ out, unsigned long long* __restrict__ count, int quant) {
   using G = Geo<D>;
   using FL = Fld<D>;
   constexpr int W = 2 * D + 3;
@@ -1302,7 +1426,7 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat,
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
     bool mine = s < (uint32_t)n;
     if (mine && slab.enabled) {
-      const int bx = (base_index(ldf<D>(state, FL::X, s), inv_dx) + half) >> G::LOG_LEAF;
+      const int bx = (base_index(__uint_as_float(vword<D>(state, stat, FL::X, s, quant)), inv_dx) + half) >> G::LOG_LEAF;
       mine = bx >= slab.lo && bx < slab.hi;
     }
     const unsigned m = __ballot_sync(0xffffffffu, mine);
@@ -1311,9 +1435,12 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat,
     base = __shfl_sync(0xffffffffu, base, 0);
     if (!mine) continue;
     uint32_t* o = out + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * W;
+    float ex[D], ev[D];
+    load_x_rt<D>(state, quant, s, ex);
+    load_v_rt<D>(state, quant, s, ev);
 #pragma unroll
-    for (int d = 0; d < D; ++d) { o[d] = ldu<D>(state, FL::X + d, s); o[D + d] = ldu<D>(state, FL::V + d, s); }
-    const uint32_t tag = ldu<D>(state, FL::TAG, s);
+    for (int d = 0; d < D; ++d) { o[d] = __float_as_uint(ex[d]); o[D + d] = __float_as_uint(ev[d]); }
+    const uint32_t tag = load_tag_rt<D>(state, quant, s);
     o[2 * D] = tag_mat(tag);
     o[2 * D + 1] = stat.color[tag_sid(tag)];
     o[2 * D + 2] = stat.gid[tag_sid(tag)];
@@ -1335,14 +1462,17 @@ __global__ void k_ranges_init(uint32_t* r, int nwords) {
 }
 // ranges[c][d][0|1] (c = 0: x, 1: v) as ordered uints; fields X and V are the first 2*D state words
 template <int D>
-__global__ void k_ranges(const uint32_t* __restrict__ state, size_t cap, int n, uint32_t* __restrict__ r) {
+__global__ void k_ranges(const uint32_t* __restrict__ state, size_t cap, int n, uint32_t* __restrict__ r, int quant) {
   float lo[2 * D], hi[2 * D];
 #pragma unroll
   for (int f = 0; f < 2 * D; ++f) { lo[f] = __int_as_float(0x7f800000); hi[f] = __int_as_float(0xff800000); }
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    float xv[2 * D];
+    load_x_rt<D>(state, quant, s, xv);
+    load_v_rt<D>(state, quant, s, xv + D);
 #pragma unroll
     for (int f = 0; f < 2 * D; ++f) {
-      const float a = ldf<D>(state, f, s);
+      const float a = xv[f];
       lo[f] = fminf(lo[f], a); hi[f] = fmaxf(hi[f], a);
     }
   }
@@ -1366,15 +1496,18 @@ __global__ void k_ranges_decode(uint32_t* r, int nwords) {
 struct PackArgs { float lo[2][3], inv[2][3]; };
 template <int D>
 __global__ void k_pack_particles(const uint32_t* __restrict__ state, Statics stat, int n, PackArgs pa,
-                                 uint32_t* __restrict__ xv, uint8_t* __restrict__ color) {
+                                 uint32_t* __restrict__ xv, uint8_t* __restrict__ color, int quant) {
   using FL = Fld<D>;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
-    const uint32_t sid = tag_sid(ldu<D>(state, FL::TAG, s)), id = stat.gid[sid];
-    if (id >= (uint32_t)n) continue;   // ids are a permutation of [0, n) on a single-device solver; never write outside
+    const uint32_t sid = tag_sid(load_tag_rt<D>(state, quant, s)), id = stat.gid[sid];
+    if (id >= (uint32_t)n) continue;
+    float px[D], pv[D];
+    load_x_rt<D>(state, quant, s, px);
+    load_v_rt<D>(state, quant, s, pv);   // ids are a permutation of [0, n) on a single-device solver; never write outside
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       // ((a - lo) * (1 / (hi - lo)) * (2^bits - 1) + 0.499).astype(uint32), every step rounded to f32 (:50-55)
-      const float x = ldf<D>(state, FL::X + d, s), v = ldf<D>(state, FL::V + d, s);
+      const float x = px[d], v = pv[d];
       const uint32_t xq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, pa.lo[0][d]), pa.inv[0][d]), 16777215.0f), 0.499f));
       const uint32_t vq = __float2uint_rz(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v, pa.lo[1][d]), pa.inv[1][d]), 255.0f), 0.499f));
       xv[(size_t)id * D + d] = (xq << 8) + vq;
@@ -1388,14 +1521,16 @@ __global__ void k_pack_particles(const uint32_t* __restrict__ state, Statics sta
 
 template <int D>
 __global__ void k_debug_binning(const uint32_t* __restrict__ state, Statics stat, int n, float inv_dx, int half,
-                                int* __restrict__ out) {
+                                int* __restrict__ out, int quant) {
   using G = Geo<D>;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < (uint32_t)n; p += gridDim.x * blockDim.x) {
-    uint32_t id = stat.gid[tag_sid(ldu<D>(state, Fld<D>::TAG, p))];
+    uint32_t id = stat.gid[tag_sid(load_tag_rt<D>(state, quant, p))];
     if (id >= (uint32_t)n) continue;
+    float bx[D];
+    load_x_rt<D>(state, quant, p, bx);
 #pragma unroll
     for (int d = 0; d < D; ++d)
-      out[(size_t)id * D + d] = (base_index(ldf<D>(state, Fld<D>::X + d, p), inv_dx) + half) >> G::LOG_LEAF;
+      out[(size_t)id * D + d] = (base_index(bx[d], inv_dx) + half) >> G::LOG_LEAF;
   }
 }
 

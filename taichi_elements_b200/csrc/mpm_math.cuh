@@ -63,6 +63,32 @@ MPM_HD float sqrt_pos_(float x) {   // x >= 0, normal range
 }
 
 // ---------------------------------------------------------------------------
+// Fixed-point rounding of the quantised storage (quant=True, mpm_quant.cuh; ref :106-114): used here because the
+// fused kernel's `self.F[p] = new_F` (:416) rounds F to its 16-bit grid BEFORE the constitutive model reads it back.
+// ---------------------------------------------------------------------------
+static constexpr float QX_MAX = 2.0f;      // :107
+static constexpr int QX_BITS = 21;
+static constexpr float QF_MAX = 4.1f;      // F_bound + 0.1 (:99, 113)
+static constexpr int QF_BITS = 16;
+static constexpr int QV_FRAC = 19, QV_EXP = 7;
+
+MPM_HD int q_round(float t) { return (int)(t + (t < 0.0f ? -0.5f : 0.5f)); }       // round half away from zero
+MPM_HD int q_fixed(float x, float max_value, int bits) {
+  const float inv_scale = (float)(1 << (bits - 1)) / max_value;
+  const int lim = (1 << (bits - 1)) - 1;
+  const float t = x * inv_scale;
+  if (!(t > -(float)lim)) return -lim;                                             // (also NaN)
+  if (t > (float)lim) return lim;
+  return q_round(t);
+}
+MPM_HD float dq_fixed(int q, float max_value, int bits) { return (float)q * (max_value / (float)(1 << (bits - 1))); }
+
+MPM_HD void round_F9(float* F) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) F[i] = dq_fixed(q_fixed(F[i], QF_MAX, QF_BITS), QF_MAX, QF_BITS);
+}
+
+// ---------------------------------------------------------------------------
 // 2x2 SVD, Taichi's closed form.  Row-major 2x2.
 // ---------------------------------------------------------------------------
 MPM_HD void svd2(const float* F, float* U, float* sig, float* V) {
@@ -388,6 +414,7 @@ MPM_HD void trial_F(const Consts& K, float dt, int material, const float* F, con
   if (fused && K.clamp_F) {                                  // [g2p2g] :415-416
 #pragma unroll
     for (int i = 0; i < DD; ++i) Fn[i] = fmaxf(-4.0f, fminf(4.0f, Fn[i]));
+    if constexpr (D == 3) round_F9(Fn);                      // the store to the 16-bit field (3D packed storage)
   }
 }
 

@@ -86,7 +86,7 @@ __device__ __forceinline__ const SubstepArgs<3>& p2g3_args(const FusedArgs<3>& a
 
 // G2P2G: the use_g2p2g fused kernel (mpm_g2p2g.cuh): the constitutive phase first gathers v and C from the INPUT grid
 // at the old position (an 8^3 node tile around the block, staged once per block) and advects; C stays in registers.
-template <int CHUNK, int MINB, bool FUSED, bool G2P2G = false>
+template <int CHUNK, int MINB, bool FUSED, bool G2P2G = false, bool Q = false>
 __global__ void __launch_bounds__(P2G3::T, MINB)
 k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg) {
   constexpr int D = 3;
@@ -178,17 +178,14 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         const uint32_t p = pq[0];
 #pragma unroll
         for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
+        using P = PStore<3, Q>;                                  // f32 words, or the packed storage of quant=True
         float x[D], v[D], fx[D], C[D * D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          x[d] = ldf<D>(a.src, FL::X + d, p);
-          v[d] = ldf<D>(a.src, FL::V + d, p);
-        }
+        P::load_x(a.src, p, x);
+        P::load_v(a.src, p, v);
         float F[D * D], aff[D * D], mass;
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) F[i] = ldf<D>(a.src, FL::F + i, p);
-        float Jp = ldf<D>(a.src, FL::JP, p);
-        const uint32_t tag = ldu<D>(a.src, FL::TAG, p), mat = tag_mat(tag);
+        P::load_F(a.src, p, F);
+        float Jp = __uint_as_float(__ldg(a.src + P::w(P::JP, p)));
+        const uint32_t tag = __ldg(a.src + P::w(P::TAG, p)), mat = tag_mat(tag);
         if ((int)p < arg.n_old) {
           int l[D];
 #pragma unroll
@@ -208,23 +205,24 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
           for (int i = 0; i < D * D; ++i) C[i] = 0.0f;                                 // :396-399
         }
         if (mat != (uint32_t)STATIONARY) {
+          P::round_v(v);                          // (packed storage: `self.v[p] = new_v` rounds, the advection reads it back)
 #pragma unroll
           for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, v[d]));  // :401-403
+          P::round_x(x);                          // (and the P2G half reads the stored x, :406)
         }
         particle_update<D>(a.K, a.dt, (int)mat, F, C, Jp, aff, mass);
+        P::store_x(a.dst, s, x);
+        P::store_v(a.dst, s, v);
+        P::store_F(a.dst, s, F);
+        a.dst[P::w(P::JP, s)] = __float_as_uint(Jp);
+        a.dst[P::w(P::TAG, s)] = tag;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          stf<D>(a.dst, FL::X + d, s, x[d]);
-          stf<D>(a.dst, FL::V + d, s, v[d]);
           vmax = fmaxf(vmax, fabsf(v[d]));
           const int nb = base_index(x[d], a.K.inv_dx);
           bb_lo[d] = min(bb_lo[d], nb); bb_hi[d] = max(bb_hi[d], nb);
           fx[d] = x[d] * a.K.inv_dx - (float)nb;                                       // :409
         }
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
-        stf<D>(a.dst, FL::JP, s, Jp);
-        stu<D>(a.dst, FL::TAG, s, tag);
         const float dx = a.K.dx;
         const int sw = (q >> 1) & 3;
         pay[q * PS + (0 ^ sw)] = make_float4(mass * v[0], mass * v[1], mass * v[2], mass);
@@ -282,8 +280,9 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
           // every word P2G reads (x .. material) is in the first FL::TAG + 1 rows of the block's tiles
           const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
           const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
+          constexpr int NW = PStore<3, Q>::N;                      // words per particle of the storage in use
           for (int i = tid; i < nt; i += T)
-            prefetch_l2_range(a.src + (size_t)(t0 + i) * FL::N * TILE, (uint32_t)(FL::TAG + 1) * TILE * 4u);
+            prefetch_l2_range(a.src + (size_t)(t0 + i) * NW * TILE, (uint32_t)NW * TILE * 4u);
           if (tid == T - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
         }
       }

@@ -127,11 +127,13 @@ class MPMSolver:
                  device=None):
         self.dim = len(res)
         assert self.dim in (2, 3), "MPM solver supports only 2D and 3D simulations."
-        if quant:
-            # the reference packs x/v/F into 40-64 B per particle (:106-114, 216-262); here the state stays
-            # f32 (116 B per particle in 3D): same API, unquantised (more accurate) numbers
+        # quant=True (:106-114, 216-262): with use_g2p2g in 3D -- the combination the reference's large scenes use --
+        # x, v and F are stored bit-packed (44 B per particle and set instead of 104; csrc/mpm_quant.cuh).  Otherwise
+        # the state stays f32: same API, unquantised (more accurate) numbers.
+        self.packed_storage = bool(quant and use_g2p2g and self.dim == 3)
+        if quant and not self.packed_storage:
             import warnings
-            warnings.warn('quant=True: particle state is kept in f32 (no bit-packing) in this build')
+            warnings.warn('quant=True without use_g2p2g (or in 2D): particle state is kept in f32 in this build')
         self.quant = quant
         self.use_g2p2g = use_g2p2g
         self.v_clamp_g2p2g = v_clamp_g2p2g
@@ -198,7 +200,7 @@ class MPMSolver:
         if rc != 0:
             raise _lib.MPMError(f'mpm_create failed ({rc})')
         self._ctx = ctx
-        self._nf = self._lib.mpm_state_fields(self.dim)          # physical words per particle (x v F C Jp tag)
+        self._nf = self._lib.mpm_ctx_state_fields(ctx)           # physical words per particle (x v F C Jp tag; 11 packed)
         self._cap = 0
         self._max_blocks = 0
         self._state = None
@@ -654,6 +656,8 @@ class MPMSolver:
         """Replace all particles by a full state (tests: start CUDA and oracle from the same bits)."""
         n, d = x.shape
         assert d == self.dim
+        if self.packed_storage:
+            raise NotImplementedError('_inject_state writes f32 words; not available with packed storage')
         self.clear_particles()
         self._reserve(n)
         rows = [np.asarray(x, np.float32).T, np.asarray(v, np.float32).T,

@@ -2,6 +2,7 @@
 // test-suite check the exact device math (SVD, plasticity, stress) against the
 // oracle without a GPU.  Never loaded by the product package.
 #include "../taichi_elements_b200/csrc/mpm_math.cuh"
+#include "../taichi_elements_b200/csrc/mpm_quant.cuh"
 extern "C" {
 void host_svd3(const float* F, int n, float* U, float* sig, float* V) {
   for (int i = 0; i < n; ++i) mpm::svd3(F + 9 * i, U + 9 * i, sig + 3 * i, V + 9 * i);
@@ -32,6 +33,14 @@ void host_particle_update(int dim, const float* consts12, int support_plasticity
       mpm::particle_update<2>(K, dt, material[i], F + 4 * i, C + 4 * i, Jp[i], affine + 4 * i, mass[i]);
     else
       mpm::particle_update<3>(K, dt, material[i], F + 9 * i, C + 9 * i, Jp[i], affine + 9 * i, mass[i]);
+  }
+}
+// quantised storage codecs (csrc/mpm_quant.cuh): encode -> packed words -> decode; kind 0 = x, 1 = v, 2 = F
+void host_quant_round(int kind, int n, const float* in, float* out, unsigned* words) {
+  for (int i = 0; i < n; ++i) {
+    if (kind == 0) { mpm::encode_x3(in + 3 * i, words + 2 * i); mpm::decode_x3(words + 2 * i, out + 3 * i); }
+    else if (kind == 1) { mpm::encode_v3(in + 3 * i, words + 2 * i); mpm::decode_v3(words + 2 * i, out + 3 * i); }
+    else { mpm::encode_F9(in + 9 * i, words + 5 * i); mpm::decode_F9(words + 5 * i, out + 9 * i); }
   }
 }
 }

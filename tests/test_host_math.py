@@ -112,3 +112,33 @@ def test_svd_free_paths_match_oracle(host_math, plastic, fused):
     scale = max(1.0, float(np.abs(o._affine).max()))
     err = np.abs(aff - o._affine).reshape(n, -1).max(1)
     assert err.max() < 2e-4 * scale, (err.argmax(), mat[err.argmax()], fast[err.argmax()])
+
+
+def test_quantised_storage_codecs_match_the_restatement(host_math):
+    """csrc/mpm_quant.cuh (x: 3 x 21-bit fixed, v: shared-exponent 19-bit fractions, F: 9 x 16-bit fixed; ref
+    engine/mpm_solver.py:106-114, 216-247) against oracle/quant_oracle.py: same rounded values, values inside the
+    representable range within half a step, saturation outside, idempotent."""
+    from oracle import quant_oracle as q
+    rng = np.random.default_rng(11)
+    n = 20000
+    x = (rng.random((n, 3)) * 4.4 - 2.2).astype(np.float32)
+    x[:4] = [[0, 0, 0], [1.9999999, -2.0, 2.0], [1e-7, -1e-7, 0.5], [3.0, -3.0, 0.123]]
+    v = (rng.normal(size=(n, 3)) * np.exp(rng.normal(size=(n, 1)) * 6)).astype(np.float32)
+    v[:3] = [[0, 0, 0], [1.0, 1e-9, -1.0], [-5.5, 0.25, 1e-3]]
+    F = (np.eye(3).reshape(1, 9) + rng.normal(size=(n, 9)) * 1.5).astype(np.float32)
+    F[0] = np.eye(3).ravel()
+    F[1] = [4.05, -4.05, 4.2, -4.2, 100, -100, 0, 1, -1]
+    for kind, a, ref, nw in ((0, x, q.round_x(x), 2), (1, v, q.round_v(v), 2), (2, F, q.round_F(F.reshape(n, 3, 3)).reshape(n, 9), 5)):
+        out = np.empty_like(a)
+        words = np.zeros((n, nw), np.uint32)
+        host_math.host_quant_round(kind, n, P(np.ascontiguousarray(a)), P(out), P(words))
+        assert np.array_equal(out, ref), kind
+        again = np.empty_like(a)
+        host_math.host_quant_round(kind, n, P(out), P(again), P(words))
+        assert np.array_equal(again, out), kind                       # a stored value is a fixed point
+    inside = np.abs(x).max(1) < 1.99
+    assert np.abs(q.round_x(x) - x)[inside].max() <= 2.0 / 2**20 / 2 * 1.001
+    assert np.abs(q.round_x(x)).max() <= 2.0
+    rel = np.abs(q.round_v(v) - v).max(1) / np.abs(v).max(1).clip(1e-30)
+    assert rel[np.abs(v).max(1) > 1e-15].max() <= 2.0**-17 * 0.5 * 1.001      # 18 significant bits of the largest component
+    assert abs(float(q.round_F(np.array([1.0], np.float32))[0]) - 1.0) < 4.1 / 2**15    # the identity is not exact (as in the reference)
