@@ -231,36 +231,39 @@ __global__ void k_bin_rank(const uint32_t* __restrict__ keys, const int* __restr
   pdl_enter();
   if (st->err) return;
   const int n = st->n_cur;
-  const int lane = threadIdx.x & 31;
   const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
-  const uint32_t nround = (nquad + 31u) & ~31u;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
-    uint4 kq = make_uint4(INVALID_KEY, INVALID_KEY, INVALID_KEY, INVALID_KEY);
-    if (t < nquad) kq = __ldg(reinterpret_cast<const uint4*>(keys) + t);
+  // Particles are stored in last substep's (block, cell) order, so the four consecutive keys of a thread mostly form
+  // one or two RUNS of equal keys: one atomic per run (adding its length) instead of one warp-wide match per particle
+  // (66 -> see profiles/README.md).  Runs of the same cell in neighbouring threads simply hit the same counter twice.
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nquad; t += gridDim.x * blockDim.x) {
+    const uint4 kq = __ldg(reinterpret_cast<const uint4*>(keys) + t);
     const uint32_t kk[4] = {kq.x, kq.y, kq.z, kq.w};
-    uint32_t rr[4];
+    uint32_t idx[4], lin[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // rows past n in the last quad hold stale keys when the keys came from G2P / the unpack pass
       const uint32_t key = 4u * t + j < (uint32_t)n ? kk[j] : INVALID_KEY;
-      uint32_t idx = 0xFFFFFFFFu - (uint32_t)lane, lin = 0;
+      idx[j] = 0xFFFFFFFFu; lin[j] = 0;
       if (key != INVALID_KEY) {
-        lin = key >> G::CB;
-        const int b = fscan[lin];
-        if (b < max_blocks) idx = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
+        if (j > 0 && key == kk[j - 1] && idx[j - 1] != 0xFFFFFFFFu) { idx[j] = idx[j - 1]; lin[j] = lin[j - 1]; continue; }
+        lin[j] = key >> G::CB;
+        const int b = fscan[lin[j]];
+        if (b < max_blocks) idx[j] = (uint32_t)b * G::CELLS + (key & (G::CELLS - 1));
         else atomicOr(&st->err, ERR_BLOCK_CAPACITY);
       }
-      const bool live = idx < 0xFFFFFF00u;
-      // one atomic per distinct bucket in the warp (neighbouring particles share cells)
-      const unsigned grp = __match_any_sync(0xffffffffu, idx);
-      const int leader = __ffs(grp) - 1;
-      int base = 0;
-      if (live && lane == leader) base = atomicAdd(&cellcount[idx], __popc(grp));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      rr[j] = (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-      if (live && rr[j] == 0) pb_key[idx / G::CELLS] = lin;
     }
-    if (t < nquad) reinterpret_cast<uint4*>(rank)[t] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+    uint32_t rr[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (idx[j] == 0xFFFFFFFFu) continue;
+      if (j > 0 && idx[j] == idx[j - 1]) { rr[j] = rr[j - 1] + 1u; continue; }     // inside a run
+      int len = 1;
+#pragma unroll
+      for (int q = j + 1; q < 4; ++q) len += (q - j == len && idx[q] == idx[j]) ? 1 : 0;
+      rr[j] = (uint32_t)atomicAdd(&cellcount[idx[j]], len);
+      if (rr[j] == 0u) pb_key[idx[j] / G::CELLS] = lin[j];
+    }
+    reinterpret_cast<uint4*>(rank)[t] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
   }
 }
 
