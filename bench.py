@@ -135,6 +135,27 @@ def cube_drop(name):
                       f'WATER cube, 8 per cell), g=(0,-20,0), dt=3e-3/39')
 
 
+def bunnies(name, n_ellipsoids=482):
+    """configs[2] / SURVEY 8(d) cfg 3: res 256 unbounded, g = (0, -25, 0), the six slip planes (mu = 0.5) of ref
+    demo/demo_3d_bunnies.py:76-107, 482 ellipsoids r = 0.048 (62 175 particles each = 29.97 M) alternating SNOW / SAND on
+    a jittered 0.2 lattice, launched downwards at 5 m/s; seeded on the device with add_ellipsoid (every particle takes
+    the SVD path once the material deforms)."""
+    rng = np.random.default_rng(3)
+    ell = []
+    for ix in np.arange(-1.6, 1.61, 0.2):
+        for iy in np.arange(0.1, 1.51, 0.2):
+            for iz in np.arange(-0.8, 0.81, 0.2):
+                if len(ell) < n_ellipsoids:
+                    c = np.array([ix, iy, iz]) + rng.uniform(-0.03, 0.03, 3)
+                    ell.append((list(map(float, c)), 0.048, SNOW if len(ell) % 2 == 0 else SAND, (0.0, -5.0, 0.0)))
+    planes = [((0, 0, 0), (0, 1, 0)), ((0, 1.9, 0), (0, -1, 0)), ((-1.9, 0, 0), (1, 0, 0)), ((1.9, 0, 0), (-1, 0, 0)),
+              ((0, 0, -0.95), (0, 0, 1)), ((0, 0, 0.95), (0, 0, -1))]
+    return dict(name=name, res=(256, ) * 3, unbounded=True, gravity=(0.0, -25.0, 0.0), frame_dt=3e-3, chunks=[],
+                ellipsoids=ell, colliders=[(p, n, 1, 0.5) for p, n in planes], preroll=20, n=None, cut_cells=[],
+                label=f'configs[2]: 3D unbounded res 256^3, {len(ell)} SNOW/SAND ellipsoids r=0.048 (add_ellipsoid, 8 per cell) '
+                      f'falling at 5 m/s between six slip planes mu=0.5, g=(0,-25,0), dt=2e-2*dx')
+
+
 def workload(name, world=1):
     w = _workload(name, world)
     base = 0
@@ -159,6 +180,10 @@ def _workload(name, world=1):
         return brick(name, world, cells=(64, 64, 64))
     if name.startswith('cube_drop'):
         return cube_drop(name)
+    if name == 'bunnies_30m':
+        return bunnies(name)
+    if name == 'bunnies_2m':
+        return bunnies(name, 32)
     raise ValueError(name)
 
 
@@ -523,8 +548,14 @@ def main():
     if world > 1:
         mpm.reserve_blocks(max(1 << 16, int(sum(c.n for c in chunks) // 160)))
     host_parts = seed(mpm, chunks, world)
+    for centre, radius, mat, vel in w.get('ellipsoids', []):      # configs[2]: seeded on the device
+        with quiet:
+            mpm.add_ellipsoid(center=centre, radius=radius, material=mat, velocity=vel)
     n_local = mpm.n_particles[None]
     n_total = int(allsum(n_local))
+    if w['n'] is None:
+        w['n'] = n_total
+        args.no_e2e = True                                          # (no host chunks to upload for this scene)
     assert n_total == w['n'], (n_total, w['n'])
     dt = substep_dt(w, mpm.default_dt)
     preroll = w['preroll'] if args.preroll < 0 else args.preroll

@@ -249,6 +249,13 @@ int mpm_seed_positions_slab(mpm_ctx* ctx, const float* x_dev, int64_t n, int64_t
 int mpm_seed_generate(mpm_ctx* ctx, int32_t mode, int64_t n, int64_t id0, const double* a, const double* b,
                       uint64_t seed, float* x_out_dev, void* stream);
 int mpm_export_local(mpm_ctx* ctx, void* out_dev, int64_t* count, void* stream);
+/* Re-cutting: after mpm_set_slab moved this rank's columns, one round of the bulk move of the rows that now lie outside
+ * (at most `capacity` per side) into LOCAL send buffers of the migration format; the host exchanges the buffers with the
+ * neighbours and gives the received ones to mpm_phase_unpack inside mpm_batch_begin/end; repeat until no rank reports
+ * rows left outside.  out3 = {rows sent to -x, rows sent to +x, rows still outside}.  Synchronises.
+ * BEFORE mpm_set_slab, call it once with capacity 0 (buffers NULL): rows outside the OLD columns are leavers of the last
+ * substep that were already delivered; they are marked dead so that a cut moving over them cannot revive them. */
+int mpm_rebalance_pack(mpm_ctx* ctx, void* send_lo_dev, void* send_hi_dev, int32_t capacity, int64_t* out3, void* stream);
 /* rows [0, n) of one state word in storage order (pair with the `id` word) */
 int mpm_download_raw(mpm_ctx* ctx, int32_t field, void* dst_host, void* stream);
 

@@ -112,6 +112,7 @@ SYMBOLS = [
     ('mpm_seed_positions_slab', _i32, [_vp, _vp, _i64, _i64, _i32, _i32, _dp, _i32, ctypes.POINTER(_i64), _vp]),
     ('mpm_seed_generate', _i32, [_vp, _i32, _i64, _i64, _dp, _dp, ctypes.c_uint64, _vp, _vp]),
     ('mpm_export_local', _i32, [_vp, _vp, ctypes.POINTER(_i64), _vp]),
+    ('mpm_rebalance_pack', _i32, [_vp, _vp, _vp, _i32, ctypes.POINTER(_i64), _vp]),
     ('mpm_voxelize', _i32, [_i32, _vp, _i64, _vp, _dbl, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_voxel_sample', _i32, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _dbl, _dp, _i32, _i32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp]),
     ('mpm_debug_binning', _i32, [_vp, _vp, _vp]),

@@ -1425,6 +1425,40 @@ extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
   return MPM_OK;
 }
 
+// DistributedMPMSolver.rebalance: one round of the bulk move after mpm_set_slab changed this rank's columns (see
+// k_rebalance_pack).  The buffers are LOCAL send buffers of the migration format (mpm_comm_bytes(dim, 0, cap)); the
+// host exchanges them and hands the received ones to mpm_phase_unpack.  out3 = rows sent to -x, to +x, rows still outside.
+extern "C" int mpm_rebalance_pack(mpm_ctx* ctx, void* send_lo_dev, void* send_hi_dev, int32_t cap, int64_t* out3,
+                                  void* stream) {
+  if (!ctx || !out3 || cap < 0) return MPM_E_INVALID;
+  if (!ctx->state[0]) return fail(ctx, MPM_E_UNBOUND, "no buffers bound");
+  if (ctx->quant || ctx->K.g2p2g) return fail(ctx, MPM_E_INVALID, "mpm_rebalance_pack: split-mode f32 storage only");
+  CK(cudaSetDevice(ctx->P.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->stage);
+  CK(cudaMemsetAsync(cnt, 0, 24, s));
+  out3[0] = out3[1] = out3[2] = 0;
+  if (ctx->n > 0) {
+    const int blocks = gs_blocks(ctx->n, 256, ctx->sm_count), half = ctx->P.grid_size / 2;
+    if (ctx->dim == 3)
+      k_rebalance_pack<3><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab,
+                                                 (uint32_t*)send_lo_dev, (uint32_t*)send_hi_dev, cap, cnt);
+    else
+      k_rebalance_pack<2><<<blocks, 256, 0, s>>>(ctx->state[ctx->cur], ctx->stat, (int)ctx->n, ctx->K.inv_dx, half, ctx->slab,
+                                                 (uint32_t*)send_lo_dev, (uint32_t*)send_hi_dev, cap, cnt);
+  }
+  if (cap > 0) k_rebalance_headers<<<1, 1, 0, s>>>((uint32_t*)send_lo_dev, (uint32_t*)send_hi_dev, cap, cnt);
+  CK(cudaGetLastError());
+  unsigned long long h[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(h, cnt, 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out3[0] = (int64_t)std::min<unsigned long long>(h[0], (unsigned long long)cap);
+  out3[1] = (int64_t)std::min<unsigned long long>(h[1], (unsigned long long)cap);
+  out3[2] = (int64_t)h[2];
+  ctx->bbox_valid = false;
+  return MPM_OK;
+}
+
 extern "C" int mpm_batch_end(mpm_ctx* ctx, void* stream) {
   REQUIRE_BATCH();
   ctx->in_batch = false;

@@ -55,13 +55,17 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
 #pragma unroll
     for (int d = 0; d < D; ++d)
       xs[d] = __ldg(reinterpret_cast<const float4*>(state + word<D>(Fld<D>::X + d, 4u * t)));   // 4 particles of one tile row
+    // with slabs a row can be DEAD (handed over while the cuts moved, mpm_rebalance_pack): its position no longer counts
+    uint4 tg = make_uint4(0, 0, 0, 0);
+    if (slab.enabled) tg = __ldg(reinterpret_cast<const uint4*>(state + word<D>(Fld<D>::TAG, 4u * t)));
     uint32_t out[4];
     uint32_t prev_lin = 0xFFFFFFFFu, prev_om = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = 4u * t + j;
       uint32_t lin = 0, cell = 0, sp = 0;
-      bool bad = false, mine = p < (uint32_t)n;
+      const uint32_t tgj = j == 0 ? tg.x : (j == 1 ? tg.y : (j == 2 ? tg.z : tg.w));
+      bool bad = false, mine = p < (uint32_t)n && tag_mat(tgj) != MAT_DEAD;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const float xv = j == 0 ? xs[d].x : (j == 1 ? xs[d].y : (j == 2 ? xs[d].z : xs[d].w));

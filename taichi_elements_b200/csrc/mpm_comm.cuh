@@ -193,6 +193,39 @@ __global__ void k_mig_unpack(uint32_t* __restrict__ state, size_t cap, uint32_t*
     }
   }
 }
+// ---- re-cutting (DistributedMPMSolver.rebalance): after the slab bounds have changed, rows whose base block column
+// now lies outside [lo, hi) are moved to the neighbour on that side in rounds of at most `cap` rows per side: the row
+// (all virtual words: its static attributes travel) goes into a message buffer of the migration format and its tag is
+// marked DEAD so that a later round does not send it again and the next binning drops it.  With cap == 0 nothing is
+// sent: rows outside the slab (leavers of the last substep, already delivered) are only marked, so that moving the cut
+// over them cannot bring them back to life.
+template <int D>
+__global__ void k_rebalance_pack(uint32_t* __restrict__ state, Statics stat, int n, float inv_dx, int half, Slab slab,
+                                 uint32_t* __restrict__ buf_lo, uint32_t* __restrict__ buf_hi, int cap,
+                                 unsigned long long* __restrict__ counters /* [0..1] sent lo / hi, [2] still outside */) {
+  using G = Geo<D>;
+  using FL = Fld<D>;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < (uint32_t)n; s += gridDim.x * blockDim.x) {
+    const size_t wt = word<D>(FL::TAG, s);
+    const uint32_t tag = state[wt];
+    if (tag_mat(tag) == MAT_DEAD) continue;
+    const int bx = (base_index(__uint_as_float(state[word<D>(FL::X, s)]), inv_dx) + half) >> G::LOG_LEAF;
+    const int dir = bx < slab.lo ? 0 : (bx >= slab.hi ? 1 : -1);
+    if (dir < 0) continue;
+    if (cap == 0) { state[wt] = make_tag(MAT_DEAD, tag_sid(tag)); continue; }
+    uint32_t* buf = dir == 0 ? buf_lo : buf_hi;
+    const unsigned long long idx = buf ? atomicAdd(&counters[dir], 1ull) : (unsigned long long)cap;
+    if (idx >= (unsigned long long)cap) { atomicAdd(&counters[2], 1ull); continue; }
+    uint32_t* m = buf + COMM_HEADER + idx;
+    for (int f = 0; f < FL::NV; ++f) m[(size_t)f * cap] = vword<D>(state, stat, f, s);
+    state[wt] = make_tag(MAT_DEAD, tag_sid(tag));
+  }
+}
+__global__ void k_rebalance_headers(uint32_t* buf_lo, uint32_t* buf_hi, int cap, const unsigned long long* counters) {
+  if (buf_lo) buf_lo[0] = (uint32_t)min(counters[0], (unsigned long long)cap);
+  if (buf_hi) buf_hi[0] = (uint32_t)min(counters[1], (unsigned long long)cap);
+}
+
 __global__ void k_mig_commit(uint32_t* from_lo, uint32_t* from_hi, int mig_cap, Status* st) {
   pdl_enter();
   if (st->err) return;

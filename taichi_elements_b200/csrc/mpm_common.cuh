@@ -37,6 +37,9 @@ static constexpr uint32_t TAG_SID = (1u << TAG_SHIFT) - 1u;
 __host__ __device__ inline uint32_t make_tag(uint32_t material, uint32_t sid) { return (material << TAG_SHIFT) | (sid & TAG_SID); }
 __host__ __device__ inline uint32_t tag_mat(uint32_t tag) { return tag >> TAG_SHIFT; }
 __host__ __device__ inline uint32_t tag_sid(uint32_t tag) { return tag & TAG_SID; }
+// Material code of a row that was handed to another rank while the cut planes were moved (mpm_rebalance_pack): the
+// binning and the local exports skip it whatever its position says; the next sort drops the row.
+static constexpr uint32_t MAT_DEAD = 7u;
 // Static per-particle attributes, indexed by sid (rows are appended, never moved by the substep; the distributed
 // solver compacts them between batches): packed colour, id (insertion index; global id with slabs), emitter id.
 struct Statics {

@@ -1427,7 +1427,7 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat,
     bool mine = s < (uint32_t)n;
     if (mine && slab.enabled) {
       const int bx = (base_index(__uint_as_float(vword<D>(state, stat, FL::X, s, quant)), inv_dx) + half) >> G::LOG_LEAF;
-      mine = bx >= slab.lo && bx < slab.hi;
+      mine = bx >= slab.lo && bx < slab.hi && tag_mat(load_tag_rt<D>(state, quant, s)) != MAT_DEAD;
     }
     const unsigned m = __ballot_sync(0xffffffffu, mine);
     unsigned long long base = 0;

@@ -426,6 +426,92 @@ def _make_distributed_solver():
             """Global maximum: with use_adaptive_dt every rank must derive the same dt (reference :762-770)."""
             return self._allmax_float(MPMSolver.compute_max_grid_velocity(self))
 
+        # ---- re-cutting ------------------------------------------------------------------
+        def _exchange_buffers(self, send, recv):
+            """Neighbour exchange of whole message buffers through torch.distributed (NCCL: device tensors; gloo -- several
+            ranks on one GPU in the tests -- through host copies).  Only the rare bulk moves use it."""
+            s = self.slab
+            if dist.get_backend(self.group) == 'gloo':
+                hs = [t.cpu() if t is not None else None for t in send]
+                hr = [torch.empty_like(t, device='cpu') if t is not None else None for t in recv]
+                neighbour_exchange(hs[0], hs[1], hr[0], hr[1], s.left, s.right, self.group)
+                for d, h in zip(recv, hr):
+                    if d is not None:
+                        d.copy_(h)
+            else:
+                torch.cuda.current_stream(self._device).synchronize()
+                neighbour_exchange(send[0], send[1], recv[0], recv[1], s.left, s.right, self.group)
+
+        def rebalance(self, cuts):
+            """Collective: move the cut planes to `cuts` (world - 1 absolute leaf-block x, the same on every rank) and
+            move the particles that change owner, in rounds of at most `mig_capacity` rows per side (a particle may hop
+            over several ranks).  Between batches only."""
+            cuts = [int(c) for c in cuts]
+            self.flush_migration()                       # nothing of the last substep may still be in flight
+            out3 = (ctypes.c_int64 * 3)()                # rows outside the OLD columns were delivered: retire them
+            self._check(self._lib.mpm_rebalance_pack(self._ctx, None, None, 0, out3, self._stream()), 'mpm_rebalance_pack')
+            self.slab = SlabDecomposition(self.world, self.rank, cuts, self.leaf_block_size, self.grid_size, self.inv_dx)
+            s = self.slab
+            self._check(self._lib.mpm_set_slab(self._ctx, 1, max(s.lo, INT_MIN), min(s.hi, INT_MAX)), 'mpm_set_slab')
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            moved = 0
+            for _ in range(10000):
+                glo, ghi = self._global_box()
+                if glo[0] > ghi[0]:
+                    break
+                self._batch_begin(glo, ghi)
+                out3 = (ctypes.c_int64 * 3)()
+                self._check(self._lib.mpm_rebalance_pack(self._ctx, ptr(self._mig_send[0]), ptr(self._mig_send[1]),
+                                                         self._mig_cap, out3, self._stream()), 'mpm_rebalance_pack')
+                self._exchange_buffers(self._mig_send, self._mig_recv)
+                self._check(self._lib.mpm_phase_unpack(self._ctx, ptr(self._mig_recv[0]), ptr(self._mig_recv[1]),
+                                                       self._stream()), 'mpm_phase_unpack')
+                if self._batch_end() != 0:
+                    raise _lib.MPMError('rebalance: ' + self._lib.mpm_last_error(self._ctx).decode())
+                for t in self._mig_send:
+                    if t is not None:
+                        t[0] = 0
+                sent, left = self._allreduce_ints([out3[0] + out3[1], out3[2]], dist.ReduceOp.SUM)
+                moved += sent
+                if sent == 0 and left == 0:
+                    break
+            self._next_box = None
+            return moved
+
+        def balance_cuts(self, cost):
+            """New cut planes that would give every rank the same share of `cost` (this rank's measured cost of a substep,
+            e.g. its P2G + G2P time), assuming the cost is spread evenly over the block columns a rank's particles occupy.
+            Collective; returns the same list on every rank."""
+            lo, hi = self._local_box()
+            half, leaf = self.grid_size // 2, self.leaf_block_size
+            have = self._n > 0 and lo[0] <= hi[0]
+            b0 = (lo[0] + half) // leaf if have else 0
+            b1 = (hi[0] + half) // leaf + 1 if have else 0
+            b0 = max(b0, self.slab.lo) if have else 0
+            b1 = min(b1, self.slab.hi) if have else 0
+            t = torch.tensor([float(cost) if have else 0.0, float(b0), float(b1)], dtype=torch.float64, device=self._coll_device())
+            allt = [torch.empty_like(t) for _ in range(self.world)]
+            if self.world > 1 and dist.is_initialized():
+                dist.all_gather(allt, t, group=self.group)
+            else:
+                allt = [t]
+            segs = [(float(a[1]), float(a[2]), float(a[0])) for a in allt if float(a[2]) > float(a[1]) and float(a[0]) > 0]
+            total = sum(c for _, _, c in segs)
+            if not segs or total <= 0:
+                return list(self.slab.cuts)
+            cuts, acc, k = [], 0.0, 1
+            for x0, x1, c in segs:
+                while k < self.world and acc + c >= total * k / self.world:
+                    frac = (total * k / self.world - acc) / c
+                    cuts.append(int(round(x0 + frac * (x1 - x0))))
+                    k += 1
+                acc += c
+            while len(cuts) < self.world - 1:
+                cuts.append(cuts[-1] + 1 if cuts else int(segs[-1][1]))
+            for i in range(1, len(cuts)):
+                cuts[i] = max(cuts[i], cuts[i - 1] + 1)
+            return cuts
+
         def reserve_blocks(self, max_blocks):
             """Pre-size the leaf-block workspace (a capacity miss cannot be retried inside a distributed batch)."""
             if max_blocks > self._max_blocks:
@@ -535,7 +621,7 @@ def _make_distributed_solver():
                 'Jp': fl[2 * d + 2 * dd].copy(), 'material': out[2 * d + 2 * dd + 1].copy(),
                 'color': out[2 * d + 2 * dd + 2].copy(), 'id': out[2 * d + 2 * dd + 3].copy(),
             }
-            keep = self.slab.mine(rows['x'][:, 0]) if n else np.zeros(0, bool)
+            keep = (self.slab.mine(rows['x'][:, 0]) & (rows['material'] != 7)) if n else np.zeros(0, bool)   # 7: retired by rebalance
             return {k: v[keep] for k, v in rows.items()}
 
         def gather_rows(self):

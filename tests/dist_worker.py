@@ -4,7 +4,8 @@
                        exchange, per-batch all-reduce -- runs on gloo, the data path is CUDA peer memory as usual)
     MPM_COMM         = auto | peer | nccl          MPM_FUSED_HALO = 1 | 0 (peer path: fused exchange or legacy kernels)
     MPM_SCENE        = mixed (five blobs crossing the cuts) | empty_rank (rank > 0 starts with no particle and receives
-                       them by migration, driven through the public step())
+                       them by migration, driven through the public step()) | rebalance (mixed, with the cut planes moved
+                       twice in mid-run: DistributedMPMSolver.rebalance / balance_cuts)
 """
 import os
 import sys
@@ -34,7 +35,7 @@ def main():
     comm = os.environ.get('MPM_COMM', 'auto')
     which = os.environ.get('MPM_SCENE', 'mixed')
     scene = []
-    if which == 'mixed':
+    if which in ('mixed', 'rebalance'):
         for i, (p, m, vel) in enumerate(mixed_scene(dim, n_per=500, seed=11)):
             vel = list(vel)
             vel[0] = 4.0 if i % 2 == 0 else -4.0
@@ -57,6 +58,21 @@ def main():
     n0 = s.n_particles[None]
     if which == 'mixed':
         s._run_substeps(dt, steps)
+    elif which == 'rebalance':
+        s._run_substeps(dt, 8)
+        moved = s.rebalance([c + 1 for c in cuts])      # shift the cuts by a column
+        counts = s._allreduce_ints([s.n_particles[None]], dist.ReduceOp.SUM)
+        s._run_substeps(dt, 8)
+        # cost-balanced cuts from a "cost" that is just the particle count: the ranks end up with similar counts
+        new_cuts = s.balance_cuts(float(len(s.particle_info()['id'])))
+        moved2 = s.rebalance(new_cuts)
+        s._run_substeps(dt, 8)
+        mine = len(s.particle_info()['id'])
+        allc = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allc, torch.tensor([mine], dtype=torch.int64)) if backend == 'gloo' else None
+        if rank == 0:
+            print('rebalance moved', moved, moved2, 'cuts', cuts, '->', new_cuts, 'counts', [int(c) for c in allc])
+        assert moved > 0
     else:
         assert (n0 > 0) == (rank == 0), (rank, n0)
         for _ in range(8):
@@ -71,7 +87,7 @@ def main():
         ref = MPMSolver((res, ) * dim, device=local)
         for p, m, vel in scene:
             ref.add_particles(p, m, velocity=vel)
-        if which == 'mixed':
+        if which in ('mixed', 'rebalance'):
             ref._run_substeps(dt, steps)
         else:
             for _ in range(8):

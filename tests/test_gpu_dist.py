@@ -167,6 +167,15 @@ def test_step_with_an_initially_empty_rank():
     _torchrun(2, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_SCENE': 'empty_rank'})
 
 
+@pytest.mark.parametrize('world', [2, 3])
+def test_rebalance_moves_the_cuts_in_mid_run(world):
+    """DistributedMPMSolver.rebalance: the cut planes are moved twice in mid-run (once by hand, once to the cuts
+    balance_cuts proposes); the particles that change owner are moved in bulk and the run still reproduces the
+    undecomposed solver (peer transport for the substeps, torch.distributed for the bulk moves; one GPU)."""
+    out = _torchrun(world, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_SCENE': 'rebalance'})
+    assert 'rebalance moved' in out
+
+
 def _loopback_ranks(world, res, cuts, **kw):
     from taichi_elements_b200.distributed import DistributedMPMSolver
     return [DistributedMPMSolver((res, ) * 3, cuts=cuts, world=world, rank=r, mig_capacity=1024, halo_capacity=256, **kw)
