@@ -111,6 +111,7 @@ struct mpm_ctx {
   int p2g_cfg = 0;
   int pdl = 1;                  // programmatic dependent launch along the substep chain (MPM_PDL)
   bool cell_zeroed = false, flags_zeroed = false;   // tables already cleared by k_clear_grid
+  int g2p_tile = 0;             // G2P tile staging: 0 cp.async per node, 1 cp.async.bulk per row (MPM_G2P_TILE)
   int pf_mode = 2;              // next-block L2 prefetch: cp.async.bulk.prefetch ranges (MPM_PREFETCH)
   int p2g_ver = 3;              // 3: mpm_p2g3.cuh (3D, dense binning); 2: mpm_p2g.cuh
   int p2g_variant = 1;   // 0 = shared-atomic scatter (first version), 1 = cell-owner
@@ -296,6 +297,7 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   if (const char* v = getenv("MPM_P2G_CFG")) ctx->p2g_cfg = atoi(v);
   if (const char* v = getenv("MPM_P2G_VER")) ctx->p2g_ver = atoi(v);
   if (const char* v = getenv("MPM_PREFETCH")) ctx->pf_mode = atoi(v);
+  if (const char* v = getenv("MPM_G2P_TILE")) ctx->g2p_tile = atoi(v);
   if (const char* v = getenv("MPM_PDL")) ctx->pdl = atoi(v);
   if (const char* v = getenv("MPM_FUSED_HALO")) ctx->fused_halo = atoi(v);
   if (const char* v = getenv("MPM_G2P2G")) ctx->fused_fast = strcmp(v, "simple") != 0;
@@ -790,14 +792,15 @@ static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
 }
 
 // G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
-template <int D, int T, int MB>
+template <int D, int T, int MB, bool BULK = false>
 static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   static LaunchCache lc;
-  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB>, T, 0);
-  launch_chain(ctx->pdl, k_g2p<D, T, MB>, grid, T, 0, s, a);
+  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB, BULK>, T, 0);
+  launch_chain(ctx->pdl, k_g2p<D, T, MB, BULK>, grid, T, 0, s, a);
 }
 template <int D>
 static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  if (ctx->g2p_tile == 1) { launch_g2p_cfg<D, 128, 5, true>(ctx, a, s); return; }   // cp.async.bulk rows + mbarrier
   switch (ctx->g2p_cfg) {
     case 1: launch_g2p_cfg<D, 256, 4>(ctx, a, s); break;
     case 2: launch_g2p_cfg<D, 128, 6>(ctx, a, s); break;

@@ -774,7 +774,7 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
 // Gather from the staged velocity tile, update v, C, x (engine/mpm_solver.py:
 // 694-724), write the particle to its sorted slot in the other state set, and
 // fold compute_max_velocity (:726-735) and the next bounding box into the pass.
-template <int D, int G2P_THREADS, int G2P_MINB>
+template <int D, int G2P_THREADS, int G2P_MINB, bool BULK = false>
 __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
@@ -814,7 +814,49 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (b < npb) stage_tile(b, tile_buf[0]);
+  // the same copy as bulk (TMA) transfers: the tile's z-rows are LEAF nodes of one leaf block followed by 2 nodes of its
+  // +z neighbour, i.e. one 64-byte and one 32-byte cp.async.bulk per row, completing on the buffer's mbarrier
+  constexpr int TROWS = G::TN / G::T;
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  constexpr bool bulk = BULK;   // MPM_G2P_TILE=1: measured 4 % slower than the per-node cp.async
+  auto stage_tile_bulk = [&](int blk, float4* dstt, unsigned long long* bar) {
+    if (tid < 2 * TROWS) {
+      const int row = tid >> 1, part = tid & 1;
+      int oct = part << (D - 1), cell = 0, r = row, c[D > 1 ? D - 1 : 1];
+#pragma unroll
+      for (int d = D - 2; d >= 0; --d) { c[d] = r % G::T; r /= G::T; }
+#pragma unroll
+      for (int d = 0; d < D - 1; ++d) {
+        const int hi = c[d] >= G::LEAF;
+        oct |= hi << d;
+        cell = (cell << G::LOG_LEAF) | (c[d] - hi * G::LEAF);
+      }
+      cell <<= G::LOG_LEAF;
+      const int slot = a.pb_nbr[blk * G::NO + oct];
+      const unsigned baddr = (unsigned)__cvta_generic_to_shared(bar);
+      if (slot >= 0) {
+        const unsigned bytes = part ? (G::T - G::LEAF) * 16u : G::LEAF * 16u;
+        const unsigned daddr = (unsigned)__cvta_generic_to_shared(dstt + row * G::T + part * G::LEAF);
+        const float4* src = a.grid + (size_t)slot * G::CELLS + cell;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(baddr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(daddr), "l"(src), "r"(bytes), "r"(baddr) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(baddr) : "memory");
+      }
+    }
+  };
+  if (bulk) {
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[i])), "r"(2 * TROWS) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  unsigned bar_phase = 0u;   // bit u: parity the next wait on buffer u expects
+  if (b < npb) { if (bulk) stage_tile_bulk(b, tile_buf[0], &s_bar[0]); else stage_tile(b, tile_buf[0]); }
   int u = 0;
   uint32_t prev_lin = 0u;
   bool have_prev = false;
@@ -860,15 +902,28 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       matn = ldu<D>(a.src, FL::TAG, p1);
     }
     float4* tile = tile_buf[u];
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (bulk) {
+      const unsigned baddr = (unsigned)__cvta_generic_to_shared(&s_bar[u]), par = (bar_phase >> u) & 1u;
+      unsigned done = 0u;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(baddr), "r"(par) : "memory");
+      bar_phase ^= 1u << u;
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
     if constexpr (D == 3) {
       // (vx, vy | vz, vz): the gather below works on packed pairs; every thread patches the nodes it copied
       for (int n = tid; n < G::TN; n += G2P_THREADS) tile[n].w = tile[n].z;
     }
+    // bulk copies write through the async proxy: order this CTA's generic accesses to both buffers before them
+    if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();   // tile complete; s_next visible; every warp is done with the previous block
     if (a.next_keys && have_prev) write_flags(prev_lin, &s_seen[u ^ 1]);
     const int nb_claim = s_next[u];
-    if (nb_claim < npb) stage_tile(nb_claim, tile_buf[u ^ 1]);
+    if (nb_claim < npb) {
+      if (bulk) stage_tile_bulk(nb_claim, tile_buf[u ^ 1], &s_bar[u ^ 1]); else stage_tile(nb_claim, tile_buf[u ^ 1]);
+    }
     {   // next block's particle rows towards L2 while this one computes
       const int nb = nb_claim;
       if (nb < npb && a.pf_mode) {
