@@ -218,6 +218,10 @@ int mpm_get_bbox(mpm_ctx* ctx, int32_t* bb_min, int32_t* bb_max, void* stream);
 /* key-layout box common to all ranks (the all-reduced bounding box), global signed cell indices */
 int mpm_set_layout_box(mpm_ctx* ctx, int32_t enabled, const int32_t* bb_min, const int32_t* bb_max);
 int mpm_batch_begin(mpm_ctx* ctx, void* stream);
+/* Right after mpm_batch_begin: dry run of the block discovery of the first substep; *need_blocks = leaf blocks the current
+ * particles occupy / reach.  A block-capacity miss cannot be retried inside a distributed batch (the neighbours have run
+ * ahead), so the host sizes `max_blocks` from this after seeding and keeps a margin afterwards.  Synchronises. */
+int mpm_batch_probe(mpm_ctx* ctx, int32_t* need_blocks, void* stream);
 int mpm_phase_unpack(mpm_ctx* ctx, const void* from_lo_dev, const void* from_hi_dev, void* stream);
 int mpm_phase_p2g(mpm_ctx* ctx, double dt, void* stream);
 int mpm_phase_halo_pack(mpm_ctx* ctx, void* stream);

@@ -98,6 +98,7 @@ SYMBOLS = [
     ('mpm_get_bbox', _i32, [_vp, _vp, _vp, _vp]),
     ('mpm_set_layout_box', _i32, [_vp, _i32, _vp, _vp]),
     ('mpm_batch_begin', _i32, [_vp, _vp]),
+    ('mpm_batch_probe', _i32, [_vp, ctypes.POINTER(_i32), _vp]),
     ('mpm_phase_unpack', _i32, [_vp, _vp, _vp, _vp]),
     ('mpm_phase_p2g', _i32, [_vp, _dbl, _vp]),
     ('mpm_phase_halo_pack', _i32, [_vp, _vp]),

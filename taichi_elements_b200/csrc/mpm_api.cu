@@ -1431,6 +1431,35 @@ extern "C" int mpm_phase_g2p(mpm_ctx* ctx, double dt, void* stream) {
 // DistributedMPMSolver.rebalance: one round of the bulk move after mpm_set_slab changed this rank's columns (see
 // k_rebalance_pack).  The buffers are LOCAL send buffers of the migration format (mpm_comm_bytes(dim, 0, cap)); the
 // host exchanges them and hands the received ones to mpm_phase_unpack.  out3 = rows sent to -x, to +x, rows still outside.
+// Dry run of the first substep's block discovery (keys, flags, scan): how many leaf blocks the current particles need.
+template <int D>
+static int probe_blocks(mpm_ctx* ctx, int32_t* need, cudaStream_t s) {
+  int nlin = 1;
+  for (int d = 0; d < D; ++d) nlin *= ctx->L.eb[d];
+  const int n = (int)ctx->n;
+  CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
+  k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, ctx->sm_count), 256, 0, s>>>(ctx->state[ctx->cur], ctx->cap, ctx->K.inv_dx, ctx->L,
+                                                                        ctx->slab, ctx->keys_a, ctx->flags, nlin, 0, ctx->d_status);
+  CK(cudaGetLastError());
+  { int rc = enqueue_scan(ctx, ctx->flags, ctx->fscan, 2 * nlin + 1, false, s); if (rc) return rc; }
+  int h[2] = {0, 0};
+  CK(cudaMemcpyAsync(&h[0], ctx->fscan + nlin, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h[1], ctx->fscan + 2 * nlin, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *need = std::max(h[0], h[1] - h[0]);
+  ctx->flags_zeroed = false;
+  ctx->keys_ready = false;
+  return MPM_OK;
+}
+extern "C" int mpm_batch_probe(mpm_ctx* ctx, int32_t* need_blocks, void* stream) {
+  REQUIRE_BATCH();
+  if (!need_blocks) return MPM_E_INVALID;
+  if (ctx->batch_enq > 0) return fail(ctx, MPM_E_INVALID, "mpm_batch_probe: only before the first substep of a batch");
+  *need_blocks = 0;
+  if (ctx->n == 0) return MPM_OK;
+  return ctx->dim == 3 ? probe_blocks<3>(ctx, need_blocks, s) : probe_blocks<2>(ctx, need_blocks, s);
+}
+
 extern "C" int mpm_rebalance_pack(mpm_ctx* ctx, void* send_lo_dev, void* send_hi_dev, int32_t cap, int64_t* out3,
                                   void* stream) {
   if (!ctx || !out3 || cap < 0) return MPM_E_INVALID;

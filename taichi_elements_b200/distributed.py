@@ -376,6 +376,15 @@ def _make_distributed_solver():
                 if glo[0] > ghi[0]:
                     return self.stats()          # no particles anywhere
                 self._batch_begin(glo, ghi)
+                if box is None:
+                    # particles were added or moved since the last batch: size the block workspace from a dry run of
+                    # the block discovery (a capacity miss inside a batch cannot be retried, the neighbours run ahead)
+                    need = ctypes.c_int32()
+                    self._check(self._lib.mpm_batch_probe(self._ctx, ctypes.byref(need), self._stream()), 'mpm_batch_probe')
+                    if need.value * 3 > self._max_blocks * 2:
+                        self._batch_end()
+                        self._rebind(max_blocks=2 * need.value)
+                        self._batch_begin(glo, ghi)
                 if self.comm == 'peer':
                     self._check(self._lib.mpm_peer_substeps(self._ctx, dt, nb, 0, self._stream()),
                                 'mpm_peer_substeps')
@@ -400,6 +409,9 @@ def _make_distributed_solver():
                                           'grown inside a distributed batch')
                 box = ([-v for v in r[1:4]], r[4:7])
                 left -= nb
+                need = max(st.n_particle_blocks, st.n_grid_blocks)      # keep a margin of 1.5x for the next batch
+                if need * 3 > self._max_blocks * 2:
+                    self._rebind(max_blocks=2 * need)
             self._next_box = box                  # valid until particles are added or cleared
             return self.stats()
 

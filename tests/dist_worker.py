@@ -53,7 +53,10 @@ def main():
                              device=local, comm=comm)
     for p, m, vel in scene:
         s.add_particles(p, m, velocity=vel)
-    s.reserve_blocks(4096)
+    if 'MPM_BLOCKS' in os.environ:
+        s._rebind(max_blocks=int(os.environ['MPM_BLOCKS']))      # too small on purpose: the solver must size it itself
+    else:
+        s.reserve_blocks(4096)
     dt = s.default_dt
     n0 = s.n_particles[None]
     if which == 'mixed':
@@ -101,6 +104,10 @@ def main():
               and np.array_equal(info['material'], ref.material.to_numpy()))
         print('comm', s.comm, 'scene', which, 'substeps', steps, 'max dx', np.abs(got['x'] - ref.x.to_numpy()).max(),
               'max dv', np.abs(got['v'] - ref.v.to_numpy()).max(), 'launches', s.stats().launches)
+    if 'MPM_BLOCKS' in os.environ:
+        ok = ok and s._max_blocks > int(os.environ['MPM_BLOCKS'])
+        if rank == 0:
+            print('blocks', os.environ['MPM_BLOCKS'], '->', s._max_blocks)
     if which == 'empty_rank' and world > 1:
         ok = ok and (s.n_particles[None] > 0 or rank == 0)          # the other ranks received particles
     flag = torch.tensor([int(ok)], device='cuda' if backend == 'nccl' else 'cpu')

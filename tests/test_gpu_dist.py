@@ -167,6 +167,13 @@ def test_step_with_an_initially_empty_rank():
     _torchrun(2, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_SCENE': 'empty_rank'})
 
 
+def test_block_workspace_is_sized_by_the_solver():
+    """A block-capacity miss cannot be retried inside a distributed batch: the solver sizes the workspace from a dry
+    run of the block discovery after seeding and keeps a margin between batches (here it starts far too small)."""
+    out = _torchrun(2, {'MPM_COMM': 'peer', 'MPM_DIST_BACKEND': 'gloo', 'MPM_BLOCKS': '24'})
+    assert 'blocks 24 ->' in out
+
+
 @pytest.mark.parametrize('world', [2, 3])
 def test_rebalance_moves_the_cuts_in_mid_run(world):
     """DistributedMPMSolver.rebalance: the cut planes are moved twice in mid-run (once by hand, once to the cuts
