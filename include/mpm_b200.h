@@ -246,8 +246,9 @@ int mpm_peer_substeps(mpm_ctx* ctx, double dt, int32_t count, int32_t deliver_on
  *   n <= bound capacity.  Synchronises.
  * mpm_seed_generate: the positions seed (:840-850, mode 1: lower, size) / seed_ellipsoid (:959-978, mode 2: center,
  *   radius) would give the particles with ids [id0, id0 + n), to x_out_dev[n][dim]; appends nothing.
- * mpm_export_local: particle_info (:1172-1180) of the rows this rank owns: [x[dim] v[dim] material color id] per
- *   row into out_dev (room for n_particles rows of 2 dim + 3 words), *count = rows written.  Synchronises. */
+ * mpm_export_local: particle_info (:1172-1180) of the rows this rank owns, compacted into field blocks sized for
+ *   n = n_particles rows each: out_dev = [x n*dim | v n*dim | material n | color n | id n] 32-bit words; the first
+ *   *count rows of every block are valid (each block is ready to be copied into its own host array).  Synchronises. */
 int mpm_seed_positions_slab(mpm_ctx* ctx, const float* x_dev, int64_t n, int64_t id_base, int32_t material,
                             int32_t color, const double* velocity, int32_t emitter, int64_t* kept, void* stream);
 int mpm_seed_generate(mpm_ctx* ctx, int32_t mode, int64_t n, int64_t id0, const double* a, const double* b,

@@ -1475,7 +1475,6 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat,
                                uint32_t* __restrict__ out, unsigned long long* __restrict__ count, int quant) {
   using G = Geo<D>;
   using FL = Fld<D>;
-  constexpr int W = 2 * D + 3;
   const int lane = threadIdx.x & 31;
   const uint32_t nround = ((uint32_t)n + 31u) & ~31u;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
@@ -1489,16 +1488,17 @@ __global__ void k_export_local(const uint32_t* __restrict__ state, Statics stat,
     if (lane == 0 && m) base = atomicAdd(count, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (!mine) continue;
-    uint32_t* o = out + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * W;
+    // field blocks sized for n rows each: [x n*D | v n*D | material n | colour n | id n]; the first *count rows are valid
+    const size_t r = (size_t)(base + __popc(m & ((1u << lane) - 1u))), nn = (size_t)n;
     float ex[D], ev[D];
     load_x_rt<D>(state, quant, s, ex);
     load_v_rt<D>(state, quant, s, ev);
 #pragma unroll
-    for (int d = 0; d < D; ++d) { o[d] = __float_as_uint(ex[d]); o[D + d] = __float_as_uint(ev[d]); }
+    for (int d = 0; d < D; ++d) { out[r * D + d] = __float_as_uint(ex[d]); out[nn * D + r * D + d] = __float_as_uint(ev[d]); }
     const uint32_t tag = load_tag_rt<D>(state, quant, s);
-    o[2 * D] = tag_mat(tag);
-    o[2 * D + 1] = stat.color[tag_sid(tag)];
-    o[2 * D + 2] = stat.gid[tag_sid(tag)];
+    out[2 * nn * D + r] = tag_mat(tag);
+    out[2 * nn * D + nn + r] = stat.color[tag_sid(tag)];
+    out[2 * nn * D + 2 * nn + r] = stat.gid[tag_sid(tag)];
   }
 }
 

@@ -560,20 +560,23 @@ def _make_distributed_solver():
             rows already handed to a neighbour are skipped.  One library kernel compacts the owned rows
             (mpm_export_local), one copy into pinned host memory."""
             n, d = self._n, self.dim
-            w = 2 * d + 3
             cnt = ctypes.c_int64()
+            names = (('position', d, np.float32), ('velocity', d, np.float32), ('material', 1, np.int32),
+                     ('color', 1, np.int32), ('id', 1, np.int32))
+            out = {}
             with torch.cuda.device(self._device):
-                dev = torch.empty((max(n, 1), w), dtype=torch.int32, device=self._device)
+                dev = torch.empty((max(n, 1) * (2 * d + 3), ), dtype=torch.int32, device=self._device)
                 self._check(self._lib.mpm_export_local(self._ctx, dev.data_ptr(), ctypes.byref(cnt), self._stream()),
                             'mpm_export_local')
-                k = int(cnt.value)
-                host = torch.empty((k, w), dtype=torch.int32, pin_memory=k > 0)
-                if k:
-                    host.copy_(dev[:k])
-            a = host.numpy()
-            return {'position': np.ascontiguousarray(a[:, 0:d]).view(np.float32),
-                    'velocity': np.ascontiguousarray(a[:, d:2 * d]).view(np.float32),
-                    'material': a[:, 2 * d].copy(), 'color': a[:, 2 * d + 1].copy(), 'id': a[:, 2 * d + 2].copy()}
+                k, off = int(cnt.value), 0
+                for name, width, dt in names:          # every field block goes straight into its own pinned array
+                    host = torch.empty((k * width, ), dtype=torch.int32, pin_memory=k > 0)
+                    if k:
+                        host.copy_(dev[off:off + k * width])
+                    a = host.numpy().view(dt)
+                    out[name] = a.reshape(k, width) if width > 1 else a
+                    off += n * width
+            return out
 
         # The insertion-order read-back paths of MPMSolver index device buffers by `id`, which is a permutation of
         # [0, n) only on a single-device solver.  Here ids are global: gather by id across the ranks instead.
