@@ -71,8 +71,9 @@ def main():
         moved2 = s.rebalance(new_cuts)
         s._run_substeps(dt, 8)
         mine = len(s.particle_info()['id'])
-        allc = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(allc, torch.tensor([mine], dtype=torch.int64)) if backend == 'gloo' else None
+        cdev = 'cpu' if backend == 'gloo' else 'cuda'
+        allc = [torch.zeros(1, dtype=torch.int64, device=cdev) for _ in range(world)]
+        dist.all_gather(allc, torch.tensor([mine], dtype=torch.int64, device=cdev))
         if rank == 0:
             print('rebalance moved', moved, moved2, 'cuts', cuts, '->', new_cuts, 'counts', [int(c) for c in allc])
         assert moved > 0

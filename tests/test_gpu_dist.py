@@ -149,6 +149,15 @@ def test_two_ranks_match_single_domain(comm):
     _torchrun(2, {'MPM_COMM': comm})
 
 
+def test_two_ranks_rebalance_over_nccl():
+    """The bulk move of a re-cut through NCCL send/recv of device buffers (the one-GPU variant below goes through gloo)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    out = _torchrun(2, {'MPM_COMM': 'peer', 'MPM_SCENE': 'rebalance'})
+    assert 'rebalance moved' in out
+
+
 @pytest.mark.parametrize('fused', ['1', '0'])
 @pytest.mark.parametrize('world', [2, 3])
 def test_peer_path_ranks_sharing_one_gpu(world, fused):
