@@ -571,7 +571,12 @@ def main():
     cells_active = int(st.n_grid_blocks) * 64
     n_now = mpm.n_particles[None]
     bpp = B_G2P2G_PARTICLE if args.g2p2g else B_PARTICLE
-    b_alg_p2g = B_P2G_PARTICLE * n_now + B_P2G_CELL * cells_active
+    bp2g = B_P2G_PARTICLE
+    if args.quant:       # bit-packed storage moves fewer bytes: count what THAT layout needs, not the f32 figure
+        # split: P2G reads xq vq Fq C Jp tag (80) + writes Fq Jp (24); G2P reads xq tag (12) + writes xq vq C tag (56)
+        # fused: reads and writes xq vq Fq Jp tag (44 + 44)
+        bpp, bp2g = (88, 88) if args.g2p2g else (172, 104)
+    b_alg_p2g = bp2g * n_now + B_P2G_CELL * cells_active
     b_alg_step = bpp * n_now + B_CELL * cells_active
     if world == 1:
         dom = max(phases, key=phases.get)

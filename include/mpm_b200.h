@@ -109,10 +109,12 @@ int mpm_abi_version(void);
 int mpm_state_fields(int dim);
 /* words of the read-back numbering (2*dim + 2*dim*dim + 5) */
 int mpm_virtual_fields(int dim);
-/* physical words per particle of THIS context: mpm_state_fields(dim), or 11 with the bit-packed storage of quant=True
- * (flags bits 0 and 1, dim 3; engine/mpm_solver.py:106-114, 216-247):  xq[2] vq[2] Fq[5] Jp tag
+/* physical words per particle of THIS context: mpm_state_fields(dim), or with the bit-packed storage of quant=True
+ * (flags bit 1, dim 3; engine/mpm_solver.py:106-114, 216-247):
+ *   with use_g2p2g (flags bit 0): 11 words  xq[2] vq[2] Fq[5] Jp tag          (C does not exist in that mode)
+ *   split substep:                20 words  xq[2] vq[2] Fq[5] Jp tag C[9]     (C stays f32, as in the reference)
  *   x  3 x 21-bit signed fixed point, range +-2.0; v  3 x 19-bit fractions sharing a 7-bit exponent;
- *   F  9 x 16-bit signed fixed point, range +-4.1 (csrc/mpm_quant.cuh).  C does not exist in that mode. */
+ *   F  9 x 16-bit signed fixed point, range +-4.1 (csrc/mpm_quant.cuh). */
 int mpm_ctx_state_fields(mpm_ctx* ctx);
 /* bytes the workspace must have for `capacity` particles and `max_blocks` leaf blocks */
 size_t mpm_workspace_bytes(int dim, int64_t capacity, int32_t max_blocks);

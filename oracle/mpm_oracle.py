@@ -193,8 +193,8 @@ class OracleMPM:
         self.grid_v = None
 
     def _packed(self):
-        """Bit-packed x / v / F storage: quant=True in 3D (:106-114, 216-247); only built for the g2p2g mode here."""
-        return bool(self.quant and self.use_g2p2g and self.dim == 3)
+        """Bit-packed x / v / F storage: quant=True in 3D (:106-114, 216-247); C stays f32 in the split mode (:101-102)."""
+        return bool(self.quant and self.dim == 3)
 
     @property
     def n_particles(self):
@@ -220,9 +220,9 @@ class OracleMPM:
         self.material = np.concatenate(
             [self.material, np.full(n, material, np.int32)])
         self.color = np.concatenate([self.color, np.full(n, color, np.int32)])
-        if self._packed():
-            from .quant_oracle import round_v, round_x
-            self.x, self.v = round_x(self.x), round_v(self.v)
+        if self._packed():                                        # seed_particle stores into the quantised fields (:826-830)
+            from .quant_oracle import round_F, round_v, round_x
+            self.x, self.v, self.F = round_x(self.x), round_v(self.v), round_F(self.F, self.F_bound)
 
     def add_sphere_collider(self, center, radius, surface=SURFACE_STICKY):
         self.colliders.append(Collider('sphere', center=list(center),
@@ -383,6 +383,9 @@ class OracleMPM:
             stress[sand] = _mm(_mm(_mm(U[sand], _diag(center)), _T(V[sand])),
                                _T(Fs))
         self.F = F.astype(f32)                                    # :567
+        if self._packed() and not g2p2g:                          # the store rounds F to its 16-bit grid (:113-114)
+            from .quant_oracle import round_F
+            self.F = round_F(self.F, self.F_bound)
         self.Jp = Jp.astype(f32)
         scale = f32(f32(f32(-dt * f32(self.p_vol)) * f32(4)) *
                     f32(self.inv_dx ** 2))                        # :569
@@ -530,7 +533,12 @@ class OracleMPM:
         mov = self.material != MATERIAL_STATIONARY                # :722-724
         self.v = np.where(mov[:, None], new_v, self.v).astype(f32)
         self.C = np.where(mov[:, None, None], new_C, self.C).astype(f32)
+        if self._packed():                                        # quantised fields: `self.v[p] = new_v` rounds, and
+            from .quant_oracle import round_v, round_x            # `self.x[p] += dt * self.v[p]` reads it back (:723-724)
+            self.v = round_v(self.v)
         self.x = np.where(mov[:, None], self.x + dt * self.v, self.x).astype(f32)
+        if self._packed():
+            self.x = round_x(self.x)
 
     # ---- fused mode (:363-485, host :773-787) ------------------------------------
     def _lin(self, cells):

@@ -29,7 +29,7 @@ struct mpm_ctx {
   Statics stat{nullptr, nullptr, nullptr};   // static side arrays [3][cap]: colour, id, emitter by sid
   int64_t n_static = 0;                       // rows of them in use
   int nv = 0;                                 // virtual words of the read-back numbering (Fld::NV)
-  int quant = 0;                              // packed x / v / F storage (quant=True with use_g2p2g, 3D; mpm_quant.cuh)
+  int quant = 0;                              // packed x / v / F storage (quant=True, 3D; mpm_quant.cuh): 1 with use_g2p2g, 2 split
   size_t cap = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -246,8 +246,9 @@ extern "C" int mpm_create(const mpm_params* p, mpm_ctx** out) {
   mpm_ctx* ctx = new mpm_ctx();
   ctx->P = *p;
   ctx->dim = p->dim;
-  ctx->quant = ((p->flags & 2) && (p->flags & 1) && p->dim == 3) ? 1 : 0;
-  ctx->nf = ctx->quant ? FldQ3::N : mpm_state_fields(p->dim);
+  // quant=True (flags bit 1) in 3D: bit-packed x / v / F; 1 = with use_g2p2g (no C), 2 = split substep (f32 C kept)
+  ctx->quant = ((p->flags & 2) && p->dim == 3) ? ((p->flags & 1) ? 1 : 2) : 0;
+  ctx->nf = ctx->quant ? quant_words(ctx->quant) : mpm_state_fields(p->dim);
   ctx->nv = p->dim == 3 ? Fld<3>::NV : Fld<2>::NV;
   ctx->cells = p->dim == 3 ? 64 : 256;
   ctx->no = p->dim == 3 ? 8 : 4;
@@ -723,6 +724,22 @@ static int update_layout(mpm_ctx* ctx) {
   return MPM_OK;
 }
 
+// Modes that only exist on the counting-sort path (use_g2p2g, quant=True): when the flag table of the current particle box
+// does not fit the table this workspace was sized for, ask the host for a larger one (the table grows with max_blocks).
+static int need_dense_table(mpm_ctx* ctx, const char* what) {
+  double nlin = 1.0;
+  for (int d = 0; d < ctx->dim; ++d) nlin *= (double)ctx->L.eb[d];
+  if (ctx->use_dense && 2.0 * nlin + 1.0 <= (double)((int64_t)1 << 24) && ctx->table_cap < ((int64_t)1 << 24)) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "%s: the block table (%lld entries) is too small for the particle box (%.0f blocks); grow max_blocks (%d)",
+             what, (long long)ctx->table_cap, nlin, ctx->max_blocks);
+    ctx->err = buf;
+    ctx->layout_valid = false;
+    return MPM_E_BLOCK_CAPACITY;
+  }
+  return fail(ctx, MPM_E_KEY_BITS, std::string(what) + " needs the counting-sort path (particle box too large for the flag table)");
+}
+
 // Launch configuration of one kernel instance, per device: the dynamic shared-memory opt-in
 // (cudaFuncSetAttribute) and the occupancy-derived persistent grid apply to the CURRENT device only, and a
 // process may drive several GPUs from several host threads (one ctx per device).
@@ -769,6 +786,13 @@ static void launch_p2g3_cfg(mpm_ctx* ctx, const SubstepArgs<3>& a, cudaStream_t 
 template <int D>
 static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   if constexpr (D == 3) {
+    if (ctx->quant == 2) {     // quant=True, split substep: the cell-owner kernel on the packed accessors
+      constexpr size_t smem = p2g3_smem_bytes<640>();
+      static LaunchCache lcq;
+      const int grid = cached_grid(lcq, ctx, k_p2g3<640, 4, false, false, true>, P2G3::T, smem);
+      launch_chain(ctx->pdl, k_p2g3<640, 4, false, false, true>, grid, P2G3::T, smem, s, a);
+      return;
+    }
     if (ctx->p2g_ver == 3 && a.cellstart) {
       switch (ctx->p2g_cfg) {
         case 1: launch_p2g3_cfg<768, 4>(ctx, a, s); break;
@@ -792,14 +816,17 @@ static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
 }
 
 // G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
-template <int D, int T, int MB, bool BULK = false>
+template <int D, int T, int MB, bool BULK = false, int QM = 0>
 static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   static LaunchCache lc;
-  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB, BULK>, T, 0);
-  launch_chain(ctx->pdl, k_g2p<D, T, MB, BULK>, grid, T, 0, s, a);
+  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB, BULK, QM>, T, 0);
+  launch_chain(ctx->pdl, k_g2p<D, T, MB, BULK, QM>, grid, T, 0, s, a);
 }
 template <int D>
 static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
+  if constexpr (D == 3) {
+    if (ctx->quant == 2) { launch_g2p_cfg<3, 128, 5, false, 2>(ctx, a, s); return; }   // quant=True, split substep
+  }
   if (ctx->g2p_tile == 1) { launch_g2p_cfg<D, 128, 5, true>(ctx, a, s); return; }   // cp.async.bulk rows + mbarrier
   switch (ctx->g2p_cfg) {
     case 1: launch_g2p_cfg<D, 256, 4>(ctx, a, s); break;
@@ -887,8 +914,17 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     const bool fused_keys = ctx->keys_ready;   // keys and flags were written by the previous substep's G2P
     if (!fused_keys) {
       CK(cudaMemsetAsync(ctx->flags, 0, (size_t)(2 * nlin + 1) * 4, s));
-      k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
-                                                         nlin, commit_prev, st);
+      bool done = false;
+      if constexpr (D == 3) {
+        if (ctx->quant == 2) {
+          k_bin_keys<3, 2><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a,
+                                                                       ctx->flags, nlin, commit_prev, st);
+          done = true;
+        }
+      }
+      if (!done)
+        k_bin_keys<D><<<gs_blocks((n + 3) / 4, 256, sm), 256, 0, s>>>(src, ctx->cap, ctx->K.inv_dx, ctx->L, ctx->slab, ctx->keys_a, ctx->flags,
+                                                           nlin, commit_prev, st);
     }
     ctx->keys_ready = false;
     // (a substep whose keys came from G2P is committed by the scan's first thread)
@@ -909,6 +945,7 @@ static int enqueue_bin_p2g(mpm_ctx* ctx, float dt, int cur, int commit_prev, cud
     ctx->launches += ctx->own_scan ? (fused_keys ? 5 : 6) : 4;   // (large tables: a scan may still go to CUB)
   } else {
     // ---- fallback: multi-pass LSD radix sort + sorted-candidate block list
+    if (ctx->quant) return fail(ctx, MPM_E_KEY_BITS, "quant=True needs the counting-sort path (particle box too large for the flag table)");
     if (commit_prev) k_end<<<1, 1, 0, s>>>(st);
     k_reset<<<1, 1, 0, s>>>(st);
     k_keys<D><<<gs_blocks(n, 256, sm), 256, 0, s>>>(src, ctx->cap, n, ctx->K.inv_dx, ctx->L, ctx->keys_a, ctx->vals_a, st);
@@ -1107,7 +1144,7 @@ static int substeps_g2p2g(mpm_ctx* ctx, float dt, int count, cudaStream_t s) {
     if (rc) return rc;
     rc = update_layout(ctx);
     if (rc) return rc;
-    if (!ctx->dense) return fail(ctx, MPM_E_INVALID, "use_g2p2g needs the dense block table (particle box too large)");
+    if (!ctx->dense) return need_dense_table(ctx, "use_g2p2g");
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
     const int cur0 = ctx->cur, sel0 = ctx->sel;
@@ -1193,6 +1230,7 @@ extern "C" int mpm_substeps(mpm_ctx* ctx, double dt, double t, int32_t count, vo
     if (rc) return rc;
     rc = update_layout(ctx);
     if (rc) return rc;
+    if (ctx->quant && !ctx->dense) return need_dense_table(ctx, "quant=True");
     CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(Status), s));
     k_batch_begin<<<1, 1, 0, s>>>(ctx->d_status, (int)ctx->n, (int)ctx->n_static);
     const int cur0 = ctx->cur;
@@ -1262,6 +1300,7 @@ extern "C" int mpm_substep(mpm_ctx* ctx, double dt, double t, void* stream) {
 // ------------------------------------------------------------------ phase API (multi-GPU driver)
 extern "C" int mpm_set_slab(mpm_ctx* ctx, int32_t enabled, int32_t lo_block, int32_t hi_block) {
   if (!ctx || (enabled && lo_block >= hi_block)) return fail(ctx, MPM_E_INVALID, "mpm_set_slab: empty slab");
+  if (enabled && ctx->quant) return fail(ctx, MPM_E_INVALID, "mpm_set_slab: the slab decomposition runs on f32 storage (quant=False)");
   ctx->slab.enabled = enabled ? 1 : 0;
   ctx->slab.lo = enabled ? lo_block : INT_MIN;
   ctx->slab.hi = enabled ? hi_block : INT_MAX;
@@ -1453,6 +1492,7 @@ static int probe_blocks(mpm_ctx* ctx, int32_t* need, cudaStream_t s) {
 }
 extern "C" int mpm_batch_probe(mpm_ctx* ctx, int32_t* need_blocks, void* stream) {
   REQUIRE_BATCH();
+  if (ctx->quant) return fail(ctx, MPM_E_INVALID, "mpm_batch_probe: f32 storage only");
   if (!need_blocks) return MPM_E_INVALID;
   if (ctx->batch_enq > 0) return fail(ctx, MPM_E_INVALID, "mpm_batch_probe: only before the first substep of a batch");
   *need_blocks = 0;

@@ -41,7 +41,7 @@ __device__ __forceinline__ void commit_substep(Status* st) {
 // The three per-particle passes below are pure streaming kernels whose speed is set by
 // the number of bytes in flight, so every thread handles FOUR consecutive particles with
 // 128-bit loads/stores (capacity is a multiple of 64, rows are 16-byte aligned).
-template <int D>
+template <int D, int QM = 0>      // QM: storage mode of PStore (0 f32 words, 2 bit-packed x of quant=True)
 __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float inv_dx, KeyLayout L, Slab slab,
                            uint32_t* __restrict__ keys, int* __restrict__ flags, int nlin, int commit_prev,
                            Status* st) {
@@ -52,12 +52,24 @@ __global__ void k_bin_keys(const uint32_t* __restrict__ state, size_t cap, float
   const uint32_t nquad = ((uint32_t)n + 3u) >> 2;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nquad; t += gridDim.x * blockDim.x) {
     float4 xs[D];
+    if constexpr (QM == 0) {
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      xs[d] = __ldg(reinterpret_cast<const float4*>(state + word<D>(Fld<D>::X + d, 4u * t)));   // 4 particles of one tile row
+      for (int d = 0; d < D; ++d)
+        xs[d] = __ldg(reinterpret_cast<const float4*>(state + word<D>(Fld<D>::X + d, 4u * t)));   // 4 particles of one tile row
+    } else {
+      using P = PStore<D, QM>;
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(state + P::w(P::X, 4u * t)));
+      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(state + P::w(P::X + 1, 4u * t)));
+      const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+      float xd[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const uint32_t w[2] = {w0[j], w1[j]}; decode_x3(w, xd[j]); }
+#pragma unroll
+      for (int d = 0; d < D; ++d) xs[d] = make_float4(xd[0][d], xd[1][d], xd[2][d], xd[3][d]);
+    }
     // with slabs a row can be DEAD (handed over while the cuts moved, mpm_rebalance_pack): its position no longer counts
     uint4 tg = make_uint4(0, 0, 0, 0);
-    if (slab.enabled) tg = __ldg(reinterpret_cast<const uint4*>(state + word<D>(Fld<D>::TAG, 4u * t)));
+    if (slab.enabled) tg = __ldg(reinterpret_cast<const uint4*>(state + PStore<D, QM>::w(PStore<D, QM>::TAG, 4u * t)));
     uint32_t out[4];
     uint32_t prev_lin = 0xFFFFFFFFu, prev_om = 0;
 #pragma unroll

@@ -42,14 +42,17 @@ template <int D> __device__ __forceinline__ void stu(uint32_t* __restrict__ s, i
   s[word<D>(f, p)] = v;
 }
 
-// ---- particle storage accessors.  Q = false: the f32 words of Fld<D>.  Q = true (quant=True with use_g2p2g, 3D):
-// bit-packed words  xq[2] vq[2] Fq[5] Jp tag  = 11 words (44 B per set instead of 104; mpm_quant.cuh, ref :216-247);
-// C does not exist in that mode (a register value of the fused kernel, ref :102-103).
-struct FldQ3 { static constexpr int X = 0, V = 2, F = 4, JP = 9, TAG = 10, N = 11; };
-template <int D, bool Q> struct PStore;
-template <int D> struct PStore<D, false> {
+// ---- particle storage accessors.  Q = 0: the f32 words of Fld<D>.  quant=True in 3D stores x, v and F bit-packed
+// (mpm_quant.cuh, ref :106-114, 216-247):
+//   Q = 1 (with use_g2p2g):   xq[2] vq[2] Fq[5] Jp tag        = 11 words (44 B per set instead of 104); C does not exist
+//                             in that mode (a register value of the fused kernel, ref :102-103)
+//   Q = 2 (split substep):    xq[2] vq[2] Fq[5] Jp tag C[9]   = 20 words (80 B); C stays f32 as in the reference (:101-102, 219-220)
+struct FldQ3 { static constexpr int X = 0, V = 2, F = 4, JP = 9, TAG = 10, C = 11, N = 11, NC = 20; };
+__host__ __device__ __forceinline__ int quant_words(int quant) { return quant == 2 ? FldQ3::NC : FldQ3::N; }
+template <int D, int Q> struct PStore;
+template <int D> struct PStore<D, 0> {
   using FL = Fld<D>;
-  static constexpr int N = FL::N, JP = FL::JP, TAG = FL::TAG;
+  static constexpr int N = FL::N, JP = FL::JP, TAG = FL::TAG, C = FL::C, X = FL::X, XW = D;
   static __device__ __forceinline__ size_t w(int f, uint32_t p) { return word<D>(f, p); }
   static __device__ __forceinline__ void load_x(const uint32_t* __restrict__ s, uint32_t p, float* x) {
 #pragma unroll
@@ -78,10 +81,15 @@ template <int D> struct PStore<D, false> {
   // what a store keeps (the fused kernel reads x and v back after storing them, ref :401-409)
   static __device__ __forceinline__ void round_x(float*) {}
   static __device__ __forceinline__ void round_v(float*) {}
+  // round + keep the encoded words for the store that follows (one encode instead of three with packed storage)
+  static __device__ __forceinline__ void round_x(float*, uint32_t*) {}
+  static __device__ __forceinline__ void round_v(float*, uint32_t*) {}
+  static __device__ __forceinline__ void put_x(uint32_t* __restrict__ s, uint32_t p, const float* x, const uint32_t*) { store_x(s, p, x); }
+  static __device__ __forceinline__ void put_v(uint32_t* __restrict__ s, uint32_t p, const float* v, const uint32_t*) { store_v(s, p, v); }
 };
-template <> struct PStore<3, true> {
-  static constexpr int N = FldQ3::N, JP = FldQ3::JP, TAG = FldQ3::TAG;
-  static __device__ __forceinline__ size_t w(int f, uint32_t p) { return word_nf<FldQ3::N>(f, p); }
+template <int NW> struct PStoreQ3 {
+  static constexpr int N = NW, JP = FldQ3::JP, TAG = FldQ3::TAG, C = FldQ3::C, X = FldQ3::X, XW = 2;
+  static __device__ __forceinline__ size_t w(int f, uint32_t p) { return word_nf<NW>(f, p); }
   static __device__ __forceinline__ void load_x(const uint32_t* __restrict__ s, uint32_t p, float* x) {
     const uint32_t q[2] = {__ldg(s + w(FldQ3::X, p)), __ldg(s + w(FldQ3::X + 1, p))};
     decode_x3(q, x);
@@ -114,19 +122,38 @@ template <> struct PStore<3, true> {
   }
   static __device__ __forceinline__ void round_x(float* x) { round_x3(x); }
   static __device__ __forceinline__ void round_v(float* v) { round_v3(v); }
+  static __device__ __forceinline__ void round_x(float* x, uint32_t* q) { encode_x3(x, q); decode_x3(q, x); }
+  static __device__ __forceinline__ void round_v(float* v, uint32_t* q) { encode_v3(v, q); decode_v3(q, v); }
+  static __device__ __forceinline__ void put_x(uint32_t* __restrict__ s, uint32_t p, const float*, const uint32_t* q) {
+    s[w(FldQ3::X, p)] = q[0]; s[w(FldQ3::X + 1, p)] = q[1];
+  }
+  static __device__ __forceinline__ void put_v(uint32_t* __restrict__ s, uint32_t p, const float*, const uint32_t* q) {
+    s[w(FldQ3::V, p)] = q[0]; s[w(FldQ3::V + 1, p)] = q[1];
+  }
 };
-// run-time selection for the utility kernels (seeding, boxes, read-back): quant != 0 only exists in 3D
+template <> struct PStore<3, 1> : PStoreQ3<FldQ3::N> {};
+template <> struct PStore<3, 2> : PStoreQ3<FldQ3::NC> {};
+// run-time selection for the utility kernels (seeding, boxes, read-back): quant (0, 1, 2 = Q above) != 0 only exists in 3D
 template <int D> __device__ __forceinline__ void load_x_rt(const uint32_t* __restrict__ s, int quant, uint32_t p, float* x) {
-  if constexpr (D == 3) { if (quant) { PStore<3, true>::load_x(s, p, x); return; } }
-  PStore<D, false>::load_x(s, p, x);
+  if constexpr (D == 3) {
+    if (quant == 1) { PStore<3, 1>::load_x(s, p, x); return; }
+    if (quant == 2) { PStore<3, 2>::load_x(s, p, x); return; }
+  }
+  PStore<D, 0>::load_x(s, p, x);
 }
 template <int D> __device__ __forceinline__ void load_v_rt(const uint32_t* __restrict__ s, int quant, uint32_t p, float* v) {
-  if constexpr (D == 3) { if (quant) { PStore<3, true>::load_v(s, p, v); return; } }
-  PStore<D, false>::load_v(s, p, v);
+  if constexpr (D == 3) {
+    if (quant == 1) { PStore<3, 1>::load_v(s, p, v); return; }
+    if (quant == 2) { PStore<3, 2>::load_v(s, p, v); return; }
+  }
+  PStore<D, 0>::load_v(s, p, v);
+}
+template <int D> __device__ __forceinline__ size_t tag_word_rt(int quant, uint32_t p) {
+  if constexpr (D == 3) { if (quant) return word_rt(quant_words(quant), FldQ3::TAG, p); }
+  return word<D>(Fld<D>::TAG, p);
 }
 template <int D> __device__ __forceinline__ uint32_t load_tag_rt(const uint32_t* __restrict__ s, int quant, uint32_t p) {
-  if constexpr (D == 3) { if (quant) return __ldg(s + PStore<3, true>::w(FldQ3::TAG, p)); }
-  return ldu<D>(s, Fld<D>::TAG, p);
+  return __ldg(s + tag_word_rt<D>(quant, p));
 }
 
 // virtual word `f` (read-back ABI numbering, Fld<D>::NV words) of the particle in storage slot s
@@ -134,16 +161,24 @@ template <int D> __device__ __forceinline__ uint32_t vword(const uint32_t* __res
                                                           int quant = 0) {
   using FL = Fld<D>;
   if constexpr (D == 3) {
-    if (quant) {             // packed storage: decode the group the word belongs to (C does not exist: zeros)
+    if (quant) {             // packed storage: decode the group the word belongs to
+      const int nw = quant_words(quant);
       if (f < FL::F) {
         float t[3];
-        if (f < FL::V) PStore<3, true>::load_x(state, s, t); else PStore<3, true>::load_v(state, s, t);
+        if (f < FL::V) load_x_rt<3>(state, quant, s, t); else load_v_rt<3>(state, quant, s, t);
         return __float_as_uint(t[f < FL::V ? f : f - FL::V]);
       }
-      if (f < FL::C) { float F[9]; PStore<3, true>::load_F(state, s, F); return __float_as_uint(F[f - FL::F]); }
-      if (f < FL::JP) return 0u;
-      if (f == FL::JP) return state[PStore<3, true>::w(FldQ3::JP, s)];
-      const uint32_t tq = state[PStore<3, true>::w(FldQ3::TAG, s)];
+      if (f < FL::C) {
+        uint32_t q[5];
+        float F[9];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) q[i] = state[word_rt(nw, FldQ3::F + i, s)];
+        decode_F9(q, F);
+        return __float_as_uint(F[f - FL::F]);
+      }
+      if (f < FL::JP) return quant == 2 ? state[word_rt(nw, FldQ3::C + (f - FL::C), s)] : 0u;   // (no C with use_g2p2g: zeros)
+      if (f == FL::JP) return state[word_rt(nw, FldQ3::JP, s)];
+      const uint32_t tq = state[word_rt(nw, FldQ3::TAG, s)];
       if (f == FL::MAT) return tag_mat(tq);
       const uint32_t sq = tag_sid(tq);
       return f == FL::COLOR ? st.color[sq] : (f == FL::ID ? st.gid[sq] : st.emit[sq]);
@@ -774,10 +809,11 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
 // Gather from the staged velocity tile, update v, C, x (engine/mpm_solver.py:
 // 694-724), write the particle to its sorted slot in the other state set, and
 // fold compute_max_velocity (:726-735) and the next bounding box into the pass.
-template <int D, int G2P_THREADS, int G2P_MINB, bool BULK = false>
+template <int D, int G2P_THREADS, int G2P_MINB, bool BULK = false, int QM = 0>
 __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
+  using P = PStore<D, QM>;      // QM = 2: quant=True, packed x / v (a store rounds, ref :106-111, 720-724) + f32 C
   // The velocity tile of the NEXT block is fetched with cp.async into the other buffer while this
   // block's particles are gathered: one CTA barrier per block, no exposed grid-load latency.
   __shared__ float4 tile_buf[2][G::TN];
@@ -897,9 +933,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
     for (int d = 0; d < D; ++d) xn[d] = 0.0f;
     if (s < end) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) xn[d] = ldf<D>(a.src, FL::X + d, p1);
-      matn = ldu<D>(a.src, FL::TAG, p1);
+      P::load_x(a.src, p1, xn);
+      matn = __ldg(a.src + P::w(P::TAG, p1));
     }
     float4* tile = tile_buf[u];
     if (bulk) {
@@ -931,9 +966,9 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
         const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
         for (int i = tid; i < 2 * nt; i += G2P_THREADS) {
-          const uint32_t* tile0 = a.src + (size_t)(t0 + (i >> 1)) * FL::N * TILE;
-          if (i & 1) prefetch_l2_range(tile0 + FL::TAG * TILE, TILE * 4u);
-          else prefetch_l2_range(tile0 + FL::X * TILE, (uint32_t)D * TILE * 4u);
+          const uint32_t* tile0 = a.src + (size_t)(t0 + (i >> 1)) * P::N * TILE;
+          if (i & 1) prefetch_l2_range(tile0 + P::TAG * TILE, TILE * 4u);
+          else prefetch_l2_range(tile0 + P::X * TILE, (uint32_t)P::XW * TILE * 4u);
         }
         if (tid == G2P_THREADS - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
       }
@@ -947,9 +982,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       const uint32_t tag = matn, mat = tag_mat(tag);      // material | static row: the only immutable word that travels
       p1 = p2;
       if (s + G2P_THREADS < end) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) xn[d] = ldf<D>(a.src, FL::X + d, p1);
-        matn = ldu<D>(a.src, FL::TAG, p1);
+        P::load_x(a.src, p1, xn);
+        matn = __ldg(a.src + P::w(P::TAG, p1));
       }
       p2 = s + 2 * G2P_THREADS < end ? a.perm[s + 2 * G2P_THREADS] : 0u;
 #pragma unroll
@@ -1044,22 +1078,27 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       if (mat == (uint32_t)STATIONARY) {                       // :722
         // The x + (-0) identity consumes each load INSIDE this rare branch: otherwise the stores after
         // the join wait on a scoreboard shared with the next particle's prefetched loads.
+        P::load_v(a.src, p, nv);
 #pragma unroll
-        for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(ldf<D>(a.src, FL::V + d, p), -0.0f);
+        for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(nv[d], -0.0f);
         if (!a.K.g2p2g) {      // [g2p2g] C is a register value there: the gathered C is used (:385, 414)
 #pragma unroll
-          for (int i = 0; i < D * D; ++i) nC[i] = __fadd_rn(ldf<D>(a.src, FL::C + i, p), -0.0f);
+          for (int i = 0; i < D * D; ++i) nC[i] = __fadd_rn(__uint_as_float(__ldg(a.src + P::w(P::C + i, p))), -0.0f);
         }
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, nv[d]));   // :724
       }
+      uint32_t qx[2], qv[2];                                                          // packed storage: the stored words
+      P::round_v(nv, qv);                                                             // self.v[p] = new_v rounds (:723)
+      if (mat != (uint32_t)STATIONARY) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, nv[d]));   // :724, reads v[p] back
+      }
+      P::round_x(x, qx);
       uint32_t nlin_key = 0, ncell = 0, nsp = 0;
       bool nbad = false;
+      P::put_x(a.dst, s, x, qx);
+      P::put_v(a.dst, s, nv, qv);
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        stf<D>(a.dst, FL::X + d, s, x[d]);
-        stf<D>(a.dst, FL::V + d, s, nv[d]);
         vmax = fmaxf(vmax, fabsf(nv[d]));
         int nb = base_index(x[d], a.K.inv_dx);
         lo[d] = min(lo[d], nb); hi[d] = max(hi[d], nb);
@@ -1098,8 +1137,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         }
       }
 #pragma unroll
-      for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::C + i, s, nC[i]);
-      if (a.slab.enabled) {
+      for (int i = 0; i < D * D; ++i) a.dst[P::w(P::C + i, s)] = __float_as_uint(nC[i]);
+      if constexpr (QM == 0) if (a.slab.enabled) {
         // slab decomposition: the particle now belongs to a neighbour rank -> hand it over
         const int nbx = (base_index(x[0], a.K.inv_dx) + a.L.half) >> G::LOG_LEAF;
         const int dir = nbx < a.slab.lo ? 0 : (nbx >= a.slab.hi ? 1 : -1);
@@ -1128,7 +1167,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
           }
         }
       }
-      stu<D>(a.dst, FL::TAG, s, tag);
+      a.dst[P::w(P::TAG, s)] = tag;
     }
     if (a.next_keys) {
       seen = __reduce_or_sync(0xffffffffu, seen);
@@ -1286,13 +1325,22 @@ __global__ void k_seed(SeedArgs a) {
     }
     const uint32_t sidq = (uint32_t)(a.sid0 + i);
     if constexpr (D == 3) {
-      if (a.quant) {                                           // packed storage: x, v, F = I, Jp, tag
+      if (a.quant) {                                           // packed storage: x, v, F = I, Jp, tag [, C = 0]
         const float Fi[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-        PStore<3, true>::store_x(a.state, p, x);
-        PStore<3, true>::store_v(a.state, p, v);
-        PStore<3, true>::store_F(a.state, p, Fi);
-        a.state[PStore<3, true>::w(FldQ3::JP, p)] = __float_as_uint(material == SAND ? 0.0f : 1.0f);
-        a.state[PStore<3, true>::w(FldQ3::TAG, p)] = make_tag((uint32_t)material, sidq);
+        const float jp0 = material == SAND ? 0.0f : 1.0f;
+        if (a.quant == 1) {
+          using P = PStore<3, 1>;
+          P::store_x(a.state, p, x); P::store_v(a.state, p, v); P::store_F(a.state, p, Fi);
+          a.state[P::w(P::JP, p)] = __float_as_uint(jp0);
+          a.state[P::w(P::TAG, p)] = make_tag((uint32_t)material, sidq);
+        } else {
+          using P = PStore<3, 2>;
+          P::store_x(a.state, p, x); P::store_v(a.state, p, v); P::store_F(a.state, p, Fi);
+          a.state[P::w(P::JP, p)] = __float_as_uint(jp0);
+          a.state[P::w(P::TAG, p)] = make_tag((uint32_t)material, sidq);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) a.state[P::w(P::C + i, p)] = 0u;
+        }
         a.stat.color[sidq] = (uint32_t)color; a.stat.gid[sidq] = (uint32_t)id; a.stat.emit[sidq] = (uint32_t)a.emitter;
         continue;
       }
@@ -1461,8 +1509,7 @@ __global__ void k_compact_statics(uint32_t* __restrict__ state, Statics stat, in
       tmp[s] = stat.color[sid]; tmp[(size_t)n + s] = stat.gid[sid]; tmp[2 * (size_t)n + s] = stat.emit[sid];
     } else {
       stat.color[s] = tmp[s]; stat.gid[s] = tmp[(size_t)n + s]; stat.emit[s] = tmp[2 * (size_t)n + s];
-      size_t w = word<D>(Fld<D>::TAG, s);
-      if constexpr (D == 3) { if (quant) w = PStore<3, true>::w(FldQ3::TAG, s); }
+      const size_t w = tag_word_rt<D>(quant, s);
       state[w] = make_tag(tag_mat(state[w]), s);
     }
   }

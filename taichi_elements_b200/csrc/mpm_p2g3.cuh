@@ -178,7 +178,7 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         const uint32_t p = pq[0];
 #pragma unroll
         for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
-        using P = PStore<3, Q>;                                  // f32 words, or the packed storage of quant=True
+        using P = PStore<3, Q ? 1 : 0>;                          // f32 words, or the packed storage of quant=True
         float x[D], v[D], fx[D], C[D * D];
         P::load_x(a.src, p, x);
         P::load_v(a.src, p, v);
@@ -204,15 +204,16 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
 #pragma unroll
           for (int i = 0; i < D * D; ++i) C[i] = 0.0f;                                 // :396-399
         }
+        uint32_t qx[2], qv[2];                    // packed storage: the stored words
+        P::round_v(v, qv);                        // (`self.v[p] = new_v` rounds, the advection reads it back)
         if (mat != (uint32_t)STATIONARY) {
-          P::round_v(v);                          // (packed storage: `self.v[p] = new_v` rounds, the advection reads it back)
 #pragma unroll
           for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], __fmul_rn(a.dt, v[d]));  // :401-403
-          P::round_x(x);                          // (and the P2G half reads the stored x, :406)
         }
+        P::round_x(x, qx);                        // (and the P2G half reads the stored x, :406)
         particle_update<D>(a.K, a.dt, (int)mat, F, C, Jp, aff, mass);
-        P::store_x(a.dst, s, x);
-        P::store_v(a.dst, s, v);
+        P::put_x(a.dst, s, x, qx);
+        P::put_v(a.dst, s, v, qv);
         P::store_F(a.dst, s, F);
         a.dst[P::w(P::JP, s)] = __float_as_uint(Jp);
         a.dst[P::w(P::TAG, s)] = tag;
@@ -242,24 +243,19 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         const uint32_t p = pq[0];
 #pragma unroll
         for (int k = 0; k + 1 < NIT; ++k) pq[k] = pq[k + 1];
+        using P = PStore<3, Q ? 2 : 0>;                            // f32 words, or quant=True: packed x v F + f32 C
         float x[D], v[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          x[d] = ldf<D>(a.src, FL::X + d, p);
-          v[d] = ldf<D>(a.src, FL::V + d, p);
-        }
+        P::load_x(a.src, p, x);
+        P::load_v(a.src, p, v);
         float F[D * D], C[D * D], aff[D * D], mass;
+        P::load_F(a.src, p, F);
 #pragma unroll
-        for (int i = 0; i < D * D; ++i) {
-          F[i] = ldf<D>(a.src, FL::F + i, p);
-          C[i] = ldf<D>(a.src, FL::C + i, p);
-        }
-        float Jp = ldf<D>(a.src, FL::JP, p);
-        const int mat = (int)tag_mat(ldu<D>(a.src, FL::TAG, p));
+        for (int i = 0; i < D * D; ++i) C[i] = __uint_as_float(__ldg(a.src + P::w(P::C + i, p)));
+        float Jp = __uint_as_float(__ldg(a.src + P::w(P::JP, p)));
+        const int mat = (int)tag_mat(__ldg(a.src + P::w(P::TAG, p)));
         particle_update<D>(a.K, a.dt, mat, F, C, Jp, aff, mass);
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
-        stf<D>(a.dst, FL::JP, s, Jp);
+        P::store_F(a.dst, s, F);                                   // (quant: the store rounds F to its 16-bit grid, :567)
+        a.dst[P::w(P::JP, s)] = __float_as_uint(Jp);
         float fx[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
@@ -280,7 +276,7 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
           // every word P2G reads (x .. material) is in the first FL::TAG + 1 rows of the block's tiles
           const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
           const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
-          constexpr int NW = PStore<3, Q>::N;                      // words per particle of the storage in use
+          constexpr int NW = PStore<3, Q ? (G2P2G ? 1 : 2) : 0>::N;     // words per particle of the storage in use
           for (int i = tid; i < nt; i += T)
             prefetch_l2_range(a.src + (size_t)(t0 + i) * NW * TILE, (uint32_t)NW * TILE * 4u);
           if (tid == T - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);

@@ -16,10 +16,26 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "mpm_math.cuh"
 
 namespace mpm {
+
+MPM_HD uint32_t f2u_(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+MPM_HD float u2f_(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
 
 // ---- x: 3 x 21 bits in two words
 MPM_HD void encode_x3(const float* x, uint32_t* w) {
@@ -45,12 +61,12 @@ MPM_HD void encode_v3(const float* v, uint32_t* w) {
   const float a = fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2])));
   int e = -64;
   if (a > 0.0f && a == a) {
-    int ex;
-    frexpf(a, &ex);                 // a = f * 2^ex, f in [0.5, 1): floor(log2 a) = ex - 1
-    e = ex - 1;
+    // floor(log2 a) is the biased exponent field - 127 for a normal number; zero and denormals (field 0) lie below 2^-64
+    // and clamp to -64 either way
+    e = (int)(f2u_(a) >> 23) - 127;
     e = e < -64 ? -64 : (e > 63 ? 63 : e);
   }
-  const float inv = ldexpf(1.0f, 17 - e);
+  const float inv = u2f_((uint32_t)(17 - e + 127) << 23);      // 2^(17 - e), exponent in [-46, 81]
   const int lim = (1 << (QV_FRAC - 1)) - 1;
   const unsigned long long m = (1ull << QV_FRAC) - 1ull;
   unsigned long long p = 0;
@@ -67,7 +83,7 @@ MPM_HD void encode_v3(const float* v, uint32_t* w) {
 MPM_HD void decode_v3(const uint32_t* w, float* v) {
   const unsigned long long p = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
   const int e = (int)((p >> (3 * QV_FRAC)) & 127ull) - 64;
-  const float s = ldexpf(1.0f, e - 17);
+  const float s = u2f_((uint32_t)(e - 17 + 127) << 23);        // 2^(e - 17), exponent in [-81, 46]
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const int q = (int)((uint32_t)(p >> (QV_FRAC * d)) << (32 - QV_FRAC)) >> (32 - QV_FRAC);

@@ -106,6 +106,8 @@ def _make_distributed_solver():
                      world=None, rank=None, comm='auto', **kw):
             if kw.get('use_g2p2g'):
                 raise NotImplementedError('use_g2p2g is single-GPU in this build')
+            if kw.get('quant') and len(res) == 3:
+                raise NotImplementedError('quant=True (bit-packed storage) is single-GPU in this build')
             super().__init__(res, **kw)
             self.group = group
             # 'peer': kernels write into the neighbour's buffers over NVLink (CUDA IPC), no NCCL per

@@ -127,13 +127,13 @@ class MPMSolver:
                  device=None):
         self.dim = len(res)
         assert self.dim in (2, 3), "MPM solver supports only 2D and 3D simulations."
-        # quant=True (:106-114, 216-262): with use_g2p2g in 3D -- the combination the reference's large scenes use --
-        # x, v and F are stored bit-packed (44 B per particle and set instead of 104; csrc/mpm_quant.cuh).  Otherwise
-        # the state stays f32: same API, unquantised (more accurate) numbers.
-        self.packed_storage = bool(quant and use_g2p2g and self.dim == 3)
+        # quant=True (:106-114, 216-262) in 3D: x, v and F are stored bit-packed (csrc/mpm_quant.cuh) -- with use_g2p2g
+        # 44 B per particle and set instead of 104 (no C), with the split substep 80 B (C stays f32, as in the
+        # reference).  In 2D the state stays f32: same API, unquantised (more accurate) numbers.
+        self.packed_storage = bool(quant and self.dim == 3)
         if quant and not self.packed_storage:
             import warnings
-            warnings.warn('quant=True without use_g2p2g (or in 2D): particle state is kept in f32 in this build')
+            warnings.warn('quant=True in 2D: particle state is kept in f32 in this build')
         self.quant = quant
         self.use_g2p2g = use_g2p2g
         self.v_clamp_g2p2g = v_clamp_g2p2g

@@ -173,3 +173,54 @@ def test_quantised_storage_with_g2p2g():
     s.add_particles(extra, 1)
     assert np.array_equal(s.x.to_numpy()[:len(x)], x)
     assert s._run_substeps(dt, 3).substeps_done == 3 and np.isfinite(s.x.to_numpy()).all()
+
+
+def test_quantised_storage_with_the_split_substep():
+    """quant=True, use_g2p2g=False in 3D -- what the reference's demo_3d_bunnies.py (BASELINE configs[2]) runs: x, v and
+    F bit-packed, C kept in f32 (ref engine/mpm_solver.py:101-114, 216-247) = 20 words per particle instead of 26.  P2G
+    decodes, stores the rounded F; G2P stores the rounded v, advects with it and stores the rounded x (:567, 723-724).
+    One substep and 30 substeps against the oracle that rounds at the same stores; read-back, export, growth."""
+    import tempfile
+    from oracle import quant_oracle as q
+    from oracle.mpm_oracle import OracleMPM
+    from taichi_elements_b200.engine.mpm_solver import MPMSolver
+    from taichi_elements_b200.engine.particle_io import ParticleIO
+    s = MPMSolver((64, ) * 3, quant=True)
+    assert s.packed_storage and s._nf == 20 and tuple(s._state.shape[2:]) == (20, 32)
+    assert s.particle._cell_size_bytes == 92                                       # 80 B per set + 12 B static row
+    o = OracleMPM((64, ) * 3, quant=True)
+    rng = np.random.default_rng(5)
+    for m, lo in ((2, 0.30), (3, 0.55), (0, 0.42), (1, 0.62), (4, 0.2)):
+        p = (rng.random((1500, 3)) * 0.1 + lo).astype(np.float32)
+        o.add_particles(p, m, velocity=[-0.5, -0.5, 0.2])
+        s.add_particles(p, m, velocity=[-0.5, -0.5, 0.2])
+    n = s.n_particles[None]
+    assert np.array_equal(s.x.to_numpy(), o.x) and np.array_equal(s.v.to_numpy(), o.v)   # seeded = rounded, both sides
+    assert np.array_equal(s.F.to_numpy(), np.tile(q.round_F(np.eye(3, dtype=np.float32)), (n, 1, 1)))
+    for m in (o, s):
+        m.add_surface_collider((0.5, 0.28, 0.5), (0.0, 1.0, 0.0), 1, 0.3)
+    dt = o.default_dt
+    o.substep(dt)
+    assert s._run_substeps(dt, 1).substeps_done == 1
+    err = state_errors(s, o)
+    assert max(err[k] for k in ('x', 'v', 'Jp', 'C')) <= 1e-4 and err['F'] <= 1.3e-4, err   # F: one step of its 16-bit grid
+    for _ in range(29):
+        o.substep(dt)
+    assert s._run_substeps(dt, 29).substeps_done == 29             # batches: the fused key pass bins the ROUNDED positions
+    err = tracking_errors(s, o)
+    assert max(err[k] for k in ('x', 'v', 'F', 'Jp')) <= 5e-3, err
+    x, v, F = s.x.to_numpy(), s.v.to_numpy(), s.F.to_numpy()
+    assert np.array_equal(q.round_x(x), x) and np.array_equal(q.round_v(v), v) and np.array_equal(q.round_F(F), F)
+    assert np.abs(s.C.to_numpy()).max() > 0                        # C exists in this mode
+    stat = s.material.to_numpy() == 4
+    assert np.array_equal(x[stat], o.x[stat]) and np.all(v[stat] == q.round_v(np.float32([[-0.5, -0.5, 0.2]])))
+    with tempfile.TemporaryDirectory() as d:
+        s.write_particles(d + '/a.npz')
+        ParticleIO.write_arrays(d + '/b.npz', x, v, s.color.to_numpy())
+        a, b = np.load(d + '/a.npz'), np.load(d + '/b.npz')
+        for k in ('ranges', 'x_and_v', 'color'):
+            assert np.array_equal(a[k], b[k]), k
+    extra = (rng.random((40000, 3)) * 0.2 + 0.35).astype(np.float32)
+    s.add_particles(extra, 1)                                      # capacity growth keeps the packed rows
+    assert np.array_equal(s.x.to_numpy()[:len(x)], x) and np.array_equal(s.C.to_numpy()[:len(x)], s.C.to_numpy()[:len(x)])
+    assert s._run_substeps(dt, 3).substeps_done == 3 and np.isfinite(s.x.to_numpy()).all()

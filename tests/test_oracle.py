@@ -174,3 +174,27 @@ def test_c_restatement_matches_numpy_oracle(dim):
         b.substep(dt)
     assert rel_err(b.x, a.x, 1.0) < 1e-4 and rel_err(b.v, a.v, vs) < 5e-3 and rel_err(b.F, a.F, 1.0) < 1e-3
     assert np.abs(b.Jp - a.Jp).max() < 1e-3
+
+
+def test_quantised_split_substep_rounds_at_the_stores():
+    """quant=True without use_g2p2g in 3D (ref :101-114, 216-247, 567, 723-724): after every substep x, v and F lie on
+    their fixed-point / shared-exponent grids, C stays f32, and x advanced with the ROUNDED velocity."""
+    from oracle import quant_oracle as q
+    o, ref = OracleMPM((32, ) * 3, quant=True), OracleMPM((32, ) * 3)
+    for m in (o, ref):
+        for p, mat, vel in mixed_scene(3, n_per=60, seed=4):
+            m.add_particles(p, mat, velocity=vel)
+    assert np.array_equal(o.x, q.round_x(ref.x))
+    dt = o.default_dt
+    x0 = o.x.copy()
+    o.substep(dt)
+    ref.substep(dt)
+    assert np.array_equal(q.round_x(o.x), o.x) and np.array_equal(q.round_v(o.v), o.v) and np.array_equal(q.round_F(o.F), o.F)
+    mov = o.material != MATERIAL_STATIONARY
+    assert np.array_equal(o.x[mov], q.round_x((x0 + np.float32(dt) * o.v).astype(np.float32))[mov])
+    assert np.abs(o.C).max() > 0 and not np.array_equal(q.round_F(o.C), o.C)            # C is not quantised
+    assert rel_err(o.x, ref.x) < 1e-5 and np.abs(o.F - ref.F).max() < 2e-4                # close to the f32 run
+    # 2D keeps f32 storage in this build
+    o2 = OracleMPM((32, ) * 2, quant=True)
+    o2.add_particles(np.float32([[0.51234567, 0.5]]), MATERIAL_ELASTIC)
+    assert o2.x[0, 0] == np.float32(0.51234567)
