@@ -504,7 +504,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='multimat_100m')
     ap.add_argument('--repeats', type=int, default=0, help='timed repeats of K steps (0: until --min-seconds, >= 3)')
-    ap.add_argument('--min-seconds', type=float, default=1.5)
+    ap.add_argument('--min-seconds', type=float, default=1.0, help='the K-step timing is repeated until this much wall time is covered')
     ap.add_argument('--batch', type=int, default=20, help='N > 1: substeps enqueued per host synchronisation')
     ap.add_argument('--preroll', type=int, default=-1, help='untimed substeps before the warm-up (-1: the workload\'s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
