@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, 'libmpm_b200.so')
+LIB_PATH = os.environ.get('MPM_B200_LIB') or os.path.join(_HERE, 'libmpm_b200.so')   # (override: A/B builds of the kernels)
 CSRC = os.path.join(_HERE, 'csrc')
 
 MPM_OK = 0
