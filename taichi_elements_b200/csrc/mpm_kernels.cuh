@@ -62,6 +62,11 @@ template <int D> struct PStore<D, 0> {
 #pragma unroll
     for (int d = 0; d < D; ++d) v[d] = ldf<D>(s, FL::V + d, p);
   }
+  // coherent loads: from a set the same kernel also writes (G2P reads x at the sorted slot and stores the new x there)
+  static __device__ __forceinline__ void load_x_rw(const uint32_t* s, uint32_t p, float* x) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = __uint_as_float(s[word<D>(FL::X + d, p)]);
+  }
   static __device__ __forceinline__ void load_F(const uint32_t* __restrict__ s, uint32_t p, float* F) {
 #pragma unroll
     for (int i = 0; i < D * D; ++i) F[i] = ldf<D>(s, FL::F + i, p);
@@ -97,6 +102,10 @@ template <int NW> struct PStoreQ3 {
   static __device__ __forceinline__ void load_v(const uint32_t* __restrict__ s, uint32_t p, float* v) {
     const uint32_t q[2] = {__ldg(s + w(FldQ3::V, p)), __ldg(s + w(FldQ3::V + 1, p))};
     decode_v3(q, v);
+  }
+  static __device__ __forceinline__ void load_x_rw(const uint32_t* s, uint32_t p, float* x) {
+    const uint32_t q[2] = {s[w(FldQ3::X, p)], s[w(FldQ3::X + 1, p)]};
+    decode_x3(q, x);
   }
   static __device__ __forceinline__ void load_F(const uint32_t* __restrict__ s, uint32_t p, float* F) {
     uint32_t q[5];
@@ -614,6 +623,9 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(SubstepArgs<D> a) {
 #pragma unroll
       for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
       stf<D>(a.dst, FL::JP, s, Jp);
+#pragma unroll
+      for (int d = 0; d < D; ++d) stf<D>(a.dst, FL::X + d, s, x[d]);   // G2P reads x and the tag at the sorted slot
+      stu<D>(a.dst, FL::TAG, s, ldu<D>(a.src, FL::TAG, p));
       float mv[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) mv[d] = mass * v[d];
@@ -922,19 +934,16 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
       for (int d = 0; d < D; ++d) org[d] = (rel[d] + a.L.ob[d]) << G::LOG_LEAF;
     }
-    // software pipeline over this thread's particles: `perm` runs two iterations
-    // ahead and the position/material loads one iteration ahead of the arithmetic, so
-    // the dependent perm -> x latency chain overlaps the previous particle's math
+    // software pipeline over this thread's particles: the position / tag loads run one iteration ahead of the arithmetic
     int s = start + tid;
-    uint32_t p1 = s < end ? a.perm[s] : 0u;
-    uint32_t p2 = s + G2P_THREADS < end ? a.perm[s + G2P_THREADS] : 0u;
     float xn[D];
     uint32_t matn = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) xn[d] = 0.0f;
+    // P2G left x and the tag of every particle at its SORTED slot of the other set: streaming reads, no perm -> x chain
     if (s < end) {
-      P::load_x(a.src, p1, xn);
-      matn = __ldg(a.src + P::w(P::TAG, p1));
+      P::load_x_rw(a.dst, s, xn);
+      matn = a.dst[P::w(P::TAG, s)];
     }
     float4* tile = tile_buf[u];
     if (bulk) {
@@ -962,30 +971,26 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     {   // next block's particle rows towards L2 while this one computes
       const int nb = nb_claim;
       if (nb < npb && a.pf_mode) {
-        // the rows G2P reads (x and the tag: two runs of 128-byte rows per tile) and perm
+        // the rows G2P reads: x and the tag of the block's own sorted slots (two runs of 128-byte rows per tile)
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
         const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
         for (int i = tid; i < 2 * nt; i += G2P_THREADS) {
-          const uint32_t* tile0 = a.src + (size_t)(t0 + (i >> 1)) * P::N * TILE;
+          const uint32_t* tile0 = a.dst + (size_t)(t0 + (i >> 1)) * P::N * TILE;
           if (i & 1) prefetch_l2_range(tile0 + P::TAG * TILE, TILE * 4u);
           else prefetch_l2_range(tile0 + P::X * TILE, (uint32_t)P::XW * TILE * 4u);
         }
-        if (tid == G2P_THREADS - 1) prefetch_l2_range(a.perm + ns, (uint32_t)(ne - ns) * 4u);
       }
     }
     for (; s < end; s += G2P_THREADS) {
-      const uint32_t p = p1;
       float x[D], fx[D], w[3][D];
       int l[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) x[d] = xn[d];
       const uint32_t tag = matn, mat = tag_mat(tag);      // material | static row: the only immutable word that travels
-      p1 = p2;
       if (s + G2P_THREADS < end) {
-        P::load_x(a.src, p1, xn);
-        matn = __ldg(a.src + P::w(P::TAG, p1));
+        P::load_x_rw(a.dst, s + G2P_THREADS, xn);
+        matn = a.dst[P::w(P::TAG, s + G2P_THREADS)];
       }
-      p2 = s + 2 * G2P_THREADS < end ? a.perm[s + 2 * G2P_THREADS] : 0u;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         int base = base_index(x[d], a.K.inv_dx);
@@ -1078,6 +1083,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       if (mat == (uint32_t)STATIONARY) {                       // :722
         // The x + (-0) identity consumes each load INSIDE this rare branch: otherwise the stores after
         // the join wait on a scoreboard shared with the next particle's prefetched loads.
+        const uint32_t p = a.perm[s];
         P::load_v(a.src, p, nv);
 #pragma unroll
         for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(nv[d], -0.0f);
@@ -1167,7 +1173,6 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
           }
         }
       }
-      a.dst[P::w(P::TAG, s)] = tag;
     }
     if (a.next_keys) {
       seen = __reduce_or_sync(0xffffffffu, seen);

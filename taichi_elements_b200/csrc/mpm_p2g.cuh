@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(P2GCfg<D>::THREADS, MINB) k_p2g_cell(SubstepAr
         for (int i = 0; i < D * D; ++i) stf<D>(a.dst, FL::F + i, s, F[i]);
         stf<D>(a.dst, FL::JP, s, Jp);
 #pragma unroll
+        for (int d = 0; d < D; ++d) stf<D>(a.dst, FL::X + d, s, x[d]);   // G2P reads x and the tag at the sorted slot
+        stu<D>(a.dst, FL::TAG, s, ldu<D>(a.src, FL::TAG, p));
+#pragma unroll
         for (int d = 0; d < D; ++d) {
           const int base = base_index(x[d], a.K.inv_dx);
           pay[d * CH + q] = x[d] * a.K.inv_dx - (float)base;            // fx (:503)
