@@ -816,16 +816,18 @@ static void launch_p2g(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
 }
 
 // G2P launch configurations (threads per CTA, min CTAs per SM); MPM_G2P_CFG picks one.
-template <int D, int T, int MB, bool BULK = false, int QM = 0>
+template <int D, int T, int MB, bool BULK = false, int QM = 0, bool XS = true>
 static void launch_g2p_cfg(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   static LaunchCache lc;
-  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB, BULK, QM>, T, 0);
-  launch_chain(ctx->pdl, k_g2p<D, T, MB, BULK, QM>, grid, T, 0, s, a);
+  const int grid = cached_grid(lc, ctx, k_g2p<D, T, MB, BULK, QM, XS>, T, 0);
+  launch_chain(ctx->pdl, k_g2p<D, T, MB, BULK, QM, XS>, grid, T, 0, s, a);
 }
 template <int D>
 static void launch_g2p(mpm_ctx* ctx, const SubstepArgs<D>& a, cudaStream_t s) {
   if constexpr (D == 3) {
     if (ctx->quant == 2) { launch_g2p_cfg<3, 128, 5, false, 2>(ctx, a, s); return; }   // quant=True, split substep
+    // after the halo variant of k_p2g3 (which does not copy x / tag to the sorted slot): follow perm
+    if (a.cb.fused) { launch_g2p_cfg<3, 128, 5, false, 0, false>(ctx, a, s); return; }
   }
   if (ctx->g2p_tile == 1) { launch_g2p_cfg<D, 128, 5, true>(ctx, a, s); return; }   // cp.async.bulk rows + mbarrier
   switch (ctx->g2p_cfg) {

@@ -821,7 +821,10 @@ __global__ void k_grid_op(float4* __restrict__ grid, const uint32_t* __restrict_
 // Gather from the staged velocity tile, update v, C, x (engine/mpm_solver.py:
 // 694-724), write the particle to its sorted slot in the other state set, and
 // fold compute_max_velocity (:726-735) and the next bounding box into the pass.
-template <int D, int G2P_THREADS, int G2P_MINB, bool BULK = false, int QM = 0>
+// XS: P2G left x and the tag at the sorted slot of the other set (every P2G kernel except the halo variant of k_p2g3, which
+// is at its register limit and measured 3-7 % slower with the four extra stores): G2P streams them.  Otherwise it follows
+// perm to the live set, as P2G does, and moves the tag itself.
+template <int D, int G2P_THREADS, int G2P_MINB, bool BULK = false, int QM = 0, bool XS = true>
 __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a) {
   using G = Geo<D>;
   using FL = Fld<D>;
@@ -940,10 +943,20 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
     uint32_t matn = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) xn[d] = 0.0f;
-    // P2G left x and the tag of every particle at its SORTED slot of the other set: streaming reads, no perm -> x chain
-    if (s < end) {
-      P::load_x_rw(a.dst, s, xn);
-      matn = a.dst[P::w(P::TAG, s)];
+    uint32_t p1 = 0u, p2 = 0u;      // (!XS) `perm` runs two iterations ahead, the loads one
+    if constexpr (XS) {
+      // P2G left x and the tag of every particle at its SORTED slot of the other set: streaming reads, no perm -> x chain
+      if (s < end) {
+        P::load_x_rw(a.dst, s, xn);
+        matn = a.dst[P::w(P::TAG, s)];
+      }
+    } else {
+      p1 = s < end ? a.perm[s] : 0u;
+      p2 = s + G2P_THREADS < end ? a.perm[s + G2P_THREADS] : 0u;
+      if (s < end) {
+        P::load_x(a.src, p1, xn);
+        matn = __ldg(a.src + P::w(P::TAG, p1));
+      }
     }
     float4* tile = tile_buf[u];
     if (bulk) {
@@ -975,7 +988,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
         const int ns = a.pb_start[nb], ne = a.pb_start[nb + 1];
         const int t0 = ns >> TILE_LOG, nt = ((ne - 1) >> TILE_LOG) - t0 + 1;
         for (int i = tid; i < 2 * nt; i += G2P_THREADS) {
-          const uint32_t* tile0 = a.dst + (size_t)(t0 + (i >> 1)) * P::N * TILE;
+          const uint32_t* tile0 = (XS ? a.dst : a.src) + (size_t)(t0 + (i >> 1)) * P::N * TILE;
           if (i & 1) prefetch_l2_range(tile0 + P::TAG * TILE, TILE * 4u);
           else prefetch_l2_range(tile0 + P::X * TILE, (uint32_t)P::XW * TILE * 4u);
         }
@@ -987,9 +1000,19 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
 #pragma unroll
       for (int d = 0; d < D; ++d) x[d] = xn[d];
       const uint32_t tag = matn, mat = tag_mat(tag);      // material | static row: the only immutable word that travels
-      if (s + G2P_THREADS < end) {
-        P::load_x_rw(a.dst, s + G2P_THREADS, xn);
-        matn = a.dst[P::w(P::TAG, s + G2P_THREADS)];
+      const uint32_t pcur = p1;
+      if constexpr (XS) {
+        if (s + G2P_THREADS < end) {
+          P::load_x_rw(a.dst, s + G2P_THREADS, xn);
+          matn = a.dst[P::w(P::TAG, s + G2P_THREADS)];
+        }
+      } else {
+        p1 = p2;
+        if (s + G2P_THREADS < end) {
+          P::load_x(a.src, p1, xn);
+          matn = __ldg(a.src + P::w(P::TAG, p1));
+        }
+        p2 = s + 2 * G2P_THREADS < end ? a.perm[s + 2 * G2P_THREADS] : 0u;
       }
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -1083,7 +1106,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
       if (mat == (uint32_t)STATIONARY) {                       // :722
         // The x + (-0) identity consumes each load INSIDE this rare branch: otherwise the stores after
         // the join wait on a scoreboard shared with the next particle's prefetched loads.
-        const uint32_t p = a.perm[s];
+        const uint32_t p = XS ? a.perm[s] : pcur;
         P::load_v(a.src, p, nv);
 #pragma unroll
         for (int d = 0; d < D; ++d) nv[d] = __fadd_rn(nv[d], -0.0f);
@@ -1173,6 +1196,7 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_MINB) k_g2p(SubstepArgs<D> a)
           }
         }
       }
+      if constexpr (!XS) a.dst[P::w(P::TAG, s)] = tag;
     }
     if (a.next_keys) {
       seen = __reduce_or_sync(0xffffffffu, seen);

@@ -257,9 +257,12 @@ k_p2g3(typename std::conditional<G2P2G, FusedArgs<3>, SubstepArgs<3>>::type arg)
         P::store_F(a.dst, s, F);                                   // (quant: the store rounds F to its 16-bit grid, :567)
         a.dst[P::w(P::JP, s)] = __float_as_uint(Jp);
         // x and the tag go to the sorted slot as well (raw words): G2P then streams them instead of chasing perm -> x
+        // (not in the halo variant: it is at its register limit and measured 3-7 % slower with them; k_g2p<.., XS = false>)
+        if constexpr (!FUSED) {
 #pragma unroll
-        for (int i = 0; i < P::XW; ++i) a.dst[P::w(P::X + i, s)] = __ldg(a.src + P::w(P::X + i, p));
-        a.dst[P::w(P::TAG, s)] = __ldg(a.src + P::w(P::TAG, p));
+          for (int i = 0; i < P::XW; ++i) a.dst[P::w(P::X + i, s)] = __ldg(a.src + P::w(P::X + i, p));
+          a.dst[P::w(P::TAG, s)] = __ldg(a.src + P::w(P::TAG, p));
+        }
         float fx[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) fx[d] = x[d] * a.K.inv_dx - (float)base_index(x[d], a.K.inv_dx);   // :503
