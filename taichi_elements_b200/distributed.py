@@ -65,6 +65,28 @@ class SlabDecomposition:
         return cuts
 
     @staticmethod
+    def cost_balanced_cuts(segments, world, fallback):
+        """Cut planes that give every rank the same share of a measured cost.  `segments` = per rank, in rank order,
+        (first block column, one past the last, cost): the cost of a rank is taken as spread evenly over the columns its
+        particles occupy.  Ranks without particles or cost are skipped; with nothing to go by the `fallback` cuts stay."""
+        segs = [(float(x0), float(x1), float(c)) for x0, x1, c in segments if x1 > x0 and c > 0]
+        total = sum(c for _, _, c in segs)
+        if not segs or total <= 0:
+            return list(fallback)
+        cuts, acc, k = [], 0.0, 1
+        for x0, x1, c in segs:
+            while k < world and acc + c >= total * k / world:
+                frac = (total * k / world - acc) / c
+                cuts.append(int(round(x0 + frac * (x1 - x0))))
+                k += 1
+            acc += c
+        while len(cuts) < world - 1:
+            cuts.append(cuts[-1] + 1 if cuts else int(segs[-1][1]))
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1] + 1)
+        return cuts
+
+    @staticmethod
     def uniform_cuts(x_lo, x_hi, world, leaf, grid_size, inv_dx):
         """Equal-width slabs over [x_lo, x_hi), snapped to leaf-block boundaries."""
         half = grid_size // 2
@@ -509,22 +531,8 @@ def _make_distributed_solver():
                 dist.all_gather(allt, t, group=self.group)
             else:
                 allt = [t]
-            segs = [(float(a[1]), float(a[2]), float(a[0])) for a in allt if float(a[2]) > float(a[1]) and float(a[0]) > 0]
-            total = sum(c for _, _, c in segs)
-            if not segs or total <= 0:
-                return list(self.slab.cuts)
-            cuts, acc, k = [], 0.0, 1
-            for x0, x1, c in segs:
-                while k < self.world and acc + c >= total * k / self.world:
-                    frac = (total * k / self.world - acc) / c
-                    cuts.append(int(round(x0 + frac * (x1 - x0))))
-                    k += 1
-                acc += c
-            while len(cuts) < self.world - 1:
-                cuts.append(cuts[-1] + 1 if cuts else int(segs[-1][1]))
-            for i in range(1, len(cuts)):
-                cuts[i] = max(cuts[i], cuts[i - 1] + 1)
-            return cuts
+            segs = [(float(a[1]), float(a[2]), float(a[0])) for a in allt]
+            return SlabDecomposition.cost_balanced_cuts(segs, self.world, list(self.slab.cuts))
 
         def reserve_blocks(self, max_blocks):
             """Pre-size the leaf-block workspace (a capacity miss cannot be retried inside a distributed batch)."""

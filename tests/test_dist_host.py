@@ -78,3 +78,28 @@ def test_neighbour_exchange_gloo(world):
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world)) and len(out) == world
+
+
+def test_cost_balanced_cuts():
+    """DistributedMPMSolver.balance_cuts: the pure part.  Equal costs keep equal-width slabs; a rank that is twice as
+    expensive per column gives columns away; empty ranks are skipped; the cuts stay strictly increasing."""
+    from taichi_elements_b200.distributed import SlabDecomposition as S
+    # two ranks, same cost, same width: the cut stays in the middle
+    assert S.cost_balanced_cuts([(100, 120, 5.0), (120, 140, 5.0)], 2, [0]) == [120]
+    # rank 0 costs three times as much over the same width: half of the total cost is reached after 2/3 of its columns
+    assert S.cost_balanced_cuts([(100, 130, 3.0), (130, 160, 1.0)], 2, [0]) == [120]
+    # four ranks, everything on rank 1: it is split four ways
+    assert S.cost_balanced_cuts([(0, 0, 0.0), (200, 240, 8.0), (0, 0, 0.0), (0, 0, 0.0)], 4, [1, 2, 3]) == [210, 220, 230]
+    # nothing measured: the old cuts stay
+    assert S.cost_balanced_cuts([(0, 0, 0.0), (0, 0, 0.0)], 2, [77]) == [77]
+    # a one-column scene still yields strictly increasing cuts
+    c = S.cost_balanced_cuts([(50, 51, 1.0), (0, 0, 0.0), (0, 0, 0.0)], 3, [1, 2])
+    assert len(c) == 2 and c[0] < c[1]
+    # shares: cost left of every cut is k / world of the total (to the rounding of a column)
+    segs = [(0, 40, 10.0), (40, 100, 30.0), (100, 110, 20.0)]
+    cuts = S.cost_balanced_cuts(segs, 3, [0, 1])
+
+    def cost_left(x):
+        return sum(c * min(max((x - a) / (b - a), 0.0), 1.0) for a, b, c in segs)
+    for k, cut in enumerate(cuts, 1):
+        assert abs(cost_left(cut) - 60.0 * k / 3) <= 2.0
