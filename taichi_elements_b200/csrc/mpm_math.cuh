@@ -11,10 +11,8 @@
 
 #if defined(__CUDACC__)
 #define MPM_HD __host__ __device__ __forceinline__
-#define MPM_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define MPM_HD inline
-#define MPM_HD_NOINLINE inline
 #endif
 
 namespace mpm {
@@ -367,12 +365,12 @@ template <int D> MPM_HD void sand_projection(const Consts& K, float* sig, float&
 }
 
 // ---------------------------------------------------------------------------
-// The per-particle part of p2g (engine/mpm_solver.py:506-574), in three pieces so that the 3D P2G kernel can
-// run the particles that need the full SVD in a second, compacted pass (mpm_p2g3.cuh):
+// The per-particle part of p2g (engine/mpm_solver.py:506-574), in three pieces (a second, compacted pass over the
+// particles that need the full SVD was measured and dropped; the split keeps the fast cases readable):
 //   trial_F               F_trial = (I + dt C) F_in                                  (:507-513)
 //   particle_update_fast  every case that does NOT need the SVD; returns false otherwise
 //   particle_update_svd   the general path (ti.svd, plasticity, stress)           (:525-566)
-// particle_update() chains them (2D kernels, the first P2G variants, the host harness).
+// particle_update() chains them (every P2G kernel, the host harness).
 //   in : F (stored), C, Jp, material, dt
 //   out: F (new stored), Jp (new), affine = stress + mass*C, mass
 //
