@@ -15,7 +15,7 @@ LIB = os.path.join(_HERE, 'libmpm_oracle.so')
 
 class _Params(ctypes.Structure):
     _fields_ = [('dim', ctypes.c_int), ('res', ctypes.c_int * 3), ('grid_size', ctypes.c_int),
-                ('padding', ctypes.c_int), ('unused', ctypes.c_int), ('support_plasticity', ctypes.c_int)] + \
+                ('padding', ctypes.c_int), ('quant', ctypes.c_int), ('support_plasticity', ctypes.c_int)] + \
                [(k, ctypes.c_float) for k in ('dx', 'inv_dx', 'p_vol', 'p_mass', 'mu_0', 'lambda_0', 'alpha',
                                               'sand_coef', 'water_density', 'inv_dx2', 'four_inv_dx')] + \
                [('gravity', ctypes.c_float * 3)]
@@ -39,8 +39,7 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()                      # (re)compiles when the library is missing or older than its source
         _lib = ctypes.CDLL(LIB)
         _lib.oracle_num_threads.restype = ctypes.c_int
         _lib.oracle_substep.restype = ctypes.c_int
@@ -62,6 +61,7 @@ class COracle(OracleMPM):
         for d in range(3):
             p.res[d] = self.res[d] if d < self.dim else 1
         p.grid_size, p.padding, p.support_plasticity = self.grid_size, self.padding, int(self.support_plasticity)
+        p.quant = int(self._packed())          # split substep only (this class has no g2p2g mode)
         p.dx, p.inv_dx, p.p_vol, p.p_mass = self.dx, self.inv_dx, self.p_vol, self.p_mass
         p.mu_0, p.lambda_0, p.alpha = self.mu_0, self.lambda_0, self.alpha
         p.sand_coef = (self.dim * self.lambda_0 + 2 * self.mu_0) / (2 * self.mu_0)
@@ -87,6 +87,7 @@ class COracle(OracleMPM):
         return t
 
     def substep(self, dt, margin=8):
+        assert not self.use_g2p2g, 'the C restatement has the split substep only'
         lib = load()
         n = self.n_particles
         if n == 0:

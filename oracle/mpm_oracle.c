@@ -29,7 +29,7 @@
 typedef struct {
   int dim;
   int res[3];
-  int grid_size, padding, unbounded_unused, support_plasticity;
+  int grid_size, padding, quant, support_plasticity;   /* quant: bit-packed x / v / F storage (3D), see q_* below */
   float dx, inv_dx, p_vol, p_mass, mu_0, lambda_0, alpha, sand_coef, water_density, inv_dx2, four_inv_dx;
   float gravity[3];
 } oracle_params;
@@ -225,6 +225,38 @@ void oracle_particle_update(const oracle_params* P, float dt, int n, const int* 
   for (int i = 0; i < n; ++i) particle_update(P, P->dim, dt, mat[i], F + (size_t)DD * i, C + (size_t)DD * i, Jp + i, affine + (size_t)DD * i, mass + i);
 }
 
+/* Quantised particle storage (quant=True in 3D, engine/mpm_solver.py:106-114, 216-247): a store into x (3 x fixed 21 bit,
+ * max 2.0), v (3 x 19-bit fractions with one shared 7-bit exponent) or F (9 x fixed 16 bit, max F_bound + 0.1) rounds to the
+ * field's grid, and later loads see the rounded value.  Taichi's quantised types are not in the reference tree [EXT]; this
+ * restates their definitions (as oracle/quant_oracle.py does, which the CUDA codecs are tested against bit for bit). */
+static float q_fixed(float x, float max_value, int bits) {
+  const float inv = (float)(1 << (bits - 1)) / max_value, scale = max_value / (float)(1 << (bits - 1));
+  const float lim = (float)((1 << (bits - 1)) - 1);
+  float t = x * inv;
+  if (!(t > -lim)) t = -lim;            /* also NaN */
+  if (t > lim) t = lim;
+  const float r = truncf(t + (t < 0.0f ? -0.5f : 0.5f));   /* round half away from zero */
+  return fminf(fmaxf(r, -lim), lim) * scale;
+}
+static void q_shared_exp3(float* v) {
+  const float a = fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2])));
+  int e = -64;
+  if (a > 0.0f) {
+    int ex;
+    frexpf(a, &ex);                     /* a = f 2^ex, f in [0.5, 1): floor(log2 a) = ex - 1 */
+    e = ex - 1;
+    if (e < -64) e = -64;
+    if (e > 63) e = 63;
+  }
+  const float inv = ldexpf(1.0f, 17 - e), s = ldexpf(1.0f, e - 17), lim = (float)((1 << 18) - 1);
+  for (int d = 0; d < 3; ++d) {
+    float t = v[d] * inv;
+    t = fminf(fmaxf(t, -lim), lim);
+    const float r = truncf(t + (t < 0.0f ? -0.5f : 0.5f));
+    v[d] = fminf(fmaxf(r, -lim), lim) * s;
+  }
+}
+
 static inline void atomic_addf(float* p, float v) {
 #pragma omp atomic
   *p += v;
@@ -259,6 +291,8 @@ int oracle_substep(const oracle_params* P, float dt, int64_t n, float* x, float*
     }
     float aff[9], mass;
     particle_update(P, D, dt, mat[p], F + p * DD, C + p * DD, Jp + p, aff, &mass);
+    if (P->quant && D == 3)                                      /* self.F[p] = F rounds (:567); the stress used the unrounded F */
+      for (int i = 0; i < DD; ++i) F[p * DD + i] = q_fixed(F[p * DD + i], 4.1f, 16);
     if (bad) continue;
     const int K = D == 3 ? 27 : 9;
     for (int o = 0; o < K; ++o) {
@@ -362,7 +396,10 @@ int oracle_substep(const oracle_params* P, float dt, int64_t n, float* x, float*
       }
     }
     if (mat[p] != 4) {                                         /* :722-724 */
+      if (P->quant && D == 3) q_shared_exp3(nv);               /* self.v[p] = new_v rounds; the advection reads it back */
       for (int d = 0; d < D; ++d) { v[p * D + d] = nv[d]; x[p * D + d] += dt * nv[d]; }
+      if (P->quant && D == 3)
+        for (int d = 0; d < D; ++d) x[p * D + d] = q_fixed(x[p * D + d], 2.0f, 21);
       for (int i = 0; i < DD; ++i) C[p * DD + i] = nC[i];
     }
   }

@@ -198,3 +198,31 @@ def test_quantised_split_substep_rounds_at_the_stores():
     o2 = OracleMPM((32, ) * 2, quant=True)
     o2.add_particles(np.float32([[0.51234567, 0.5]]), MATERIAL_ELASTIC)
     assert o2.x[0, 0] == np.float32(0.51234567)
+
+
+def test_c_restatement_matches_numpy_oracle_with_quantised_storage():
+    """The two restatements round at the same stores (quant=True, split substep, 3D): after a substep they agree to one
+    step of each field's grid (a value within round-off of a rounding boundary may land one step apart), and both lie
+    exactly on the grids."""
+    from oracle import quant_oracle as q
+    from oracle.c_oracle import COracle
+    a, b = OracleMPM((32, ) * 3, quant=True), COracle((32, ) * 3, quant=True)
+    for o in (a, b):
+        o.add_surface_collider((0.5, 0.25, 0.5), (0.2, 1.0, 0.1), 2, 0.3)
+        for p, m, vel in mixed_scene(3, seed=3):
+            o.add_particles(p, m, velocity=vel)
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.F, b.F)
+    dt = a.default_dt
+    for it in range(4):
+        a.substep(dt)
+        b.substep(dt)
+        for o in (a, b):
+            assert np.array_equal(q.round_x(o.x), o.x) and np.array_equal(q.round_v(o.v), o.v)
+            assert np.array_equal(q.round_F(o.F), o.F)
+        if it == 0:
+            vmax = np.abs(a.v).max(axis=1, keepdims=True)
+            assert np.abs(b.x - a.x).max() <= 2.0 / 2**20 * 1.01                         # one step of the 21-bit grid
+            assert (np.abs(b.v - a.v) <= np.maximum(vmax, 1e-3) * 2.0**-17 + 2e-5).all()   # one step of the 19-bit fractions
+            assert np.abs(b.F - a.F).max() <= 4.1 / 2**15 * 1.01                         # one step of the 16-bit grid
+    vs = float(np.abs(a.v).max())
+    assert rel_err(b.x, a.x, 1.0) < 1e-4 and rel_err(b.v, a.v, vs) < 5e-3 and rel_err(b.F, a.F, 1.0) < 1e-3
