@@ -587,6 +587,8 @@ def main():
             'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': traffic['bytes_per_launch'] if traffic else None,
             'traffic_source': traffic['source'] if traffic else 'no ncu capture committed for this workload',
+            'traffic_note': 'includes 16 B per particle that P2G leaves at the sorted slot (x, tag) so that G2P streams them; '
+                            'G2P moves 8 B per particle less than before for it',
             'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_alg_p2g,
             'kernel_ms': {k: round(float(v), 4) for k, v in phases.items()}, 'dominant_phase': dom,
             'kernel_ms_note': 'CUDA events on the kernels\' stream, separate pass of K steps right after the timed ones '
