@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from scenes import mixed_scene
 from taichi_elements_b200.engine.mpm_solver import MPMSolver
-for dim, g2p2g, quant in ((3, False, False), (3, True, False), (3, True, True), (2, False, False), (2, True, False)):
+for dim, g2p2g, quant in ((3, False, False), (3, False, True), (3, True, False), (3, True, True), (2, False, False), (2, True, False)):
     s = MPMSolver((32, ) * dim, use_g2p2g=g2p2g, quant=quant)
     s.add_surface_collider((0.5, 0.2, 0.5)[:dim], (0, 1, 0)[:dim], 1, 0.3)
     for p, m, vel in mixed_scene(dim, n_per=300, seed=3):
